@@ -1,0 +1,12 @@
+"""acmil_b200 -- B200-native gated-attention MIL aggregation (drop-in for dazhangyu123/ACMIL's heads).
+
+Compute lives in ``lib/libacmil_b200.so`` (hand-written sm_100a CUDA behind the C-ABI of
+``include/acmil_b200.h``); this package is the host-side mirror of the reference's nn.Module interface.
+"""
+from . import _lib  # noqa: F401
+from .gated_pool import GatedPool, GatedPoolResult, GatedPoolSpec  # noqa: F401
+from .heads import (ABMIL, ACMIL_GA, Attention2, Attention_Gated, Attention_with_Classifier,  # noqa: F401
+                    AttentionGated, Classifier_1fc, DAttention, DimReduction)
+from .utils import Struct, set_seed  # noqa: F401
+
+__version__ = "0.1.0"

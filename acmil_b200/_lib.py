@@ -1,0 +1,106 @@
+"""ctypes binding of libacmil_b200.so (include/acmil_b200.h).
+
+The library is built in-tree by ``acmil_b200.build`` (nvcc, sm_100a).  There is no
+Python / CPU fallback: if the library cannot be loaded, or no CUDA device is present when a
+compute entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libacmil_b200.so")
+
+MAX_BRANCH, MAX_MASKED, MAX_SLIDES, MAX_CLASS = 8, 32, 64, 16
+ACT_TANH, ACT_RELU, ACT_GELU = 0, 1, 2
+IMPL_AUTO, IMPL_FFMA, IMPL_UMMA = 0, 1, 2
+ACT_IDS = {"tanh": ACT_TANH, "relu": ACT_RELU, "gelu": ACT_GELU}
+
+
+class AcmilError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"acmil_b200 error {code}: {msg}")
+        self.code = code
+
+
+class GpShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "d_in", "d_inner", "d_attn", "n_branch", "front", "front_bias", "front_act", "act_a",
+        "gated", "gate_bias", "score_bias", "reserved")]
+
+
+class GpWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_w1", "d_b1", "d_wv", "d_bv", "d_wu", "d_bu", "d_ww", "d_bw")]
+
+
+class GpBatch(C.Structure):
+    _fields_ = [("d_x", C.c_void_p), ("row_offsets", C.POINTER(C.c_int64)), ("n_slides", C.c_int32),
+                ("n_masked", C.c_int32), ("shard_row_begin", C.POINTER(C.c_int64)), ("d_a_out", C.c_void_p),
+                ("a_ld", C.c_int64)]
+
+
+class GpHeads(C.Structure):
+    _fields_ = [("n_class", C.c_int32), ("n_branch_heads", C.c_int32), ("d_wc", C.c_void_p), ("d_bc", C.c_void_p),
+                ("slide_head", C.c_int32), ("shared_head", C.c_int32), ("d_ws", C.c_void_p), ("d_bs", C.c_void_p)]
+
+
+class GpOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_sub", "d_slide", "d_afeat", "d_bag_feat", "d_lse_m", "d_lse_l", "d_topk_idx", "d_masked_idx")]
+
+
+# every symbol include/acmil_b200.h declares: (restype, argtypes)
+_SIZE_P = C.POINTER(C.c_size_t)
+SYMBOLS = {
+    "acmil_last_error": (C.c_char_p, []),
+    "acmil_abi_version": (C.c_int, []),
+    "acmil_device_count": (C.c_int, []),
+    "acmil_launch_count": (C.c_int64, []),
+    "acmil_gp_packed_bytes": (C.c_int, [C.POINTER(GpShape), _SIZE_P]),
+    "acmil_gp_pack": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_gp_sizes": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, _SIZE_P, _SIZE_P]),
+    "acmil_gp_partial": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpBatch), C.c_int, C.c_void_p,
+                                   C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_gp_finish": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_void_p, C.c_size_t, C.c_int,
+                                  C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(GpHeads),
+                                  C.POINTER(GpOutputs), C.c_void_p]),
+    "acmil_gp_attn_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "acmil_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building first if the .so is absent and nvcc is available) and returns the CDLL."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise ImportError(f"{LIB_PATH} is missing; run `python -m acmil_b200.build`")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.acmil_abi_version() != 1:
+            raise ImportError("libacmil_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AcmilError(rc, load().acmil_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    return int(load().acmil_launch_count())

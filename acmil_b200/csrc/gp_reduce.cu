@@ -1,0 +1,519 @@
+// Second half of the gated-attention pool: merge of per-CTA partials, top-n / mask selection,
+// normalisation, classifier heads; plus the small [K, N] ops (attention stats, row softmax).
+//
+//   gp_reduce_kernel : per (bag, branch, 32-feature chunk): picks this rank's top-n candidates,
+//                      adds every other candidate back into the sums (exact: nothing is ever
+//                      subtracted), LSE-merges the segment partials -> one rank record per bag.
+//   gp_finish_kernel : per bag: global top-n over the ranks' lists (= torch.topk order,
+//                      transformer.py:315), masked = top[rsel] (:316-317), masked scores count as
+//                      -1e9 in the softmax exactly like masked_fill (:320), afeat = softmax(A) h
+//                      (:323-324), classifier heads (:325-330), -1e9 written into a_out.
+#include "gp_common.cuh"
+
+namespace {
+
+constexpr int RT = 256;
+constexpr float MASK_FILL = -1e9f;
+
+struct GpReduceParams {
+  acmil_gp_shape sh;
+  const unsigned char* ws;
+  GpWorkspace wl;
+  GpSegTable seg;
+  GpRecord rec;
+  float* record;  // [S][stride]
+};
+
+// block-wide argmax of (score desc, idx asc); returns winner position (or -1) to every thread
+__device__ int block_argbest(float s, int i, int pos, float* r_s, int* r_i, int* r_p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+    const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+    if (p2 >= 0 && (pos < 0 || cand_better(s2, i2, s, i))) { s = s2; i = i2; pos = p2; }
+  }
+  __syncthreads();
+  if (lane == 0) { r_s[warp] = s; r_i[warp] = i; r_p[warp] = pos; }
+  __syncthreads();
+  float bs = r_s[0];
+  int bi = r_i[0], bp = r_p[0];
+  for (int w = 1; w < nw; ++w) {
+    if (r_p[w] >= 0 && (bp < 0 || cand_better(r_s[w], r_i[w], bs, bi))) { bs = r_s[w]; bi = r_i[w]; bp = r_p[w]; }
+  }
+  return bp;
+}
+
+__device__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < nw; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+__device__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < nw; ++w) r += red[w];  // fixed order: deterministic
+  return r;
+}
+
+__global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ float r_s[RT / 32];
+  __shared__ int r_i[RT / 32], r_p[RT / 32];
+  __shared__ float red[RT / 32];
+  __shared__ float wsum[RT / 32][32];
+  __shared__ int sel_pos[NMAX];
+
+  const int L = p.sh.d_inner, K = p.sh.n_branch;
+  const int FC = L / 32;
+  const int fc = blockIdx.x % FC, k = (blockIdx.x / FC) % K, s = blockIdx.x / (FC * K);
+  const int seg0 = p.seg.seg_begin[s], nseg = p.seg.seg_begin[s + 1] - seg0;
+  const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncand = nseg * nm;
+
+  float* c_score = reinterpret_cast<float*>(dsm);
+  int* c_idx = reinterpret_cast<int*>(c_score + ncand);
+  int* c_slot = c_idx + ncand;
+  int* c_sel = c_slot + ncand;
+
+  const float* part = reinterpret_cast<const float*>(p.ws + p.wl.part);
+  const int* g_cnt = reinterpret_cast<const int*>(p.ws + p.wl.cand_cnt);
+  const float* g_score = reinterpret_cast<const float*>(p.ws + p.wl.cand_score);
+  const int* g_idx = reinterpret_cast<const int*>(p.ws + p.wl.cand_idx);
+  const int* g_slot = reinterpret_cast<const int*>(p.ws + p.wl.cand_slot);
+  const float* g_h = reinterpret_cast<const float*>(p.ws + p.wl.cand_h);
+
+  // ---- 1. gather this (bag, branch)'s candidates ----
+  int my_valid = 0;
+  for (int c = tid; c < ncand; c += RT) {
+    const int sg = c / nm, i = c % nm;
+    const size_t g = ((size_t)(seg0 + sg) * K + k) * cap + i;
+    const bool live = i < g_cnt[(size_t)(seg0 + sg) * K + k];
+    c_score[c] = live ? g_score[g] : -INFINITY;
+    c_idx[c] = live ? g_idx[g] : 0x7fffffff;
+    c_slot[c] = live ? g_slot[g] : -1;
+    c_sel[c] = 0;
+    my_valid += live ? 1 : 0;
+  }
+  const int total = (int)(block_sum((float)my_valid, red) + 0.5f);
+  const int nsel = min(nm, total);
+
+  // ---- 2. this rank's top-nsel (sorted: score desc, index asc) ----
+  for (int round = 0; round < nsel; ++round) {
+    float bs = -INFINITY;
+    int bi = 0x7fffffff, bp = -1;
+    for (int c = tid; c < ncand; c += RT) {
+      if (c_slot[c] >= 0 && !c_sel[c] && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
+        bs = c_score[c]; bi = c_idx[c]; bp = c;
+      }
+    }
+    const int win = block_argbest(bs, bi, bp, r_s, r_i, r_p);
+    if (tid == 0) { sel_pos[round] = win; c_sel[win] = 1; }
+    __syncthreads();
+  }
+
+  // ---- 3. m*, l ----
+  float mx = -INFINITY;
+  for (int sg = tid; sg < nseg; sg += RT) mx = fmaxf(mx, part[((size_t)(seg0 + sg) * K + k) * (L + 2)]);
+  for (int c = tid; c < ncand; c += RT)
+    if (c_slot[c] >= 0 && !c_sel[c]) mx = fmaxf(mx, c_score[c]);
+  const float mstar = block_max(mx, red);
+  float ls = 0.f;
+  for (int sg = tid; sg < nseg; sg += RT) {
+    const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
+    if (pr[0] != -INFINITY) ls += expf(pr[0] - mstar) * pr[1];
+  }
+  for (int c = tid; c < ncand; c += RT)
+    if (c_slot[c] >= 0 && !c_sel[c]) ls += expf(c_score[c] - mstar);
+  const float lstar = block_sum(ls, red);
+
+  // ---- 4. acc for this 32-feature chunk ----
+  const int jf = fc * 32 + lane;
+  float a = 0.f;
+  for (int sg = warp; sg < nseg; sg += RT / 32) {
+    const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
+    const float m = pr[0];
+    if (m != -INFINITY) a = fmaf(expf(m - mstar), pr[2 + jf], a);
+  }
+  for (int c = warp; c < ncand; c += RT / 32) {
+    if (c_slot[c] >= 0 && !c_sel[c]) {
+      const int sg = c / nm;
+      a = fmaf(expf(c_score[c] - mstar), g_h[(((size_t)(seg0 + sg) * K + k) * cap + c_slot[c]) * L + jf], a);
+    }
+  }
+  wsum[warp][lane] = a;
+  __syncthreads();
+
+  float* rec = p.record + (size_t)s * p.rec.stride();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < RT / 32; ++w) t += wsum[w][lane];
+    rec[p.rec.acc() + (size_t)k * L + jf] = t;
+  }
+  // ---- 5. rank list ----
+  const int nmc = p.rec.nmc;
+  for (int i = warp; i < nmc; i += RT / 32) {
+    float hv = 0.f;
+    if (i < nsel) {
+      const int c = sel_pos[i];
+      const int sg = c / nm;
+      hv = g_h[(((size_t)(seg0 + sg) * K + k) * cap + c_slot[c]) * L + jf];
+    }
+    rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = hv;
+  }
+  if (fc == 0) {
+    if (tid == 0) {
+      rec[p.rec.m() + k] = mstar;
+      rec[p.rec.l() + k] = lstar;
+      reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
+    }
+    for (int i = tid; i < nmc; i += RT) {
+      float sc = -INFINITY;
+      int gi = 0x7fffffff;
+      if (i < nsel) {
+        sc = c_score[sel_pos[i]];
+        gi = c_idx[sel_pos[i]] + (int)p.seg.shard_begin[s];
+      }
+      rec[p.rec.score() + (size_t)k * nmc + i] = sc;
+      reinterpret_cast<int*>(rec)[p.rec.idx() + (size_t)k * nmc + i] = gi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ GpFinishParams p) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ float red[RT / 32];
+  __shared__ float s_m[KMAX], s_l[KMAX];
+  __shared__ int s_ntop[KMAX];
+
+  const int L = p.sh.d_inner, K = p.sh.n_branch, P = p.n_ranks, nmc = p.rec.nmc;
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t stride = p.rec.stride();
+  const int ne = P * nmc;  // candidate entries per branch (dense, holes = -inf)
+
+  float* af = reinterpret_cast<float*>(dsm);            // [K][L]
+  float* bag = af + (size_t)K * L;                      // [L]
+  float* e_score = bag + L;                             // [K][ne]
+  int* e_idx = reinterpret_cast<int*>(e_score + (size_t)K * ne);
+  int* e_flag = e_idx + (size_t)K * ne;                 // 0 dead, 1 live, 2 top (unmasked), 3 masked
+  int* top_pos = e_flag + (size_t)K * ne;               // [K][NMAX]
+
+  auto recp = [&](int r) { return p.records + ((size_t)r * p.n_slides + s) * stride; };
+
+  const int keep = p.keep[s];
+  // ---- 1. global top-n and the masked subset (one warp per branch) ----
+  for (int k = warp; k < K; k += RT / 32) {
+    int live = 0;
+    for (int e = lane; e < ne; e += 32) {
+      const int r = e / nmc, i = e % nmc;
+      const float* rc = recp(r);
+      const int cnt = reinterpret_cast<const int*>(rc)[p.rec.cnt() + k];
+      const bool ok = i < cnt;
+      e_score[k * ne + e] = ok ? rc[p.rec.score() + (size_t)k * nmc + i] : -INFINITY;
+      e_idx[k * ne + e] = ok ? reinterpret_cast<const int*>(rc)[p.rec.idx() + (size_t)k * nmc + i] : 0x7fffffff;
+      e_flag[k * ne + e] = ok ? 1 : 0;
+      live += ok ? 1 : 0;
+    }
+    live = (int)(warp_sum((float)live) + 0.5f);
+    const int ntop = min(p.n_masked, live);
+    __syncwarp();
+    for (int round = 0; round < ntop; ++round) {
+      float bs = -INFINITY;
+      int bi = 0x7fffffff, bp = -1;
+      for (int e = lane; e < ne; e += 32) {
+        if (e_flag[k * ne + e] == 1 && (bp < 0 || cand_better(e_score[k * ne + e], e_idx[k * ne + e], bs, bi))) {
+          bs = e_score[k * ne + e]; bi = e_idx[k * ne + e]; bp = e;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
+      }
+      if (lane == 0) {
+        top_pos[k * NMAX + round] = bp;
+        e_flag[k * ne + bp] = 2;
+        if (p.out.d_topk_idx) p.out.d_topk_idx[((size_t)s * K + k) * p.n_masked + round] = bi;
+      }
+      __syncwarp();
+    }
+    if (p.out.d_topk_idx)
+      for (int i = ntop + lane; i < p.n_masked; i += 32) p.out.d_topk_idx[((size_t)s * K + k) * p.n_masked + i] = -1;
+    if (lane == 0) s_ntop[k] = ntop;
+    __syncwarp();
+    for (int i = lane; i < keep; i += 32) {
+      const int64_t sel = p.rsel[((size_t)s * K + k) * p.keep_ld + i];
+      if (sel >= 0 && sel < ntop) {
+        const int pos = top_pos[k * NMAX + (int)sel];
+        e_flag[k * ne + pos] = 3;
+        const int gi = e_idx[k * ne + pos];
+        if (p.out.d_masked_idx) p.out.d_masked_idx[((size_t)s * K + k) * p.keep_ld + i] = gi;
+        const int64_t loc = (int64_t)gi - p.shard_begin[s];
+        if (p.a_out && loc >= 0 && loc < p.row_off[s + 1] - p.row_off[s])
+          p.a_out[(size_t)k * p.a_ld + p.row_off[s] + loc] = MASK_FILL;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. per branch: m*, l*, afeat ----
+  for (int k = 0; k < K; ++k) {
+    float mx = -INFINITY;
+    for (int r = tid; r < P; r += RT) mx = fmaxf(mx, recp(r)[p.rec.m() + k]);
+    for (int e = tid; e < ne; e += RT) {
+      const int f = e_flag[k * ne + e];
+      if (f == 1 || f == 2) mx = fmaxf(mx, e_score[k * ne + e]);
+      if (f == 3) mx = fmaxf(mx, MASK_FILL);
+    }
+    const float mstar = block_max(mx, red);
+    float ls = 0.f;
+    for (int r = tid; r < P; r += RT) {
+      const float* rc = recp(r);
+      if (rc[p.rec.m() + k] != -INFINITY) ls += expf(rc[p.rec.m() + k] - mstar) * rc[p.rec.l() + k];
+    }
+    for (int e = tid; e < ne; e += RT) {
+      const int f = e_flag[k * ne + e];
+      if (f == 1 || f == 2) ls += expf(e_score[k * ne + e] - mstar);
+      if (f == 3) ls += expf(MASK_FILL - mstar);
+    }
+    const float lstar = block_sum(ls, red);
+    if (tid == 0) { s_m[k] = mstar; s_l[k] = lstar; }
+    for (int jf = tid; jf < L; jf += RT) {
+      float a = 0.f;
+      for (int r = 0; r < P; ++r) {
+        const float* rc = recp(r);
+        const float m = rc[p.rec.m() + k];
+        if (m != -INFINITY) a = fmaf(expf(m - mstar), rc[p.rec.acc() + (size_t)k * L + jf], a);
+      }
+      for (int e = 0; e < ne; ++e) {
+        const int f = e_flag[k * ne + e];
+        if (f == 0) continue;
+        const float sc = f == 3 ? MASK_FILL : e_score[k * ne + e];
+        const float w = expf(sc - mstar);
+        if (w != 0.f) {
+          const int r = e / nmc, i = e % nmc;
+          a = fmaf(w, recp(r)[p.rec.h() + ((size_t)k * nmc + i) * L + jf], a);
+        }
+      }
+      const float v = a / lstar;
+      af[(size_t)k * L + jf] = v;
+      if (p.out.d_afeat) p.out.d_afeat[((size_t)s * K + k) * L + jf] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < K) {
+    if (p.out.d_lse_m) p.out.d_lse_m[(size_t)s * K + tid] = s_m[tid];
+    if (p.out.d_lse_l) p.out.d_lse_l[(size_t)s * K + tid] = s_l[tid];
+  }
+  // bag feature = mean over branches of afeat  (== mean_k softmax(A_k) @ h, transformer.py:328-329)
+  for (int jf = tid; jf < L; jf += RT) {
+    float t = 0.f;
+    for (int k = 0; k < K; ++k) t += af[(size_t)k * L + jf];
+    t /= (float)K;
+    bag[jf] = t;
+    if (p.out.d_bag_feat) p.out.d_bag_feat[(size_t)s * L + jf] = t;
+  }
+  __syncthreads();
+
+  // ---- 3. heads: one warp per output logit ----
+  const int C = p.heads.n_class;
+  if (p.out.d_sub && (p.heads.n_branch_heads > 0 || p.heads.shared_head)) {
+    for (int o = warp; o < K * C; o += RT / 32) {
+      const int k = o / C, c = o % C;
+      const float* w = p.heads.n_branch_heads > 0 ? p.heads.d_wc + ((size_t)k * C + c) * L : p.heads.d_ws + (size_t)c * L;
+      const float b = p.heads.n_branch_heads > 0 ? p.heads.d_bc[k * C + c] : p.heads.d_bs[c];
+      float t = 0.f;
+      for (int jf = lane; jf < L; jf += 32) t = fmaf(w[jf], af[(size_t)k * L + jf], t);
+      t = warp_sum(t);
+      if (lane == 0) p.out.d_sub[((size_t)s * K + k) * C + c] = t + b;
+    }
+  }
+  if (p.out.d_slide && p.heads.slide_head) {
+    for (int c = warp; c < C; c += RT / 32) {
+      float t = 0.f;
+      for (int jf = lane; jf < L; jf += 32) t = fmaf(p.heads.d_ws[(size_t)c * L + jf], bag[jf], t);
+      t = warp_sum(t);
+      if (lane == 0) p.out.d_slide[(size_t)s * C + c] = t + p.heads.d_bs[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention statistics of one bag: gram[i][j] = sum_n P_i P_j, ent[k] = sum_n P_k log P_k
+struct GpStatsParams {
+  const float* a;
+  int64_t a_ld;
+  int K, S;
+  int64_t row_off[SMAX + 1];
+  const float* m;
+  const float* l;
+  float* gram;
+  float* ent;
+  float* div;
+};
+
+__global__ void __launch_bounds__(512) gp_stats_kernel(const __grid_constant__ GpStatsParams p) {
+  __shared__ float red[16];
+  __shared__ float g_s[KMAX * KMAX];
+  const int s = blockIdx.x, K = p.K, tid = threadIdx.x;
+  const int64_t r0 = p.row_off[s], n = p.row_off[s + 1] - r0;
+  float mk[KMAX], il[KMAX], logl[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    mk[k] = k < K ? p.m[(size_t)s * K + k] : 0.f;
+    const float l = k < K ? p.l[(size_t)s * K + k] : 1.f;
+    il[k] = 1.f / l;
+    logl[k] = logf(l);
+  }
+  float g[KMAX * (KMAX + 1) / 2], en[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX * (KMAX + 1) / 2; ++i) g[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) en[k] = 0.f;
+  for (int64_t r = tid; r < n; r += blockDim.x) {
+    float pv[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      pv[k] = 0.f;
+      if (k < K) {
+        const float z = p.a[(size_t)k * p.a_ld + r0 + r] - mk[k];
+        pv[k] = expf(z) * il[k];
+        // p log p with p == 0 contributes 0 (torch: softmax * log_softmax = 0 * (-1e9) = -0)
+        en[k] += pv[k] * (z - logl[k]);
+      }
+    }
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+#pragma unroll
+      for (int j = i; j < KMAX; ++j) {
+        g[q] = fmaf(pv[i], pv[j], g[q]);
+        ++q;
+      }
+  }
+  int q = 0;
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i)
+#pragma unroll
+    for (int j = i; j < KMAX; ++j) {
+      const float t = block_sum(g[q++], red);
+      if (tid == 0 && i < K && j < K) {
+        g_s[i * KMAX + j] = t;
+        g_s[j * KMAX + i] = t;
+        if (p.gram) { p.gram[((size_t)s * K + i) * K + j] = t; p.gram[((size_t)s * K + j) * K + i] = t; }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const float t = block_sum(en[k], red);
+    if (tid == 0 && k < K && p.ent) p.ent[(size_t)s * K + k] = t;
+  }
+  if (tid == 0 && p.div) {
+    float d = 0.f;
+    for (int i = 0; i < K; ++i)
+      for (int j = i + 1; j < K; ++j)
+        d += g_s[i * KMAX + j] / (fmaxf(sqrtf(g_s[i * KMAX + i]), 1e-8f) * fmaxf(sqrtf(g_s[j * KMAX + j]), 1e-8f)) /
+             (float)(K * (K - 1) / 2);
+    p.div[s] = d;
+  }
+}
+
+__global__ void __launch_bounds__(512) softmax_rows_kernel(const float* __restrict__ a, int64_t a_ld, int64_t n,
+                                                           float* __restrict__ out, int64_t out_ld) {
+  __shared__ float red[16];
+  const float* row = a + (size_t)blockIdx.x * a_ld;
+  float* orow = out + (size_t)blockIdx.x * out_ld;
+  float mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, row[i]);
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) sm += expf(row[i] - mx);
+  sm = block_sum(sm, red);
+  const float inv = 1.f / sm;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) orow[i] = expf(row[i] - mx) * inv;
+}
+
+}  // namespace
+
+int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_record, cudaStream_t st) {
+  GpReduceParams p;
+  p.sh = mp.sh;
+  p.ws = mp.ws;
+  p.wl = mp.wl;
+  p.seg = mp.seg;
+  p.rec = rec;
+  p.record = d_record;
+  const int S = mp.seg.n_slides, K = mp.sh.n_branch, FC = mp.sh.d_inner / 32;
+  if (S == 0) return ACMIL_OK;
+  int max_cand = 0;
+  for (int s = 0; s < S; ++s) {
+    const int c = (mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]) * mp.seg.nm[s];
+    if (c > max_cand) max_cand = c;
+  }
+  const size_t smem = (size_t)max_cand * 16 + 16;
+  ACMIL_REQUIRE(smem <= 200 * 1024, ACMIL_E_INVALID, "reduce: too many candidates per bag (%d)", max_cand);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  gp_reduce_kernel<<<S * K * FC, RT, smem, st>>>(p);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+int gp_launch_finish(const GpFinishParams& p, cudaStream_t st) {
+  if (p.n_slides == 0) return ACMIL_OK;
+  const int K = p.sh.n_branch, L = p.sh.d_inner;
+  const size_t ne = (size_t)p.n_ranks * p.rec.nmc;
+  const size_t smem = ((size_t)K * L + L + 3 * K * ne + (size_t)K * NMAX) * 4 + 16;
+  ACMIL_REQUIRE(smem <= 200 * 1024, ACMIL_E_INVALID, "finish: n_ranks * n_masked too large (%zu entries)", ne);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  gp_finish_kernel<<<p.n_slides, RT, smem, st>>>(p);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+int gp_launch_stats(const float* d_a, int64_t a_ld, int K, const int64_t* row_offsets, int S, const float* d_m,
+                    const float* d_l, float* d_gram, float* d_ent, float* d_div, cudaStream_t st) {
+  if (S == 0) return ACMIL_OK;
+  GpStatsParams p;
+  p.a = d_a; p.a_ld = a_ld; p.K = K; p.S = S;
+  for (int s = 0; s <= S; ++s) p.row_off[s] = row_offsets[s];
+  p.m = d_m; p.l = d_l; p.gram = d_gram; p.ent = d_ent; p.div = d_div;
+  gp_stats_kernel<<<S, 512, 0, st>>>(p);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+int gp_launch_softmax_rows(const float* d_a, int64_t a_ld, int n_rows, int64_t n, float* d_out, int64_t out_ld,
+                           cudaStream_t st) {
+  if (n_rows == 0 || n == 0) return ACMIL_OK;
+  softmax_rows_kernel<<<n_rows, 512, 0, st>>>(d_a, a_ld, n, d_out, out_ld);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}

@@ -1,0 +1,183 @@
+/*
+ * acmil_b200 -- C-ABI of the B200-native gated-attention MIL pooling path.
+ *
+ * The reference (dazhangyu123/ACMIL) is pure Python: its "operator interface" for this
+ * path is the forward() of a handful of nn.Modules.  Each entry point below replaces the
+ * eager-op sequence of one of those forwards; the Python modules in acmil_b200/ keep the
+ * reference's constructor / forward signatures and parameter names and call these through
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ *   acmil_gp_pack      <- weights of  DimReduction.fc1            (architecture/network.py:37-57)
+ *                                     Attention_Gated.{V,U,weights} (architecture/transformer.py:239-267,
+ *                                                                  architecture/Attention.py:29-59,
+ *                                                                  architecture/attmil.py:45-98, 100-146)
+ *   acmil_gp_partial   <- ACMIL_GA.forward  lines 305-324  (architecture/transformer.py): dimreduction,
+ *                         gate, stochastic top-k candidate tracking, softmax-over-N partial sums, A_out
+ *   acmil_gp_finish    <- ACMIL_GA.forward  lines 311-330: top-k / random mask selection, softmax
+ *                         normalisation, A @ x, per-branch Classifier_1fc, bag feature, Slide_classifier;
+ *                         ABMIL.forward 277-286; Attention_with_Classifier.forward (Attention.py:67-71);
+ *                         attmil AttentionGated / DAttention forward (attmil.py:84-98, 128-146)
+ *   acmil_gp_attn_stats<- branch-diversity loss and attention entropy
+ *                         (Step3_WSI_classification_ACMIL.py:208-214, 259)
+ *   acmil_softmax_rows <- F.softmax(A, dim=1) of Attention_Gated(isNorm=True) (Attention.py:56-57)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ACMIL_E_* code otherwise; the message is
+ *     available from acmil_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *   - all pointers named d_* are DEVICE pointers into caller-owned memory (torch.empty); the
+ *     library never allocates, frees or retains caller memory.  `stream` is a cudaStream_t.
+ *   - a "batch" is S bags ("slides") whose rows are concatenated: x is [R_total, d_in] row-major
+ *     fp32 and row_offsets[S+1] (HOST array, int64) delimits the bags (like cu_seqlens).
+ *   - scores are written branch-major over the concatenation: a_out[k * a_ld + r].
+ *   - there is no CPU fallback: with no CUDA device every compute entry point fails with
+ *     ACMIL_E_CUDA.
+ */
+#ifndef ACMIL_B200_H
+#define ACMIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACMIL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ACMIL_API __attribute__((visibility("default")))
+#else
+#define ACMIL_API
+#endif
+
+enum {
+  ACMIL_OK = 0,
+  ACMIL_E_INVALID = -1,      /* bad argument / unsupported shape */
+  ACMIL_E_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+  ACMIL_E_WORKSPACE = -3,    /* caller buffer too small */
+  ACMIL_E_UNSUPPORTED = -4   /* requested implementation cannot run this shape */
+};
+
+enum { ACMIL_ACT_TANH = 0, ACMIL_ACT_RELU = 1, ACMIL_ACT_GELU = 2 };
+enum { ACMIL_IMPL_AUTO = 0, ACMIL_IMPL_FFMA = 1, ACMIL_IMPL_UMMA = 2 };
+
+#define ACMIL_MAX_BRANCH 8     /* n_token */
+#define ACMIL_MAX_MASKED 32    /* n_masked_patch */
+#define ACMIL_MAX_SLIDES 64    /* bags per launch */
+#define ACMIL_MAX_CLASS 16
+
+/* Static description of one gated-attention pooling head. */
+typedef struct acmil_gp_shape {
+  int32_t d_in;        /* width of the rows of x (D_feat; 1024 for attmil) */
+  int32_t d_inner;     /* L: width the pool runs over (D_inner; = d_in when front == 0) */
+  int32_t d_attn;      /* D: hidden width of the gate (128 everywhere in the reference) */
+  int32_t n_branch;    /* K = n_token */
+  int32_t front;       /* 0: pool x itself (Attention.py); 1: h = act(x W1^T [+ b1]) first */
+  int32_t front_bias;  /* DimReduction: 0; attmil feature layer: 1 */
+  int32_t front_act;   /* ACMIL_ACT_RELU | ACMIL_ACT_GELU */
+  int32_t act_a;       /* activation of the V branch: ACMIL_ACT_* */
+  int32_t gated;       /* 1: multiply by sigmoid(U branch); 0: Attention2 / DAttention */
+  int32_t gate_bias;   /* V/U Linear have a bias */
+  int32_t score_bias;  /* attention_weights Linear has a bias */
+  int32_t reserved;
+} acmil_gp_shape;
+
+/* Weights in the reference's own layout (nn.Linear: [out, in] row-major fp32, device). */
+typedef struct acmil_gp_weights {
+  const float* d_w1;   /* [d_inner, d_in]   or NULL when front == 0 */
+  const float* d_b1;   /* [d_inner]         or NULL */
+  const float* d_wv;   /* [d_attn, d_inner] */
+  const float* d_bv;   /* [d_attn]          or NULL */
+  const float* d_wu;   /* [d_attn, d_inner] or NULL when gated == 0 */
+  const float* d_bu;   /* [d_attn]          or NULL */
+  const float* d_ww;   /* [n_branch, d_attn] */
+  const float* d_bw;   /* [n_branch]        or NULL */
+} acmil_gp_weights;
+
+/* One batch of bags on one device (one rank's row shard of each bag when sharded). */
+typedef struct acmil_gp_batch {
+  const float* d_x;            /* [R_total, d_in] fp32 */
+  const int64_t* row_offsets;  /* HOST [n_slides + 1], row_offsets[0] == 0 */
+  int32_t n_slides;
+  int32_t n_masked;            /* n_masked_patch requested (0 = eval / no masking) */
+  /* global position of this shard inside each bag (sharded bags; NULL = shard is the bag) */
+  const int64_t* shard_row_begin;  /* HOST [n_slides] or NULL */
+  float* d_a_out;              /* [n_branch, a_ld] raw scores of the local rows (may be NULL) */
+  int64_t a_ld;                /* leading dimension of d_a_out (>= R_total) */
+} acmil_gp_batch;
+
+/* Classifier heads applied by acmil_gp_finish (Classifier_1fc: nn.Linear [C, L]). */
+typedef struct acmil_gp_heads {
+  int32_t n_class;
+  int32_t n_branch_heads;      /* K per-branch classifiers (ACMIL_GA) or 0 */
+  const float* d_wc;           /* [K, C, L] stacked classifier.{i}.fc.weight, or NULL */
+  const float* d_bc;           /* [K, C] */
+  int32_t slide_head;          /* 1: Slide_classifier on mean-branch feature (ACMIL_GA) */
+  int32_t shared_head;         /* 1: one classifier applied to every branch feature
+                                     (ABMIL / Attention_with_Classifier / attmil) via d_ws */
+  const float* d_ws;           /* [C, L] */
+  const float* d_bs;           /* [C] */
+} acmil_gp_heads;
+
+typedef struct acmil_gp_outputs {
+  float* d_sub;          /* [S, K, C]  per-branch logits (or NULL) */
+  float* d_slide;        /* [S, C]     slide logits      (or NULL) */
+  float* d_afeat;        /* [S, K, L]  softmax(A) @ h */
+  float* d_bag_feat;     /* [S, L]     mean over branches */
+  float* d_lse_m;        /* [S, K]     max score (after masking) */
+  float* d_lse_l;        /* [S, K]     sum exp(score - m) */
+  int64_t* d_topk_idx;   /* [S, K, n_masked]  torch.topk order (or NULL) */
+  int64_t* d_masked_idx; /* [S, K, keep]      indices set to -1e9 (or NULL) */
+} acmil_gp_outputs;
+
+ACMIL_API const char* acmil_last_error(void);
+ACMIL_API int acmil_abi_version(void);
+/* number of CUDA devices visible to the library (0 on a CPU-only box; never fails) */
+ACMIL_API int acmil_device_count(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+ACMIL_API int64_t acmil_launch_count(void);
+
+/* ---- weight packing ------------------------------------------------------------------ */
+ACMIL_API int acmil_gp_packed_bytes(const acmil_gp_shape* shape, size_t* bytes);
+ACMIL_API int acmil_gp_pack(const acmil_gp_shape* shape, const acmil_gp_weights* w,
+                  void* d_packed, size_t packed_bytes, void* stream);
+
+/* ---- pass over the rows -------------------------------------------------------------- */
+/* Sizes (bytes) of the scratch workspace and of the per-rank partial record that
+ * acmil_gp_partial fills.  The partial record is what sharded ranks all-gather. */
+ACMIL_API int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int impl,
+                   size_t* workspace_bytes, size_t* partial_bytes);
+
+/* Runs the fused row pass on this rank's rows: front projection, gate, raw scores -> d_a_out,
+ * running top-n candidates per branch (when n_masked > 0) kept out of the sums, online-softmax
+ * partial sums; then reduces the per-CTA partials into ONE record per bag in d_partial. */
+ACMIL_API int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_batch* batch,
+                     int impl, void* d_workspace, size_t workspace_bytes,
+                     void* d_partial, size_t partial_bytes, void* stream);
+
+/* Merges n_ranks partial records (d_partials = n_ranks records back to back, as produced by an
+ * all-gather; n_ranks == 1 for a single GPU), picks the global top-n per branch, masks
+ * d_rsel-selected ones (rsel[S, K, keep] = argsort(rand)[:, :keep] drawn by the caller with
+ * torch), normalises, applies the heads, and writes -1e9 into d_a_out at the masked positions
+ * that fall inside this rank's shard.
+ *   keep: number of masked patches per branch = int(min(n_masked, N) * mask_drop), per bag
+ *         (HOST array [S]); rsel row stride is keep_ld. */
+ACMIL_API int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch,
+                    const void* d_partials, size_t partial_bytes, int n_ranks,
+                    const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
+                    const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream);
+
+/* ---- small ops on the [K, N] score matrix --------------------------------------------- */
+/* Per bag: gram[K,K] = sum_n P_i P_j, ent[K] = sum_n P log P with P = softmax(A_out) given the
+ * (m, l) of acmil_gp_finish; div = mean pairwise cosine; all fp32. */
+ACMIL_API int acmil_gp_attn_stats(const float* d_a, int64_t a_ld, int32_t n_branch, const int64_t* row_offsets,
+                        int32_t n_slides, const float* d_lse_m, const float* d_lse_l,
+                        float* d_gram, float* d_ent, float* d_div, void* stream);
+/* out[k, n] = softmax over n of a[k, n] (one bag). */
+ACMIL_API int acmil_softmax_rows(const float* d_a, int64_t a_ld, int32_t n_rows, int64_t n, float* d_out,
+                       int64_t out_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACMIL_B200_H */

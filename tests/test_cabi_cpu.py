@@ -1,0 +1,114 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports exactly what include/acmil_b200.h declares,
+host-only entry points work without a GPU, compute entry points refuse loudly, and the drop-in modules keep
+the reference's parameter names / shapes / initialisation order."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_names, load_golden
+
+HEADER = os.path.join(ROOT, "include", "acmil_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"ACMIL_API\s+[\w\s\*]+?\b(acmil_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import acmil_b200._lib as L
+    lib = L.load()
+    decl = declared_symbols()
+    assert len(decl) >= 11
+    assert sorted(L.SYMBOLS) == decl, "ctypes table and header disagree"
+    nm = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (acmil_\w+)", nm))
+    assert set(decl) <= exported
+    assert lib.acmil_abi_version() == 1
+    assert lib.acmil_device_count() >= 0
+
+
+def test_struct_sizes_match_header_layout():
+    import acmil_b200._lib as L
+    assert C.sizeof(L.GpShape) == 48
+    assert C.sizeof(L.GpWeights) == 64
+    assert C.sizeof(L.GpBatch) == 48
+    assert C.sizeof(L.GpHeads) == 48
+    assert C.sizeof(L.GpOutputs) == 64
+
+
+def test_host_only_entry_points_and_validation():
+    import acmil_b200._lib as L
+    lib = L.load()
+    shape = L.GpShape(384, 128, 128, 5, 1, 0, 1, 0, 1, 1, 1, 0)
+    n = C.c_size_t(0)
+    assert lib.acmil_gp_packed_bytes(C.byref(shape), C.byref(n)) == 0
+    f32 = (384 * 128 + 128 + 2 * 128 * 128 + 2 * 128 + 8 * 128 + 8) * 4
+    assert n.value >= f32
+    off = (C.c_int64 * 3)(0, 50000, 50007)
+    batch = L.GpBatch(None, off, 2, 10, None, None, 50007)
+    ws, part = C.c_size_t(0), C.c_size_t(0)
+    assert lib.acmil_gp_sizes(C.byref(shape), C.byref(batch), L.IMPL_FFMA, C.byref(ws), C.byref(part)) == 0
+    stride = 2 * 5 + 5 * 128 + 5 + 2 * 5 * 10 + 5 * 10 * 128
+    assert part.value == 2 * stride * 4
+    assert ws.value > 0
+    # validation errors come back as codes + messages, never exceptions/aborts
+    bad = L.GpShape(384, 128, 128, 9, 1, 0, 1, 0, 1, 1, 1, 0)
+    assert lib.acmil_gp_packed_bytes(C.byref(bad), C.byref(n)) == -1
+    assert b"n_branch" in lib.acmil_last_error()
+    off_bad = (C.c_int64 * 3)(0, 10, 5)
+    batch_bad = L.GpBatch(None, off_bad, 2, 0, None, None, 10)
+    assert lib.acmil_gp_sizes(C.byref(shape), C.byref(batch_bad), 0, C.byref(ws), C.byref(part)) == -1
+    batch_bad = L.GpBatch(None, off, 2, 33, None, None, 50007)
+    assert lib.acmil_gp_sizes(C.byref(shape), C.byref(batch_bad), 0, C.byref(ws), C.byref(part)) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import acmil_b200._lib as L
+    from acmil_b200 import ACMIL_GA, Struct
+    lib = L.load()
+    assert lib.acmil_device_count() == 0
+    shape = L.GpShape(384, 128, 128, 5, 1, 0, 1, 0, 1, 1, 1, 0)
+    w = L.GpWeights(1, None, 1, None, 1, None, 1, None)
+    assert lib.acmil_gp_pack(C.byref(shape), C.byref(w), C.c_void_p(1), 1 << 30, None) == -2
+    assert b"no CUDA device" in lib.acmil_last_error()
+    m = ACMIL_GA(Struct(D_feat=384, D_inner=128, n_class=2, n_token=5), n_token=5).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 8, 384))
+
+
+@pytest.mark.parametrize("name", golden_names("acmil_ga_") + golden_names("abmil_"))
+def test_state_dict_layout_is_the_references(name):
+    """Fixtures hold state_dicts saved from the reference's own modules: names, shapes and order must load."""
+    from acmil_b200 import ABMIL, ACMIL_GA, Struct
+    w, g = load_golden(name)
+    d_feat, d_inner, n_class, k, n_masked = (int(v) for v in g["meta_conf"])
+    conf = Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class, n_token=k)
+    torch.manual_seed(int(g["meta_model_seed"]))
+    m = ACMIL_GA(conf, n_token=k, n_masked_patch=n_masked) if name.startswith("acmil") else ABMIL(conf)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(w.keys())
+    for key, v in sd.items():
+        # same construction order => same initial values under the same seed as the reference
+        assert np.array_equal(v.numpy(), w[key]), key
+
+
+def test_attention_py_and_attmil_parameter_names():
+    from acmil_b200.architecture import Attention as A
+    from acmil_b200.architecture.attmil import AttentionGated, DAttention
+    from test_oracle_golden import ATTMIL_AG_SHAPES, ATTMIL_DA_SHAPES
+    w, _ = load_golden("attention_py_k4_n640")
+    awc = A.Attention_with_Classifier(256, 128, 4, 3)
+    assert list(awc.state_dict().keys()) == [k[len("awc::"):] for k in w if k.startswith("awc::")]
+    for bias in (False, True):
+        sd = AttentionGated(act="gelu", bias=bias).state_dict()
+        assert {k: tuple(v.shape) for k, v in sd.items()} == ATTMIL_AG_SHAPES(bias)
+        assert list(sd.keys()) == list(ATTMIL_AG_SHAPES(bias).keys())
+    sd = DAttention(3, False, "relu").state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == ATTMIL_DA_SHAPES

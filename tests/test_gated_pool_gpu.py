@@ -1,0 +1,377 @@
+"""Parity of the CUDA path (through the C-ABI) against (1) golden vectors produced by the reference
+itself and (2) the numpy oracle on seeded inputs up to the BASELINE.json sizes.
+
+Tolerances (north_star: "slide logits and attention scores within 1e-3 fp32 rel-tol; top-k mask
+indices bit-exact under fixed seed"):
+  logits / pooled features : rtol 1e-3 (+ atol 1e-5)
+  raw attention scores      : rtol 1e-3 + atol 1e-5   (|A| ~ 0.1; atol guards the zero crossings)
+  mask / top-k indices      : exact
+The kernels are fp32-faithful (error-compensated), so the tests also assert a 20x tighter bound to
+catch regressions early; the official bound is the one above.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, golden_x, load_golden, np_seeded_state
+from oracle import gated_pool as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5
+TIGHT = dict(rtol=5e-5, atol=2e-6)
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def both(a, b):
+    close(a, b)
+    close(a, b, **TIGHT)
+
+
+def impls():
+    import acmil_b200._lib as L
+    return [L.IMPL_FFMA, L.IMPL_AUTO]
+
+
+def make_acmil(w, g, impl):
+    from acmil_b200 import ACMIL_GA, Struct
+    d_feat, d_inner, n_class, k, n_masked = (int(v) for v in g["meta_conf"])
+    conf = Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class, n_token=k)
+    m = ACMIL_GA(conf, n_token=k, n_masked_patch=n_masked, mask_drop=float(g["meta_mask_drop"]))
+    m.load_state_dict({k_: torch.from_numpy(v) for k_, v in w.items()})   # reference checkpoint layout
+    m._op.impl = impl
+    return m.cuda()
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("name", golden_names("acmil_ga_"))
+def test_acmil_ga_eval_golden(name, impl):
+    w, g = load_golden(name)
+    x = golden_x(g).cuda()
+    m = make_acmil(w, g, impl).eval()
+    with torch.no_grad():
+        sub, slide, a = m(x)
+        feat = m.forward_feature(x)
+    assert sub.shape == g["eval_sub"].shape and slide.shape == g["eval_slide"].shape and a.shape == g["eval_A"].shape
+    both(a, g["eval_A"])
+    both(sub, g["eval_sub"])
+    both(slide, g["eval_slide"])
+    both(feat, g["eval_feat"])
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("name", [n for n in golden_names("acmil_ga_") if n != "acmil_ga_k1_n1024"])
+def test_acmil_ga_train_mask_golden(name, impl):
+    """Mask indices must be bit-exact given the reference's own uniform draw (stored in the fixture)."""
+    w, g = load_golden(name)
+    x = golden_x(g).cuda()
+    m = make_acmil(w, g, impl).train()
+    k, n_masked = int(g["meta_conf"][3]), int(g["meta_conf"][4])
+    n = x.shape[1]
+    nm = min(n_masked, n)
+    keep = int(nm * float(g["meta_mask_drop"]))
+    rsel = torch.argsort(torch.from_numpy(g["train_rand"]), dim=-1)[:, :keep].cuda()
+    with torch.no_grad():
+        branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+        head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+        res, _ = m._pool(x[0], n_masked=n_masked if keep else 0, keep=keep, rsel=rsel if keep else None,
+                         branch=branch, head=head, slide_head=True)
+    a = res.scores.cpu().numpy()
+    if keep:
+        got = np.sort(res.masked_idx[0].cpu().numpy(), axis=-1)
+        assert np.array_equal(got, g["train_masked_sorted"]), "masked indices differ from the reference"
+        # torch.topk order of the raw scores
+        raw = g["eval_A"][0]
+        assert np.array_equal(res.topk_idx[0, :, :nm].cpu().numpy(), O.topk_indices(raw, nm))
+    assert np.array_equal(a == -1e9, g["train_A"][0] == -1e9)
+    both(a, g["train_A"][0])
+    both(res.sub[0], g["train_sub"])
+    both(res.slide, g["train_slide"])
+    both(res.bag_feat, g["train_feat"])
+
+
+def test_module_rng_stream_matches_reference_call_sequence():
+    """ACMIL_GA.forward in train mode must consume the generator exactly like transformer.py:316
+    (one torch.rand(K, nm, device=x.device)), so a seeded run masks what the reference would mask."""
+    w, g = load_golden("acmil_ga_k5_n1024")
+    x = golden_x(g).cuda()
+    m = make_acmil(w, g, 0).train()
+    with torch.no_grad():
+        m.eval()
+        _, _, raw = m(x)
+        m.train()
+        torch.manual_seed(123)
+        expect_rand = torch.rand(5, 10, device="cuda")
+        after_ref = torch.rand(3, device="cuda")
+        torch.manual_seed(123)
+        _, _, a = m(x)
+        after_mine = torch.rand(3, device="cuda")
+    assert torch.equal(after_ref, after_mine), "generator stream diverged"
+    top = torch.topk(raw[0], 10, dim=-1).indices
+    rsel = torch.argsort(expect_rand, dim=-1)[:, :6]
+    expect = torch.gather(top, 1, rsel)
+    got = (a[0] == -1e9).nonzero()[:, 1].reshape(5, 6)
+    assert torch.equal(got.sort(dim=-1).values, expect.sort(dim=-1).values)
+    # eval never masks
+    m.eval()
+    with torch.no_grad():
+        _, _, a2 = m(x)
+    assert not bool((a2 == -1e9).any())
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("name", golden_names("abmil_"))
+def test_abmil_golden(name, impl):
+    from acmil_b200 import ABMIL, Struct
+    w, g = load_golden(name)
+    d_feat, d_inner, n_class = (int(v) for v in g["meta_conf"][:3])
+    m = ABMIL(Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class, n_token=1))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    m._op.impl = impl
+    m = m.cuda().eval()
+    with torch.no_grad():
+        y = m(golden_x(g).cuda())
+    assert y.shape == g["eval_out"].shape
+    both(y, g["eval_out"])
+
+
+@pytest.mark.parametrize("name", golden_names("attention_py_"))
+def test_attention_py_golden(name):
+    from acmil_b200.architecture import Attention as A
+    from acmil_b200.architecture.transformer import Attention_Gated as TG
+    w, g = load_golden(name)
+    Lw, D, K, ncls = (int(v) for v in g["meta_conf"])
+    x = golden_x(g).cuda()
+
+    def sub(prefix):
+        return {k[len(prefix):]: torch.from_numpy(v) for k, v in w.items() if k.startswith(prefix)}
+
+    gate = A.Attention_Gated(Lw, D, K)
+    gate.load_state_dict(sub("gate::"))
+    gate = gate.cuda().eval()
+    awc = A.Attention_with_Classifier(Lw, D, K, ncls)
+    awc.load_state_dict(sub("awc::"))
+    awc = awc.cuda().eval()
+    tg = TG(Lw, D, K)
+    tg.load_state_dict(sub("tgate::"))
+    tg = tg.cuda().eval()
+    with torch.no_grad():
+        both(gate(x, isNorm=False), g["gate_raw"])
+        close(gate(x), g["gate_norm"], rtol=1e-3, atol=1e-9)
+        both(awc(x), g["awc_pred"])
+        both(tg(x), g["tgate_raw"])
+
+
+def test_attmil_golden():
+    from acmil_b200.architecture.attmil import AttentionGated, DAttention
+    from test_oracle_golden import ATTMIL_AG_SHAPES, ATTMIL_DA_SHAPES
+    _, g = load_golden("attmil_n600")
+    x = golden_x(g).cuda()
+    seed = int(g["meta_w_seed"])
+    for act in ("relu", "gelu", "tanh"):
+        for bias in (False, True):
+            m = AttentionGated(act=act, bias=bias)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in np_seeded_state(ATTMIL_AG_SHAPES(bias), seed).items()})
+            m = m.cuda().eval()
+            with torch.no_grad():
+                close(m(x), g[f"ag_{act}_{int(bias)}"], rtol=1e-3, atol=2e-5)
+    for act in ("relu", "gelu"):
+        m = DAttention(n_classes=3, dropout=False, act=act)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in np_seeded_state(ATTMIL_DA_SHAPES, seed + 1).items()})
+        m = m.cuda().eval()
+        with torch.no_grad():
+            y, a = m(x, return_attn=True)
+            _, a_ori = m(x, return_attn=True, no_norm=True)
+        close(y, g[f"da_{act}_y"], rtol=1e-3, atol=2e-5)
+        close(a, g[f"da_{act}_A"], rtol=1e-3, atol=1e-9)
+        close(a_ori, g[f"da_{act}_Aori"], rtol=1e-3, atol=2e-5)
+
+
+# ----------------------------------------------------------------------------- oracle at full size
+def _random_acmil(seed, d_feat=384, d_inner=128, k=5, n_class=2, n_masked=10, drop=0.6, scale_ww=1.0):
+    from acmil_b200 import ACMIL_GA, Struct
+    torch.manual_seed(seed)
+    m = ACMIL_GA(Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class, n_token=k), n_token=k,
+                 n_masked_patch=n_masked, mask_drop=drop)
+    with torch.no_grad():
+        m.attention.attention_weights.weight.mul_(scale_ww)
+    return m
+
+
+def _np_state(m):
+    return {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("n,scale_ww", [(50000, 1.0), (50000, 40.0), (12345, 8.0)])
+def test_full_size_vs_oracle(n, scale_ww, impl):
+    """BASELINE.json config 2 size (N=50k, D=384, K=5, mask 10/0.6).  scale_ww > 1 makes the attention
+    peaky (trained-model-like): the masked rows then carry most of the softmax mass, which is the case a
+    subtract-after-the-fact implementation would get wrong."""
+    m = _random_acmil(100 + n % 7, scale_ww=scale_ww)
+    m._op.impl = impl
+    p = _np_state(m)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(1, n, 384, generator=g)
+    rand = torch.rand(5, 10, generator=g)
+    ref32 = O.acmil_ga_forward(p, x.numpy(), training=True, n_masked_patch=10, mask_drop=0.6, rand=rand.numpy())
+    ref64 = O.acmil_ga_forward(p, x.numpy(), training=True, n_masked_patch=10, mask_drop=0.6, rand=rand.numpy(),
+                               dtype=np.float64)
+    rsel = torch.argsort(rand, dim=-1)[:, :6].cuda()
+    with torch.no_grad():
+        branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+        head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+        res, _ = m._pool(x[0].cuda(), n_masked=10, keep=6, rsel=rsel, branch=branch, head=head, slide_head=True)
+    got_mask = np.sort(res.masked_idx[0].cpu().numpy(), -1)
+    ref_mask = np.sort(ref32["masked_indices"], -1)
+    if not np.array_equal(got_mask, ref_mask):
+        # only acceptable if the fp32 reference itself disagrees with fp64 there (a rounding-noise tie)
+        assert not np.array_equal(ref_mask, np.sort(ref64["masked_indices"], -1)), "mask differs from a stable reference"
+        pytest.skip("fp32 tie in the reference ordering for this seed")
+    a = res.scores.cpu().numpy()
+    close(a, ref32["A_out"][0])
+    close(res.slide, ref32["slide"])
+    close(res.sub[0], ref32["sub"])
+    close(res.bag_feat, ref32["bag_feat"])
+    # versus fp64 truth we must be as good as the fp32 reference is
+    err_mine = np.abs(a - ref64["A_out"][0]).max()
+    err_ref = np.abs(ref32["A_out"][0] - ref64["A_out"][0]).max()
+    assert err_mine <= max(4 * err_ref, 2e-6), (err_mine, err_ref)
+
+
+@pytest.mark.parametrize("impl", impls())
+def test_ragged_batch_equals_single_bags(impl):
+    """Several bags of different sizes in one launch == each bag alone (and empty-tail tiles are inert)."""
+    m = _random_acmil(7).cuda().eval()
+    m._op.impl = impl
+    sizes = [1, 63, 64, 65, 127, 128, 129, 1000, 4097]
+    g = torch.Generator().manual_seed(5)
+    bags = [torch.randn(n, 384, generator=g).cuda() for n in sizes]
+    off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    w = m._weights()
+    op = m._op
+    packed = op.pack(w.get("w1"), None, w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
+    branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+    head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+    with torch.no_grad():
+        res = op.run(packed, torch.cat(bags), off, branch_w=branch[0], branch_b=branch[1], head_w=head[0],
+                     head_b=head[1], slide_head=True)
+        for i, b in enumerate(bags):
+            sub, slide, a = m(b[None])
+            close(res.sub[i], sub.cpu().numpy(), rtol=1e-5, atol=1e-6)
+            close(res.slide[i:i + 1], slide.cpu().numpy(), rtol=1e-5, atol=1e-6)
+            close(res.scores[:, off[i]:off[i + 1]], a[0].cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+def test_row_sharded_partials_merge(ranks, impl):
+    """Bag sharded by rows over `ranks` shards (here: sequentially on one GPU), records concatenated the way
+    all_gather_into_tensor would, finished once: must equal the unsharded result, masks included."""
+    m = _random_acmil(11, scale_ww=20.0).cuda().train()
+    m._op.impl = impl
+    n = 10007
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, 384, generator=g).cuda()
+    rsel = torch.argsort(torch.rand(5, 10, generator=g), dim=-1)[:, :6].cuda()
+    w = m._weights()
+    op = m._op
+    packed = op.pack(w.get("w1"), None, w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
+    branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+    head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+    kw = dict(keep=[6], rsel=rsel, branch_w=branch[0], branch_b=branch[1], head_w=head[0], head_b=head[1], slide_head=True)
+    with torch.no_grad():
+        full = op.run(packed, x, [0, n], n_masked=10, **kw)
+        bounds = [n * r // ranks for r in range(ranks + 1)]
+        bounds[1] = min(bounds[1], 3) if ranks == 8 else bounds[1]     # a shard smaller than n_masked
+        recs, ctxs = [], []
+        for r in range(ranks):
+            xs = x[bounds[r]:bounds[r + 1]].contiguous()
+            rec, ctx = op.partial(packed, xs, [0, xs.shape[0]], n_masked=10, shard_begin=[bounds[r]])
+            recs.append(rec)
+            ctxs.append(ctx)
+        gathered = torch.cat(recs)
+        outs = [op.finish(ctxs[r], gathered, ranks, **kw) for r in range(ranks)]
+    for r, o in enumerate(outs):
+        assert torch.equal(o.masked_idx.sort(-1).values, full.masked_idx.sort(-1).values)
+        assert torch.equal(o.topk_idx, full.topk_idx)
+        close(o.sub, full.sub.cpu().numpy(), rtol=2e-5, atol=1e-6)
+        close(o.slide, full.slide.cpu().numpy(), rtol=2e-5, atol=1e-6)
+        close(o.scores, full.scores[:, bounds[r]:bounds[r + 1]].cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_attn_stats_and_softmax_rows():
+    from acmil_b200 import GatedPool
+    w, g = load_golden("acmil_ga_k5_n1024")
+    x = golden_x(g).cuda()
+    m = make_acmil(w, g, 0).eval()
+    with torch.no_grad():
+        res, _ = m._pool(x[0])
+        gram, ent, div = GatedPool.attn_stats(res.scores, [0, 1024], res.lse_m, res.lse_l)
+        close(div, [float(g["eval_div"])], rtol=1e-3, atol=1e-7)
+        close(ent.sum() / 5, float(g["eval_ent"]), rtol=1e-3)
+        a = torch.from_numpy(g["train_A"][0]).cuda()       # with -1e9 entries
+        sm = GatedPool.softmax_rows(a)
+        close(sm, torch.softmax(a, dim=1).cpu().numpy(), rtol=1e-5, atol=1e-12)
+        lse = torch.logsumexp(a, dim=1)
+        mx = a.max(dim=1).values
+        _, _, div2 = GatedPool.attn_stats(a, [0, 1024], mx[None].contiguous(), torch.exp(lse - mx)[None].contiguous())
+        close(div2, [float(g["train_div"])], rtol=1e-3, atol=1e-7)
+
+
+def test_backward_matches_torch_autograd():
+    """Training: gradients of (sub CE + slide CE + diversity) w.r.t. every parameter equal those of the
+    same graph written with torch ops (the reference's op sequence) on the same device and mask."""
+    import torch.nn.functional as F
+    m = _random_acmil(21).cuda().train()
+    n = 3000
+    x = torch.randn(1, n, 384, generator=torch.Generator().manual_seed(4)).cuda()
+    y = torch.tensor([1], device="cuda")
+    torch.manual_seed(77)
+    sub, slide, a = m(x)
+    masked = (a[0] == -1e9)
+    assert int(masked.sum()) == 30
+
+    def losses(sub, slide, a):
+        p = torch.softmax(a, dim=-1)
+        d = sum(torch.cosine_similarity(p[:, i], p[:, j], dim=-1).mean() for i in range(5) for j in range(i + 1, 5)) / 10
+        return F.cross_entropy(sub, y.repeat_interleave(5)) + F.cross_entropy(slide, y) + d
+
+    losses(sub, slide, a).backward()
+    mine = {k: v.grad.clone() for k, v in m.named_parameters()}
+    m.zero_grad()
+    h = F.relu(F.linear(x[0], m.dimreduction.fc1.weight))
+    g = m.attention
+    s = F.linear(torch.tanh(g.attention_V[0](h)) * torch.sigmoid(g.attention_U[0](h)), g.attention_weights.weight,
+                 g.attention_weights.bias).t().masked_fill(masked, -1e9)
+    af = torch.softmax(s, 1) @ h
+    sub2 = torch.stack([c.fc(af[i]) for i, c in enumerate(m.classifier)])
+    slide2 = m.Slide_classifier.fc(torch.softmax(s, 1).mean(0, keepdim=True) @ h)
+    close(sub, sub2.detach().cpu().numpy(), rtol=1e-4, atol=1e-6)
+    losses(sub2, slide2, s[None]).backward()
+    for k, v in m.named_parameters():
+        close(mine[k], v.grad.cpu().numpy(), rtol=2e-3, atol=1e-6)
+
+
+def test_cabi_error_behaviour():
+    import ctypes as C
+    import acmil_b200._lib as L
+    lib = L.load()
+    shape = L.GpShape(384, 128, 64, 5, 1, 0, 1, 0, 1, 1, 1, 0)      # d_attn 64: unsupported
+    n = C.c_size_t(0)
+    assert lib.acmil_gp_packed_bytes(C.byref(shape), C.byref(n)) == -4
+    assert b"d_attn" in lib.acmil_last_error()
+    m = _random_acmil(3).cuda().eval()
+    with pytest.raises(ValueError):
+        m._op.run(torch.empty(16, dtype=torch.uint8, device="cuda"), torch.zeros(4, 100, device="cuda"), [0, 4])
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 384))      # CPU tensor: no CPU path
+    before = L.launch_count()
+    with torch.no_grad():
+        m(torch.zeros(1, 4, 384, device="cuda"))
+    assert L.launch_count() >= before + 3

@@ -147,3 +147,25 @@ def test_partials_merge_equals_softmax_pool():
     parts = [O.pool_partials(h[s:e], a[:, s:e]) for s, e in zip(cuts[:-1], cuts[1:])]
     got, _, _ = O.merge_partials(*zip(*parts))
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", golden_names("acmil_ga_"))
+def test_torch_port_matches_golden(name):
+    """oracle/torch_port.py (the CPU baseline bench.py times) against the reference's vectors."""
+    import torch
+    from oracle import torch_port as T
+    w, g = load_golden(name)
+    p = {k: torch.from_numpy(v) for k, v in w.items()}
+    x = golden_x(g)
+    with torch.no_grad():
+        sub, slide, a = T.acmil_ga_forward(p, x)
+    close(a.numpy(), g["eval_A"])
+    close(sub.numpy(), g["eval_sub"])
+    close(slide.numpy(), g["eval_slide"])
+    if "train_rand" in g and g["train_masked_sorted"].size:
+        n_masked = int(g["meta_conf"][4])
+        with torch.no_grad():
+            sub, slide, a = T.acmil_ga_forward(p, x, True, n_masked, float(g["meta_mask_drop"]),
+                                               torch.from_numpy(g["train_rand"]))
+        assert np.array_equal(a.numpy() == -1e9, g["train_A"] == -1e9)
+        close(slide.numpy(), g["train_slide"])
