@@ -58,6 +58,8 @@ SYMBOLS = {
     "acmil_abi_version": (C.c_int, []),
     "acmil_device_count": (C.c_int, []),
     "acmil_launch_count": (C.c_int64, []),
+    "acmil_prof_enable": (C.c_int, [C.c_int]),
+    "acmil_prof_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "acmil_gp_packed_bytes": (C.c_int, [C.POINTER(GpShape), _SIZE_P]),
     "acmil_gp_pack": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "acmil_gp_sizes": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, _SIZE_P, _SIZE_P]),

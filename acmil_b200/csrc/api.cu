@@ -1,6 +1,9 @@
 // C-ABI entry points (include/acmil_b200.h).  No torch types, no exceptions, caller-owned memory.
 #include <stdarg.h>
 
+#include <utility>
+#include <vector>
+
 #include "gp_common.cuh"
 
 int gp_launch_main_umma(const GpMainParams& p, cudaStream_t st);  // gp_umma.cu
@@ -18,6 +21,12 @@ void acmil_set_error(const char* fmt, ...) {
 }
 
 namespace {
+
+struct ProfState {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  size_t used = 0;
+} g_prof;
 
 int sm_count() {
   static int n = 0;
@@ -116,6 +125,26 @@ int acmil_device_count(void) {
 }
 int64_t acmil_launch_count(void) { return g_acmil_launches; }
 
+int acmil_prof_enable(int on) {
+  g_prof.on = on != 0;
+  if (!on) g_prof.used = 0;
+  return ACMIL_OK;
+}
+
+int acmil_prof_collect(double* main_ms_sum, int64_t* n_launches) {
+  double sum = 0.0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    ACMIL_CHECK_CUDA(cudaEventSynchronize(g_prof.pool[i].second));
+    float ms = 0.f;
+    ACMIL_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.pool[i].first, g_prof.pool[i].second));
+    sum += ms;
+  }
+  if (main_ms_sum) *main_ms_sum = sum;
+  if (n_launches) *n_launches = (int64_t)g_prof.used;
+  g_prof.used = 0;
+  return ACMIL_OK;
+}
+
 int acmil_gp_packed_bytes(const acmil_gp_shape* shape, size_t* bytes) {
   if (int rc = check_shape(shape)) return rc;
   ACMIL_REQUIRE(bytes != nullptr, ACMIL_E_INVALID, "bytes is NULL");
@@ -184,8 +213,21 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
   p.lay = gp_pack_layout(*shape);
   p.ws = reinterpret_cast<unsigned char*>(d_workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    if (g_prof.used == g_prof.pool.size()) {
+      ACMIL_CHECK_CUDA(cudaEventCreate(&e0));
+      ACMIL_CHECK_CUDA(cudaEventCreate(&e1));
+      g_prof.pool.emplace_back(e0, e1);
+    }
+    e0 = g_prof.pool[g_prof.used].first;
+    e1 = g_prof.pool[g_prof.used].second;
+    ++g_prof.used;
+    ACMIL_CHECK_CUDA(cudaEventRecord(e0, st));
+  }
   int rc = use == ACMIL_IMPL_UMMA ? gp_launch_main_umma(p, st) : gp_launch_main_ffma(p, st);
   if (rc) return rc;
+  if (e1) ACMIL_CHECK_CUDA(cudaEventRecord(e1, st));
   return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), st);
 }
 

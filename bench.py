@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the ACMIL gated-attention pool hot path (BASELINE.json metric: slides/sec, ACMIL ga,
+N=50k, D=384; HBM GB/s on the fused pool kernel).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU port of the reference
+                                                             # forward on the box's host cores
+
+One "step" = one pass of the hot path over one batch of `--slides` synthetic bags per GPU
+(config 2 of BASELINE.json: n_token=5, n_masked_patch=10, mask_drop=0.6, train-mode forward so that the
+stochastic top-k masking is inside the step).  At N GPUs every bag is row-sharded over the N ranks (each
+rank owns N_rows/N patches of each bag; the only exchange is the all-gather of the per-bag partial
+records) and a step processes N * slides bags, so per-GPU work is fixed: "scaling": "weak".
+
+Timing: W >= 3 warm-up steps, then K steps bracketed by barrier + cuda.synchronize, CUDA events on the
+launch stream, max over ranks.  Consecutive steps read different device-resident bag groups, each group
+(slides * 76.8 MB) larger than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, D_FEAT, D_INNER, K_BRANCH, N_CLASS, N_MASKED, MASK_DROP = 50000, 384, 128, 5, 2, 10, 0.6
+# x 76.8 MB + A_out 1.0 MB + params 0.337 MB per bag
+ALGO_BYTES_PER_SLIDE = N_ROWS * D_FEAT * 4 + K_BRANCH * N_ROWS * 4 + 84369 * 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slides", type=int, default=8, help="bags per step per GPU")
+    ap.add_argument("--groups", type=int, default=3, help="distinct device-resident bag groups rotated over steps")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "ffma", "umma"])
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_port_rate(n_rows, slides, warmup, mode):
+    """slides/sec of the CPU port of the reference forward (oracle/torch_port.py) on all host cores."""
+    from oracle import torch_port as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = T.random_state(D_FEAT, D_INNER, 128, K_BRANCH, N_CLASS, seed=0)
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(1, n_rows, D_FEAT, generator=g) for _ in range(2)]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + slides):
+            t0 = time.perf_counter()
+            T.acmil_ga_forward(p, xs[i % 2], mode == "train", N_MASKED, MASK_DROP)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, sec = cpu_port_rate(a.rows, a.steps, max(a.warmup, 1), a.mode)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "slides/sec (ACMIL ga, N=50k, D=384)", "value": rate, "unit": "slides/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, 1, cpu=True),
+        "cpu_baseline": {"value": rate, "unit": "slides/s", "cores": cores, "kind": "port",
+                         "sample": f"{a.steps} bags of {a.rows}x{D_FEAT} fp32, one bag per step, torch CPU ops in the "
+                                   f"reference's op order (oracle/torch_port.py)"},
+        "e2e": {"value": rate, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, world, cpu=False):
+    return {"workload": f"ACMIL ga n_token={K_BRANCH} n_masked_patch={N_MASKED} mask_drop={MASK_DROP} "
+                        f"D_feat={D_FEAT} D_inner={D_INNER}, synthetic N(0,1) fp32 bags of N={a.rows} rows "
+                        f"(BASELINE.json configs[1]), {a.mode}-mode forward",
+            "bags_per_step": 1 if cpu else a.slides * world, "rows_per_bag": a.rows,
+            "parallelism": "cpu" if cpu else (f"bag rows sharded over {world} GPUs" if world > 1 else "1 GPU"),
+            "l2_policy": "each step reads a different resident bag group; one group > 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch.distributed as dist
+    from acmil_b200 import ACMIL_GA, Struct, _lib
+    from acmil_b200.sharding import shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    impl = {"auto": _lib.IMPL_AUTO, "ffma": _lib.IMPL_FFMA, "umma": _lib.IMPL_UMMA}[a.kernel]
+
+    torch.manual_seed(0)
+    conf = Struct(D_feat=D_FEAT, D_inner=D_INNER, n_class=N_CLASS, n_token=K_BRANCH)
+    model = ACMIL_GA(conf, n_token=K_BRANCH, n_masked_patch=N_MASKED, mask_drop=MASK_DROP).to(dev)
+    model.train(a.mode == "train")
+    op = model._op
+    op.impl = impl
+    w = model._weights()
+    packed = op.pack(w.get("w1"), None, w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
+    branch_w = torch.stack([c.fc.weight for c in model.classifier]).detach()
+    branch_b = torch.stack([c.fc.bias for c in model.classifier]).detach()
+    head_w, head_b = model.Slide_classifier.fc.weight.detach(), model.Slide_classifier.fc.bias.detach()
+
+    S = a.slides * world                      # bags per step (each sharded over `world` ranks)
+    b = shard_bounds(a.rows, world)
+    n_loc = b[rank + 1] - b[rank]
+    offsets = [i * n_loc for i in range(S + 1)]
+    shard_begin = [b[rank]] * S
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    groups = [torch.randn(S * n_loc, D_FEAT, generator=gen, device=dev) for _ in range(a.groups)]
+    masking = a.mode == "train"
+    nm = min(N_MASKED, a.rows)
+    keep = int(nm * MASK_DROP)
+
+    def step(i):
+        rsel = None
+        if masking:
+            r = torch.rand(S, K_BRANCH, nm, device=dev)          # per bag: transformer.py:316
+            rsel = torch.argsort(r, dim=-1)[..., :keep].contiguous()
+            if world > 1:
+                dist.broadcast(rsel, src=0)
+        return op.run(packed, groups[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
+                      keep=[keep if masking else 0] * S, rsel=rsel, branch_w=branch_w, branch_b=branch_b,
+                      head_w=head_w, head_b=head_b, slide_head=True, shard_begin=shard_begin if world > 1 else None,
+                      group=dist.group.WORLD if world > 1 else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(a.warmup, 3)):
+            step(i)
+        barrier()
+        l0 = _lib.launch_count()
+        step(0)
+        torch.cuda.synchronize()
+        launches_per_step = _lib.launch_count() - l0
+
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        lib.acmil_prof_enable(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            res = step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        import ctypes as C
+        main_ms, n_main = C.c_double(0), C.c_int64(0)
+        lib.acmil_prof_collect(C.byref(main_ms), C.byref(n_main))
+        lib.acmil_prof_enable(0)
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        checksum = float(res.slide.sum().item())
+
+        # ---- end to end: pinned host bag -> H2D -> module forward (the call a user makes) -> logits D2H ----
+        e2e = None
+        if a.e2e_steps > 0:
+            host = [torch.randn(n_loc, D_FEAT).pin_memory() for _ in range(2)]
+            xdev = torch.empty(1, n_loc, D_FEAT, device=dev)
+            shard = None
+            if world > 1:
+                from acmil_b200.sharding import ShardedACMIL
+                shard = ShardedACMIL(model, dist.group.WORLD)
+
+            def user_call(i):
+                xdev[0].copy_(host[i % 2], non_blocking=True)
+                if shard is None:
+                    _, slide, _ = model(xdev)
+                else:
+                    _, slide, _ = shard(xdev, a.rows, b[rank])
+                return slide.cpu()
+
+            for i in range(2):
+                user_call(i)
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = a.e2e_steps * a.slides
+            for i in range(n_e2e):
+                out = user_call(i)
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            # at world > 1 one bag (sharded) per call; n_e2e bags in total
+            e2e = {"value": n_e2e / dt, "unit": "slides/s",
+                   "h2d_bytes_per_step": a.slides * n_loc * D_FEAT * 4 * world,
+                   "d2h_bytes_per_step": a.slides * N_CLASS * 4 * world,
+                   "api": "ACMIL_GA.forward(x[1,N,D]) per bag: pinned host -> device copy, fused kernels, logits .cpu()",
+                   "bags": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    slides_total = S * a.steps
+    value = slides_total / (ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    main_avg_ms = main_ms.value / max(n_main.value, 1)
+    algo_bytes = ALGO_BYTES_PER_SLIDE * (a.rows / N_ROWS) * a.slides        # per launch (this rank's share)
+    achieved = algo_bytes / (main_avg_ms * 1e-3) / 1e9 if main_avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "slides/sec (ACMIL ga, N=50k, D=384)", "value": value, "unit": "slides/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, world),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "row pass (gp_main_*)", "kernel_ms": main_avg_ms,
+                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
+        "kernel_impl": a.kernel, "checksum": checksum,
+    }
+    if not a.no_cpu_baseline:
+        rate, sec = cpu_port_rate(a.rows, 6, 2, a.mode)
+        line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"6 bags of {a.rows}x{D_FEAT} fp32 after 2 warm-ups (oracle/torch_port.py, "
+                                          f"torch CPU ops in the reference's op order)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (acmil_b200 has no CPU path); use --impl reference for the CPU arm")
+        run_ours(args)

@@ -137,6 +137,12 @@ ACMIL_API int acmil_device_count(void);
 /* kernels launched by this library in this process so far (bench.py's gpu_launches) */
 ACMIL_API int64_t acmil_launch_count(void);
 
+/* Profiling hook used by bench.py: while enabled, every acmil_gp_partial call brackets its row-pass
+ * ("main") kernel with CUDA events on the launch stream.  acmil_prof_collect synchronises them, adds
+ * up the elapsed milliseconds and resets the list. */
+ACMIL_API int acmil_prof_enable(int on);
+ACMIL_API int acmil_prof_collect(double* main_ms_sum, int64_t* n_launches);
+
 /* ---- weight packing ------------------------------------------------------------------ */
 ACMIL_API int acmil_gp_packed_bytes(const acmil_gp_shape* shape, size_t* bytes);
 ACMIL_API int acmil_gp_pack(const acmil_gp_shape* shape, const acmil_gp_weights* w,
