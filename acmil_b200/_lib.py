@@ -35,6 +35,12 @@ class GpWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_w1", "d_b1", "d_wv", "d_bv", "d_wu", "d_bu", "d_ww", "d_bw")]
 
 
+class GpConsts(C.Structure):
+    _fields_ = [("b1", C.c_float * 128), ("bv", C.c_float * 128), ("bu", C.c_float * 128),
+                ("ww", (C.c_float * 128) * 8), ("bw", C.c_float * 8), ("inv_scale", C.c_float * 4),
+                ("valid", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
 class GpBatch(C.Structure):
     _fields_ = [("d_x", C.c_void_p), ("row_offsets", C.POINTER(C.c_int64)), ("n_slides", C.c_int32),
                 ("n_masked", C.c_int32), ("shard_row_begin", C.POINTER(C.c_int64)), ("d_a_out", C.c_void_p),
@@ -61,10 +67,12 @@ SYMBOLS = {
     "acmil_prof_enable": (C.c_int, [C.c_int]),
     "acmil_prof_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "acmil_gp_packed_bytes": (C.c_int, [C.POINTER(GpShape), _SIZE_P]),
-    "acmil_gp_pack": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_gp_pack": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpWeights), C.c_void_p, C.c_size_t,
+                                C.POINTER(GpConsts), C.c_void_p]),
+    "acmil_gp_umma_supported": (C.c_int, [C.POINTER(GpShape)]),
     "acmil_gp_sizes": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, _SIZE_P, _SIZE_P]),
-    "acmil_gp_partial": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpBatch), C.c_int, C.c_void_p,
-                                   C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_gp_partial": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpConsts), C.POINTER(GpBatch), C.c_int,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "acmil_gp_finish": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_void_p, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(GpHeads),
                                   C.POINTER(GpOutputs), C.c_void_p]),

@@ -6,9 +6,12 @@
 
 #include "gp_common.cuh"
 
-int gp_launch_main_umma(const GpMainParams& p, cudaStream_t st);  // gp_umma.cu
+// gp_umma.cu
+int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, const unsigned char* d_umma, cudaStream_t st);
 int gp_umma_supported(const acmil_gp_shape& s);
-int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned char* d_umma, cudaStream_t st);
+int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned char* d_umma, acmil_gp_consts* consts,
+                 const float* d_f32, const GpPackLayout& lay, cudaStream_t st);
+int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t);
 
 static thread_local char g_err[512] = "";
 int64_t g_acmil_launches = 0;
@@ -71,9 +74,10 @@ int pick_impl(const acmil_gp_shape& s, int impl) {
 }
 
 int plan(const acmil_gp_shape& s, const acmil_gp_batch& b, int impl, GpSegTable* seg, GpWorkspace* wl) {
-  const int tile_rows = impl == ACMIL_IMPL_UMMA ? 128 : 64;
-  const int target = impl == ACMIL_IMPL_UMMA ? sm_count() : 4 * sm_count();
-  ACMIL_REQUIRE(gp_build_segments(b, tile_rows, target, seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
+  if (impl == ACMIL_IMPL_UMMA)
+    ACMIL_REQUIRE(gp_umma_build_plan(b, sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
+  else
+    ACMIL_REQUIRE(gp_build_segments(b, 64, 4 * sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
   *wl = gp_workspace_layout(s, seg->n_seg, seg->n_masked_cap);
   return ACMIL_OK;
 }
@@ -152,8 +156,10 @@ int acmil_gp_packed_bytes(const acmil_gp_shape* shape, size_t* bytes) {
   return ACMIL_OK;
 }
 
+int acmil_gp_umma_supported(const acmil_gp_shape* shape) { return shape != nullptr && gp_umma_supported(*shape); }
+
 int acmil_gp_pack(const acmil_gp_shape* shape, const acmil_gp_weights* w, void* d_packed, size_t packed_bytes,
-                  void* stream) {
+                  acmil_gp_consts* consts, void* stream) {
   if (int rc = check_shape(shape)) return rc;
   ACMIL_REQUIRE(w != nullptr && d_packed != nullptr, ACMIL_E_INVALID, "weights / d_packed is NULL");
   ACMIL_REQUIRE(w->d_wv != nullptr && w->d_ww != nullptr, ACMIL_E_INVALID, "d_wv and d_ww are required");
@@ -167,8 +173,11 @@ int acmil_gp_pack(const acmil_gp_shape* shape, const acmil_gp_weights* w, void* 
   gp_pack_f32_kernel<<<296, 256, 0, st>>>(*shape, *w, l, reinterpret_cast<float*>(d_packed));
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
+  if (consts) consts->valid = 0;
   if (gp_umma_supported(*shape)) {
-    if (int rc = gp_umma_pack(*shape, *w, reinterpret_cast<unsigned char*>(d_packed) + l.umma_off, st)) return rc;
+    if (int rc = gp_umma_pack(*shape, *w, reinterpret_cast<unsigned char*>(d_packed) + l.umma_off, consts,
+                              reinterpret_cast<const float*>(d_packed), l, st))
+      return rc;
   }
   return ACMIL_OK;
 }
@@ -180,13 +189,20 @@ int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int
   GpSegTable seg;
   GpWorkspace wl;
   if (int rc = plan(*shape, *batch, pick_impl(*shape, impl), &seg, &wl)) return rc;
-  if (workspace_bytes) *workspace_bytes = wl.total_bytes;
+  size_t ws = wl.total_bytes;
+  if (impl == ACMIL_IMPL_AUTO && pick_impl(*shape, impl) == ACMIL_IMPL_UMMA) {
+    // AUTO may still run the FFMA kernel (no host constants): size for whichever needs more
+    if (int rc = plan(*shape, *batch, ACMIL_IMPL_FFMA, &seg, &wl)) return rc;
+    if (wl.total_bytes > ws) ws = wl.total_bytes;
+  }
+  if (workspace_bytes) *workspace_bytes = ws;
   if (partial_bytes) *partial_bytes = gp_record(*shape, batch->n_masked).stride() * 4 * (size_t)batch->n_slides;
   return ACMIL_OK;
 }
 
-int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_batch* batch, int impl,
-                     void* d_workspace, size_t workspace_bytes, void* d_partial, size_t partial_bytes, void* stream) {
+int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                     const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes, void* d_partial,
+                     size_t partial_bytes, void* stream) {
   if (int rc = check_shape(shape)) return rc;
   if (int rc = check_batch(batch)) return rc;
   ACMIL_REQUIRE(d_packed && d_workspace && d_partial, ACMIL_E_INVALID, "NULL device buffer");
@@ -194,7 +210,9 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
   ACMIL_REQUIRE(batch->d_a_out == nullptr || batch->a_ld >= batch->row_offsets[batch->n_slides], ACMIL_E_INVALID,
                 "a_ld smaller than the number of rows");
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
-  const int use = pick_impl(*shape, impl);
+  int use = pick_impl(*shape, impl);
+  if (impl == ACMIL_IMPL_AUTO && use == ACMIL_IMPL_UMMA && !(consts && consts->valid == ACMIL_ABI_VERSION))
+    use = ACMIL_IMPL_FFMA;   // no host constants supplied: stay on the general kernel
   ACMIL_REQUIRE(use != ACMIL_IMPL_UMMA || gp_umma_supported(*shape), ACMIL_E_UNSUPPORTED,
                 "tcgen05 kernel does not support this shape");
   GpMainParams p;
@@ -225,7 +243,9 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
     ++g_prof.used;
     ACMIL_CHECK_CUDA(cudaEventRecord(e0, st));
   }
-  int rc = use == ACMIL_IMPL_UMMA ? gp_launch_main_umma(p, st) : gp_launch_main_ffma(p, st);
+  int rc = use == ACMIL_IMPL_UMMA
+               ? gp_launch_main_umma(p, consts, reinterpret_cast<const unsigned char*>(d_packed) + p.lay.umma_off, st)
+               : gp_launch_main_ffma(p, st);
   if (rc) return rc;
   if (e1) ACMIL_CHECK_CUDA(cudaEventRecord(e1, st));
   return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), st);

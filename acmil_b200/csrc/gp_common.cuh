@@ -67,8 +67,8 @@ static inline GpPackLayout gp_pack_layout(const acmil_gp_shape& s) {
   l.bw = o;  o += KMAX;
   l.f32_floats = o;
   l.umma_off = ((o * 4 + 1023) / 1024) * 1024;
-  // hi/lo fp16 images of W1 [L x d_in] and [Wv;Wu] [256 x L]
-  l.umma_bytes = (s.front ? (size_t)s.d_in * L * 4 : 0) + (size_t)2 * D * L * 4;
+  // [absmax, pad to 1024][per-CTA images: hi/lo fp16 of a W1 half (64 x d_in) and of Wv or Wu (128 x 128)]
+  l.umma_bytes = 1024 + 2 * ((size_t)((s.d_in + 63) / 64) * 8192 * 2 + 65536);
   l.total_bytes = l.umma_off + l.umma_bytes;
   return l;
 }
@@ -86,6 +86,13 @@ struct GpSegTable {
   int32_t seg_begin[SMAX + 1];   // segments of bag s: [seg_begin[s], seg_begin[s+1])
   int32_t tiles_per_seg[SMAX];
   int32_t nm[SMAX];              // candidates tracked per branch = min(n_masked, local rows)
+  // tcgen05 kernel only: bags are cut into 256-row pair-tiles, cluster c owns the global pair-tiles
+  // [c * u_total_pt / u_nclusters, (c + 1) * u_total_pt / u_nclusters); every (cluster, bag) it touches
+  // produces 8 segments (2 CTAs x 4 epilogue warps): seg_begin[s] + (c - u_cfirst[s]) * 8 + cta * 4 + warp
+  int32_t u_nclusters;
+  int32_t u_total_pt;
+  int32_t u_pt_begin[SMAX + 1];
+  int32_t u_cfirst[SMAX];
 };
 
 static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int target_seg, GpSegTable* t) {

@@ -72,6 +72,7 @@ class GatedPool:
         self._shape = spec.c_struct()
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._consts = L.GpConsts()       # host copy of the small vectors for the tcgen05 kernel
         self._bufs: dict = {}
 
     # ------------------------------------------------------------------ weights
@@ -92,7 +93,8 @@ class GatedPool:
         packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            L.check(lib.acmil_gp_pack(C.byref(self._shape), C.byref(w), _ptr(packed), nbytes.value, C.c_void_p(st)))
+            L.check(lib.acmil_gp_pack(C.byref(self._shape), C.byref(w), _ptr(packed), nbytes.value,
+                                      C.byref(self._consts), C.c_void_p(st)))
         self._packed, self._packed_key = packed, key
         self._keepalive = keep
         return packed
@@ -130,8 +132,9 @@ class GatedPool:
         part = torch.empty(max(part_b.value, 4) // 4, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), C.byref(batch), impl, _ptr(ws), ws.numel(),
-                                         _ptr(part), part.numel() * 4, st))
+            consts = C.byref(self._consts) if (packed is self._packed and self._consts.valid) else None
+            L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
+                                         ws.numel(), _ptr(part), part.numel() * 4, st))
         ctx = dict(batch=batch, keepalive=(off, sb, x), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
                    row_offsets=list(row_offsets))
         return part, ctx

@@ -94,6 +94,21 @@ typedef struct acmil_gp_weights {
   const float* d_bw;   /* [n_branch]        or NULL */
 } acmil_gp_weights;
 
+/* HOST-side copy of the small per-head vectors (biases, score weights) and of the power-of-two operand
+ * scales, filled by acmil_gp_pack.  The tcgen05 kernel receives them as kernel parameters (constant bank)
+ * so that the gate epilogue needs no loads for them.  The struct is caller-owned; the library keeps no
+ * copy.  Pass NULL to acmil_gp_pack / acmil_gp_partial to stay on the FFMA kernel. */
+typedef struct acmil_gp_consts {
+  float b1[128];
+  float bv[128];
+  float bu[128];
+  float ww[ACMIL_MAX_BRANCH][128];
+  float bw[ACMIL_MAX_BRANCH];
+  float inv_scale[4];   /* 1 / 2^e applied to the W1, Wv, Wu operand images; [3] unused */
+  int32_t valid;        /* set to ACMIL_ABI_VERSION by acmil_gp_pack when the tcgen05 images were built */
+  int32_t reserved[3];
+} acmil_gp_consts;
+
 /* One batch of bags on one device (one rank's row shard of each bag when sharded). */
 typedef struct acmil_gp_batch {
   const float* d_x;            /* [R_total, d_in] fp32 */
@@ -145,8 +160,10 @@ ACMIL_API int acmil_prof_collect(double* main_ms_sum, int64_t* n_launches);
 
 /* ---- weight packing ------------------------------------------------------------------ */
 ACMIL_API int acmil_gp_packed_bytes(const acmil_gp_shape* shape, size_t* bytes);
+/* Packs the weights into the kernels' layouts.  When `consts` is non-NULL and the shape is supported by
+ * the tcgen05 kernel it also fills *consts (one small device->host copy + stream synchronisation). */
 ACMIL_API int acmil_gp_pack(const acmil_gp_shape* shape, const acmil_gp_weights* w,
-                  void* d_packed, size_t packed_bytes, void* stream);
+                  void* d_packed, size_t packed_bytes, acmil_gp_consts* consts, void* stream);
 
 /* ---- pass over the rows -------------------------------------------------------------- */
 /* Sizes (bytes) of the scratch workspace and of the per-rank partial record that
@@ -157,9 +174,11 @@ ACMIL_API int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* 
 /* Runs the fused row pass on this rank's rows: front projection, gate, raw scores -> d_a_out,
  * running top-n candidates per branch (when n_masked > 0) kept out of the sums, online-softmax
  * partial sums; then reduces the per-CTA partials into ONE record per bag in d_partial. */
-ACMIL_API int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_batch* batch,
-                     int impl, void* d_workspace, size_t workspace_bytes,
+ACMIL_API int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                     const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes,
                      void* d_partial, size_t partial_bytes, void* stream);
+/* 1 when ACMIL_IMPL_AUTO would pick the tcgen05 kernel for this shape (given valid consts). */
+ACMIL_API int acmil_gp_umma_supported(const acmil_gp_shape* shape);
 
 /* Merges n_ranks partial records (d_partials = n_ranks records back to back, as produced by an
  * all-gather; n_ranks == 1 for a single GPU), picks the global top-n per branch, masks

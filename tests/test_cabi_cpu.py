@@ -40,6 +40,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.GpBatch) == 48
     assert C.sizeof(L.GpHeads) == 48
     assert C.sizeof(L.GpOutputs) == 64
+    assert C.sizeof(L.GpConsts) == (3 * 128 + 8 * 128 + 8 + 4) * 4 + 16
 
 
 def test_host_only_entry_points_and_validation():
@@ -76,7 +77,7 @@ def test_no_cpu_fallback():
     assert lib.acmil_device_count() == 0
     shape = L.GpShape(384, 128, 128, 5, 1, 0, 1, 0, 1, 1, 1, 0)
     w = L.GpWeights(1, None, 1, None, 1, None, 1, None)
-    assert lib.acmil_gp_pack(C.byref(shape), C.byref(w), C.c_void_p(1), 1 << 30, None) == -2
+    assert lib.acmil_gp_pack(C.byref(shape), C.byref(w), C.c_void_p(1), 1 << 30, None, None) == -2
     assert b"no CUDA device" in lib.acmil_last_error()
     m = ACMIL_GA(Struct(D_feat=384, D_inner=128, n_class=2, n_token=5), n_token=5).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
