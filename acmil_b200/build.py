@@ -27,6 +27,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags() -> list[str]:
+    extra = os.environ.get("ACMIL_NVCC_EXTRA", "").split()
+    return NVCC_FLAGS + extra
+
+
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -46,7 +51,7 @@ def _digest() -> str:
         h.update(f.encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -59,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
+        cmd = [_nvcc(), *_flags(), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:

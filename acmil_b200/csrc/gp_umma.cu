@@ -35,6 +35,22 @@ constexpr int STAGE_BYTES = 128 * KC * 4;
 constexpr uint32_t TM_D1 = 0, TM_D2 = 128, TM_HHI = 256, TM_HLO = 320, TM_X = 384;
 constexpr float LOG2E = 1.4426950408889634f;
 
+#ifndef GP_UMMA_PROF
+#define GP_UMMA_PROF 0
+#endif
+#if GP_UMMA_PROF
+__device__ long long g_umma_prof[148][32];
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(slot) prof[slot] += clock64() - _t0
+#define PROF_DECL() long long prof[16] = {0}
+#define PROF_FLUSH(base) do { for (int _i = 0; _i < 8; ++_i) g_umma_prof[blockIdx.x][(base) + _i] = prof[_i]; } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(slot) do {} while (0)
+#define PROF_DECL() do {} while (0)
+#define PROF_FLUSH(base) do {} while (0)
+#endif
+
 struct UmmaConsts {
   float b1[128], bv[128], bu[128], ww[KMAX][128], bw[KMAX];
   float inv_s1, inv_sv, inv_su;
@@ -51,8 +67,11 @@ struct UmmaParams {
 
 // smem carve-up (offsets from the 1024-aligned base)
 struct SmemMap {
-  uint32_t w1, wg, stage, tbuf, ps, bars, total;
+  uint32_t w1, wg, stage, tbuf, ps, cst, bars, total;
 };
+// per-unit record of gate constants in smem: {ww[0..KB-1], bv', bu'} padded to CREC floats, where
+// bv' = -2 log2e bv and bu' = -log2e bu are the biases in the exponent domain
+__host__ __device__ constexpr int cst_rec(int kb) { return kb <= 2 ? 4 : (kb <= 6 ? 8 : 10); }
 __host__ __device__ inline SmemMap smem_map(int din) {
   SmemMap m;
   m.w1 = 0;
@@ -60,7 +79,8 @@ __host__ __device__ inline SmemMap smem_map(int din) {
   m.stage = m.wg + 65536u;
   m.tbuf = m.stage + NSTAGE * STAGE_BYTES;
   m.ps = m.tbuf + 4 * 2048;
-  m.bars = m.ps + 4 * 1024;
+  m.cst = m.ps + 4 * 1024;
+  m.bars = m.cst + 128 * 10 * 4;
   m.total = m.bars + 256;
   return m;
 }
@@ -127,6 +147,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     for (uint32_t off = 0; off < p.cta_img_bytes; off += 16384) bulk_load(smem + off, src + off, 16384, &bars->wload);
     tma_prefetch_desc(&p.tmap);
   }
+  {
+    constexpr int CREC = cst_rec(KB);
+    float* cst = reinterpret_cast<float*>(smem + sm.cst);
+    for (int u = tid; u < 128; u += UT) {
+#pragma unroll
+      for (int k = 0; k < KB; ++k) cst[u * CREC + k] = p.c.ww[k][u];
+      cst[u * CREC + KB] = p.c.bv[u] * (-2.f * LOG2E);
+      cst[u * CREC + KB + 1] = p.c.bu[u] * (-LOG2E);
+    }
+  }
   if (warp == 2) {
     tmem_alloc<2>(&bars->tmem_base, 512);
     tmem_relinquish<2>();
@@ -144,14 +174,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     return t;
   };
 
-  const int wg = warp >> 2;
-  if (wg == 0) setmaxnreg_dec<64>();
-  else if (wg == 1) setmaxnreg_dec<112>();
-  else setmaxnreg_inc<240>();
-
+  // NOTE: each setmaxnreg sits at the top of a branch that never rejoins the others before the kernel's
+  // tail, otherwise ptxas allocates the whole kernel for the smallest budget.
+  if (warp < 4) {
+  setmaxnreg_dec<64>();
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      PROF_DECL();
       int s_hint = 0;
       uint32_t ctr = 0;
       for (int g = g0; g < g1; ++g) {
@@ -159,17 +189,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         const int64_t grow = seg.row_off[tp.s] + tp.row_in_bag;
         for (int c = 0; c < NCH; ++c, ++ctr) {
           const uint32_t st = ctr % NSTAGE, ph = (ctr / NSTAGE) & 1u;
-          mbar_wait(&bars->empty_x[st], ph ^ 1u);
+          { PROF_T0(); mbar_wait(&bars->empty_x[st], ph ^ 1u); PROF_ADD(0); }
           mbar_expect_tx(&bars->full_x[st], STAGE_BYTES);
           tma_load_2d_hint(smem + sm.stage + st * STAGE_BYTES, &p.tmap, c * KC, (int)grow, &bars->full_x[st], kEvictFirst);
         }
       }
+      PROF_FLUSH(0);
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA) =====================================
     if (cta == 0 && lane == 0 && T > 0) {
-      mbar_wait_cluster(&bars->w_ready, 0);   // both CTAs' weight images have landed
+      PROF_DECL();
+      const long long t_start = clock64();
+      { PROF_T0(); mbar_wait_cluster(&bars->w_ready, 0); PROF_ADD(0); }  // both CTAs' weight images have landed
       const uint32_t idesc = umma_idesc_f16(256, 128);
       const uint32_t w1_hi = smem_u32(smem + sm.w1), w1_lo = w1_hi + p.w1_part_bytes;
       const uint32_t wg_hi = smem_u32(smem + sm.wg), wg_lo = wg_hi + 32768u;
@@ -177,11 +210,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       auto g1_chunks = [&](int t, int c_begin, int c_end) {
         for (int c = c_begin; c < c_end; ++c, ++xc) {
           if (c == 0 && t > 0) {  // D1 of the previous tile must have been drained by the epilogue
-            mbar_wait_cluster(&bars->d1_empty, (uint32_t)(t - 1) & 1u);
+            { PROF_T0(); mbar_wait_cluster(&bars->d1_empty, (uint32_t)(t - 1) & 1u); PROF_ADD(1); }
             tc_fence_after();
           }
           const uint32_t q = xc % NXOP, ph = (xc / NXOP) & 1u;
-          mbar_wait_cluster(&bars->xop_full[q], ph);
+          { PROF_T0(); mbar_wait_cluster(&bars->xop_full[q], ph); PROF_ADD(2); }
           tc_fence_after();
           const uint32_t xa_hi = tm + TM_X + q * 32, xa_lo = xa_hi + 16;
           const uint32_t boff = (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 64u;
@@ -197,9 +230,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         }
       };
       auto g2_half = [&](int t, int h) {
-        if (h == 0) mbar_wait_cluster(&bars->hop_full, (uint32_t)t & 1u);
+        if (h == 0) { PROF_T0(); mbar_wait_cluster(&bars->hop_full, (uint32_t)t & 1u); PROF_ADD(3); }
         const uint32_t u = 2u * (uint32_t)t + (uint32_t)h;
-        if (u > 0) mbar_wait_cluster(&bars->d2_empty, (u - 1u) & 1u);
+        if (u > 0) { PROF_T0(); mbar_wait_cluster(&bars->d2_empty, (u - 1u) & 1u); PROF_ADD(4); }
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -214,10 +247,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       g1_chunks(0, 0, NCH);
       for (int t = 0; t < T; ++t) {
         g2_half(t, 0);
-        if (t + 1 < T) g1_chunks(t + 1, 0, NCH / 2);
         g2_half(t, 1);
-        if (t + 1 < T) g1_chunks(t + 1, NCH / 2, NCH);
+        if (t + 1 < T) g1_chunks(t + 1, 0, NCH);
       }
+#if GP_UMMA_PROF
+      prof[7] = clock64() - t_start;
+#endif
+      PROF_FLUSH(8);
     }
     __syncwarp();
   } else if (warp == 3) {
@@ -227,17 +263,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       mbar_arrive_cluster(&bars->w_ready, 0);
     }
     __syncwarp();
-  } else if (warp == 2) {
+  }
   } else if (warp < 8) {
     // ===================================== converters: fp32 staging -> fp16 hi/lo in TMEM =====================================
+    setmaxnreg_dec<112>();
     const int r = (warp - 4) * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
     uint32_t ctr = 0;
+    PROF_DECL();
+#if GP_UMMA_PROF
+    const long long t_start = clock64();
+#endif
     for (int t = 0; t < T; ++t) {
       for (int c = 0; c < NCH; ++c, ++ctr) {
         const uint32_t st = ctr % NSTAGE, ph = (ctr / NSTAGE) & 1u;
         const uint32_t q = ctr % NXOP, phq = (ctr / NXOP) & 1u;
-        mbar_wait(&bars->full_x[st], ph);
+        { PROF_T0(); mbar_wait(&bars->full_x[st], ph); PROF_ADD(0); }
         const uint8_t* rowp = smem + sm.stage + st * STAGE_BYTES + r * 128;
         float4 v[8];
 #pragma unroll
@@ -250,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->empty_x[st]);   // staging slot may be refilled
-        mbar_wait_cluster(&bars->xop_empty[q], phq ^ 1u);
+        { PROF_T0(); mbar_wait_cluster(&bars->xop_empty[q], phq ^ 1u); PROF_ADD(1); }
         tc_fence_after();
         tmem_st16(tm + lane_addr + TM_X + q * 32, hi);
         tmem_st16(tm + lane_addr + TM_X + q * 32 + 16, lo);
@@ -260,8 +301,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         if (lane == 0) mbar_arrive_cluster(&bars->xop_full[q], 0);
       }
     }
+#if GP_UMMA_PROF
+    prof[7] = clock64() - t_start;
+    if (warp == 4 && lane == 0) PROF_FLUSH(16);
+#endif
   } else {
     // ===================================== epilogue: thread = row =====================================
+    setmaxnreg_inc<240>();
     const int ew = warp - 8;
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     float* tbuf = reinterpret_cast<float*>(smem + sm.tbuf + ew * 2048);   // [32 rows][16 feats], chunk-swizzled
@@ -333,6 +379,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       }
     };
 
+    PROF_DECL();
+#if GP_UMMA_PROF
+    const long long t_start = clock64();
+#endif
     for (int t = 0; t < T; ++t) {
       const TilePos tp = tile_pos(g0 + t, s_hint);
       if (tp.s != s_cur) {
@@ -343,8 +393,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       const bool valid = row_in_bag < n_rows;
 
       // ---------------- Epi1: D1 -> relu -> fp16 hi/lo operand of the gate GEMM ----------------
-      mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u);
+      { PROF_T0(); mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u); PROF_ADD(0); }
       tc_fence_after();
+#if GP_UMMA_PROF
+      const long long t_e1 = clock64();
+#endif
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint32_t v[32];
@@ -368,13 +421,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         mbar_arrive_cluster(&bars->d1_empty, 0);
       }
 
+#if GP_UMMA_PROF
+      prof[2] += clock64() - t_e1;
+      const long long t_e2 = clock64();
+#endif
       // ---------------- Epi2: gate + scores ----------------
       float sc_[KB];
 #pragma unroll
       for (int k = 0; k < KB; ++k) sc_[k] = p.c.bw[k];
+      const float* cstp = reinterpret_cast<const float*>(smem + sm.cst);
+      const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        mbar_wait_cluster(&bars->d2_full, (uint32_t)(2 * t + h) & 1u);
+        { PROF_T0(); mbar_wait_cluster(&bars->d2_full, (uint32_t)(2 * t + h) & 1u); PROF_ADD(1); }
         tc_fence_after();
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -390,18 +449,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int u = h * 64 + sub * 32 + i;
-            const float a = fmaf(__uint_as_float(zv[i]), p.c.inv_sv, p.c.bv[u]);
-            const float b = fmaf(__uint_as_float(zu[i]), p.c.inv_su, p.c.bu[u]);
-            // tanh(a) * sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)),  Ea = e^-2a, Eb = e^-b  (exponents clamped at 40)
-            const float ea = ex2_approx(fminf(a * (-2.f * LOG2E), 57.7f));
-            const float eb = ex2_approx(fminf(b * (-LOG2E), 57.7f));
+            constexpr int CREC = cst_rec(KB);
+            float cr[CREC];
+            if constexpr (CREC == 10) {
+#pragma unroll
+              for (int j = 0; j < 5; ++j) *reinterpret_cast<float2*>(&cr[2 * j]) = *reinterpret_cast<const float2*>(cstp + u * CREC + 2 * j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CREC / 4; ++j) *reinterpret_cast<float4*>(&cr[4 * j]) = *reinterpret_cast<const float4*>(cstp + u * CREC + 4 * j);
+            }
+            // tanh(a) * sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)),  Ea = e^-2a, Eb = e^-b  (exponents clamped at 40);
+            // scales and biases are pre-multiplied into the exponent domain
+            const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[i]), cva, cr[KB]), 57.7f));
+            const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[i]), cua, cr[KB + 1]), 57.7f));
             const float gte = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
 #pragma unroll
-            for (int k = 0; k < KB; ++k) sc_[k] = fmaf(gte, p.c.ww[k][u], sc_[k]);
+            for (int k = 0; k < KB; ++k) sc_[k] = fmaf(gte, cr[k], sc_[k]);
           }
         }
       }
 
+#if GP_UMMA_PROF
+      prof[3] += clock64() - t_e2;
+      const long long t_e3 = clock64();
+#endif
       // ---------------- raw scores out ----------------
       if (p.mp.a_out != nullptr && valid) {
 #pragma unroll
@@ -510,6 +581,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       }
       __syncwarp();
 
+#if GP_UMMA_PROF
+      prof[4] += clock64() - t_e3;
+      const long long t_e4 = clock64();
+#endif
       // entries that fell out of a list this tile rejoin the sums; their h rows were parked in scratch by
       // an earlier tile and must be read BEFORE this tile's new entries reuse the freed slots
       float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)seg_id * K * cap * L;
@@ -577,8 +652,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         }
         __syncwarp();
       }
+#if GP_UMMA_PROF
+      prof[5] += clock64() - t_e4;
+#endif
     }
     flush_stream();
+#if GP_UMMA_PROF
+    prof[7] = clock64() - t_start;
+    if (warp == 8 && lane == 0) PROF_FLUSH(24);
+#endif
   }
 
   // ---- teardown ----
@@ -675,6 +757,12 @@ int launch_kb(const UmmaParams& up, int grid, size_t smem, cudaStream_t st) {
 }
 
 }  // namespace
+
+#if GP_UMMA_PROF
+extern "C" __attribute__((visibility("default"))) int acmil_debug_umma_prof(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_umma_prof, sizeof(long long) * n);
+}
+#endif
 
 int gp_umma_supported(const acmil_gp_shape& s) {
   return s.front == 1 && s.front_act == ACMIL_ACT_RELU && s.act_a == ACMIL_ACT_TANH && s.gated == 1 && s.d_inner == 128 &&
