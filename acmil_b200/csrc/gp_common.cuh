@@ -12,7 +12,7 @@
 #define NMAX ACMIL_MAX_MASKED
 #define SMAX ACMIL_MAX_SLIDES
 #define GP_DATTN 128            // gate hidden width supported by the kernels
-#define GP_MAX_SEG_CAND 8192    // nseg(slide) * n_masked bound for the reduce kernel's smem
+#define GP_MAX_SEG_CAND 12288   // nseg(slide) * n_masked bound for the reduce kernel's smem
 
 // ----------------------------------------------------------------------------- errors
 void acmil_set_error(const char* fmt, ...);
@@ -88,7 +88,7 @@ struct GpSegTable {
   int32_t nm[SMAX];              // candidates tracked per branch = min(n_masked, local rows)
   // tcgen05 kernel only: bags are cut into 256-row pair-tiles, cluster c owns the global pair-tiles
   // [c * u_total_pt / u_nclusters, (c + 1) * u_total_pt / u_nclusters); every (cluster, bag) it touches
-  // produces 8 segments (2 CTAs x 4 epilogue warps): seg_begin[s] + (c - u_cfirst[s]) * 8 + cta * 4 + warp
+  // produces 16 segments (2 CTAs x 8 epilogue warps): seg_begin[s] + (c - u_cfirst[s]) * 16 + cta * 8 + warp
   int32_t u_nclusters;
   int32_t u_total_pt;
   int32_t u_pt_begin[SMAX + 1];

@@ -15,9 +15,10 @@
 //  * TMEM (512 columns): D1 h-accumulator 128 | D2 gate accumulator 128 (two halves per tile) |
 //    h operand hi/lo 128 | x operand ring 4 x 32.
 //
-// Roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
-// allocator, warps 4-7 converters (thread = row), warps 8-11 epilogue (thread = row; each warp keeps a
-// private online-softmax stream and candidate lists, so there is no cross-warp traffic per tile).
+// Roles per CTA (512 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
+// allocator, warps 4-7 converters (thread = row), warps 8-15 epilogue (16 rows per warp through the
+// 16-lane TMEM shapes; each warp keeps a private online-softmax stream and candidate lists, so there is
+// no cross-warp traffic per tile).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -27,7 +28,7 @@
 namespace {
 using namespace sm100;
 
-constexpr int UT = 384;
+constexpr int UT = 512;
 constexpr int KC = 32;       // x columns per chunk (one 128-byte swizzle span of fp32)
 constexpr int NSTAGE = 3;    // fp32 staging ring (TMA destination)
 constexpr int NXOP = 4;      // TMEM x-operand ring
@@ -78,8 +79,8 @@ __host__ __device__ inline SmemMap smem_map(int din) {
   m.wg = (uint32_t)(din / 64) * 8192u * 2u;
   m.stage = m.wg + 65536u;
   m.tbuf = m.stage + NSTAGE * STAGE_BYTES;
-  m.ps = m.tbuf + 4 * 2048;
-  m.cst = m.ps + 4 * 1024;
+  m.ps = m.tbuf + 8 * 1024;
+  m.cst = m.ps + 8 * 512;
   m.bars = m.cst + 128 * 10 * 4;
   m.total = m.bars + 256;
   return m;
@@ -88,7 +89,7 @@ __host__ __device__ inline SmemMap smem_map(int din) {
 struct Bars {
   uint64_t full_x[NSTAGE], empty_x[NSTAGE];
   uint64_t xop_full[NXOP], xop_empty[NXOP];
-  uint64_t d1_full, d1_empty, hop_full, d2_full, d2_empty, wload, w_ready;
+  uint64_t d1_full, d1_empty, hop_full, d2_full[2], d2_empty[2], wload, w_ready;
   uint32_t tmem_base;
 };
 
@@ -108,6 +109,15 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
   hi = pack_half2(ah, bh);
   lo = pack_half2(a - ah, b - bh);
+}
+
+// element k of a register array without dynamic indexing (k is warp-uniform)
+template <int KB>
+__device__ __forceinline__ int sel_k(const int (&a)[KB], int k) {
+  int r = a[0];
+#pragma unroll
+  for (int i = 1; i < KB; ++i) r = (k == i) ? a[i] : r;
+  return r;
 }
 
 template <int KB>
@@ -134,10 +144,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full_x[i], 1); mbar_init(&bars->empty_x[i], 4); }
     for (int i = 0; i < NXOP; ++i) { mbar_init(&bars->xop_full[i], 8); mbar_init(&bars->xop_empty[i], 1); }
     mbar_init(&bars->d1_full, 1);
-    mbar_init(&bars->d1_empty, 8);
-    mbar_init(&bars->hop_full, 8);
-    mbar_init(&bars->d2_full, 1);
-    mbar_init(&bars->d2_empty, 8);
+    mbar_init(&bars->d1_empty, 16);
+    mbar_init(&bars->hop_full, 16);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->d2_full[i], 1); mbar_init(&bars->d2_empty[i], 16); }
     mbar_init(&bars->wload, 1);
     mbar_init(&bars->w_ready, 2);
     fence_mbar_init();
@@ -229,25 +238,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
         }
       };
-      auto g2_half = [&](int t, int h) {
-        if (h == 0) { PROF_T0(); mbar_wait_cluster(&bars->hop_full, (uint32_t)t & 1u); PROF_ADD(3); }
-        const uint32_t u = 2u * (uint32_t)t + (uint32_t)h;
-        if (u > 0) { PROF_T0(); mbar_wait_cluster(&bars->d2_empty, (u - 1u) & 1u); PROF_ADD(4); }
+      const uint32_t idesc64 = umma_idesc_f16(256, 64);
+      // gate GEMM in four 32-unit quarters (N = 64: 32 V + 32 U columns) ping-ponging between two D2 buffers,
+      // so the epilogue works on one quarter while the tensor core produces the next
+      auto g2_quarter = [&](int t, int qr) {
+        const int b = qr & 1;
+        if (qr == 0) { PROF_T0(); mbar_wait_cluster(&bars->hop_full, (uint32_t)t & 1u); PROF_ADD(3); }
+        const uint32_t n_use = 2u * (uint32_t)t + (uint32_t)(qr >> 1);      // how often buffer b was used before
+        if (n_use > 0) { PROF_T0(); mbar_wait_cluster(&bars->d2_empty[b], (n_use - 1u) & 1u); PROF_ADD(4); }
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t boff = (uint32_t)(h * 2 + (ks >> 2)) * 8192u + (uint32_t)(ks & 3) * 32u;
+          const uint32_t boff = (uint32_t)(qr * 2 + (ks >> 2)) * 4096u + (uint32_t)(ks & 3) * 32u;
           const uint64_t bhi = umma_desc_k_sw128(wg_hi + boff), blo = umma_desc_k_sw128(wg_lo + boff);
-          umma_ts<2>(tm + TM_D2, tm + TM_HHI + ks * 8, bhi, idesc, ks ? 1u : 0u);
-          umma_ts<2>(tm + TM_D2, tm + TM_HLO + ks * 8, bhi, idesc, 1u);
-          umma_ts<2>(tm + TM_D2, tm + TM_HHI + ks * 8, blo, idesc, 1u);
+          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, bhi, idesc64, ks ? 1u : 0u);
+          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HLO + ks * 8, bhi, idesc64, 1u);
+          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, blo, idesc64, 1u);
         }
-        umma_commit_2sm(&bars->d2_full, 3);
+        umma_commit_2sm(&bars->d2_full[b], 3);
       };
       g1_chunks(0, 0, NCH);
       for (int t = 0; t < T; ++t) {
-        g2_half(t, 0);
-        g2_half(t, 1);
+        g2_quarter(t, 0);
+        g2_quarter(t, 1);
+        g2_quarter(t, 2);
+        g2_quarter(t, 3);
         if (t + 1 < T) g1_chunks(t + 1, 0, NCH);
       }
 #if GP_UMMA_PROF
@@ -306,21 +321,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     if (warp == 4 && lane == 0) PROF_FLUSH(16);
 #endif
   } else {
-    // ===================================== epilogue: thread = row =====================================
-    setmaxnreg_inc<240>();
-    const int ew = warp - 8;
-    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-    float* tbuf = reinterpret_cast<float*>(smem + sm.tbuf + ew * 2048);   // [32 rows][16 feats], chunk-swizzled
-    float* psw = reinterpret_cast<float*>(smem + sm.ps + ew * 1024);      // [32 rows][8]
+    // ===================================== epilogue: 8 warps x 16 rows =====================================
+    // Warp (q, hs) owns TMEM lanes / tile rows [32q + 16hs, +16) and reads them with the 16-lane tcgen05.ld
+    // shapes: in 16x256b thread t gets rows ra = base + t/4 and rb = ra + 8, columns 8i + 2(t%4) + {0,1};
+    // in 16x128b (the packed fp16 operand) it gets column 4i + t%4 of the same two rows -- i.e. the same
+    // features.  Every warp is an independent stream (own m, l, acc, candidate lists): no cross-warp traffic.
+    setmaxnreg_inc<168>();
+    const int e_idx = warp - 8, q = e_idx & 3, hs = e_idx >> 2;
+    const int lane_base = q * 32 + hs * 16;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const int rg = lane >> 2, cp = lane & 3;
+    float* tbuf = reinterpret_cast<float*>(smem + sm.tbuf + e_idx * 1024);   // [16 rows][16 feats]
+    float* psw = reinterpret_cast<float*>(smem + sm.ps + e_idx * 512);       // [16 rows][8]
+    const float* cstp = reinterpret_cast<const float*>(smem + sm.cst);
+    constexpr int CREC = cst_rec(KB);
     const int L = 128;
     const int cap = seg.n_masked_cap;
-    const int jf = lane & 15, par = lane >> 4;
+    const int jf = lane & 15, rs = lane >> 4;     // pool: feature inside the 16-feature chunk, row subset
+    const float* tE0 = tbuf + rs * (128 + 16) + jf;          // even i, swizzle phase 0
+    const float* tE1 = tbuf + rs * (128 + 16) + (jf ^ 8);    // even i, phase 1
+    const float* tO0 = tbuf + rs * (128 - 16) + jf;          // odd i
+    const float* tO1 = tbuf + rs * (128 - 16) + (jf ^ 8);
+    const float* pE = psw + rs * (64 + 8);
+    const float* pO = psw + rs * (64 - 8);
+    const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
 
-    float m_run[KB], l_run[KB], acc[8][KB];
-    // candidate lists: lane i holds entry i of every branch
+    float l_run[KB], acc[8][KB];     // l_run: per-lane partial of sum exp(score)
+    // candidate lists (unsorted): lane i holds entry i of every branch, its h row is parked in scratch slot i
     float c_s[KB];
-    int c_i[KB], c_sl[KB], c_cnt[KB];
-    unsigned c_free[KB];
+    int c_i[KB], c_cnt[KB];
     int s_cur = -1, s_hint = 0, nm = 0, seg_id = 0;
     int64_t n_rows = 0;
 
@@ -328,16 +357,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       s_cur = s;
       nm = seg.nm[s];
       n_rows = seg.row_off[s + 1] - seg.row_off[s];
-      seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 8 + (int)cta * 4 + ew;
+      seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 16 + (int)cta * 8 + e_idx;
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
-        m_run[k] = -INFINITY;
         l_run[k] = 0.f;
-        c_s[k] = -INFINITY;
+        c_s[k] = INFINITY;      // lanes >= cnt never win the "minimum" search
         c_i[k] = 0x7fffffff;
-        c_sl[k] = 0;
         c_cnt[k] = 0;
-        c_free[k] = nm >= 32 ? 0xffffffffu : ((1u << nm) - 1u);
 #pragma unroll
         for (int g = 0; g < 8; ++g) acc[g][k] = 0.f;
       }
@@ -348,14 +374,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         if (k < K) {
+          const float lt = warp_sum(l_run[k]);
           if (lane == 0) {
-            part[(size_t)k * (L + 2) + 0] = m_run[k];
-            part[(size_t)k * (L + 2) + 1] = l_run[k];
+            part[(size_t)k * (L + 2) + 0] = 0.f;     // softmax reference point of this kernel
+            part[(size_t)k * (L + 2) + 1] = lt;
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float v = acc[g][k] + __shfl_xor_sync(0xffffffffu, acc[g][k], 16);   // even + odd rows
-            if (par == 0) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = v;
+            const float v = acc[g][k] + __shfl_xor_sync(0xffffffffu, acc[g][k], 16);   // two row subsets
+            if (rs == 0) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = v;
           }
         }
       }
@@ -372,7 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
               const bool live = lane < c_cnt[k];
               g_score[k * cap + lane] = live ? c_s[k] : -INFINITY;
               g_idx[k * cap + lane] = live ? c_i[k] : 0x7fffffff;
-              g_slot[k * cap + lane] = live ? c_sl[k] : 0;
+              g_slot[k * cap + lane] = lane;
             }
           }
         }
@@ -383,14 +410,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #if GP_UMMA_PROF
     const long long t_start = clock64();
 #endif
+#pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const TilePos tp = tile_pos(g0 + t, s_hint);
       if (tp.s != s_cur) {
         flush_stream();
         reset_stream(tp.s);
       }
-      const int64_t row_in_bag = tp.row_in_bag + ew * 32 + lane;
-      const bool valid = row_in_bag < n_rows;
+      const int64_t row_a = tp.row_in_bag + lane_base + rg, row_b = row_a + 8;
+      const bool valid_a = row_a < n_rows, valid_b = row_b < n_rows;
 
       // ---------------- Epi1: D1 -> relu -> fp16 hi/lo operand of the gate GEMM ----------------
       { PROF_T0(); mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u); PROF_ADD(0); }
@@ -398,20 +426,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #if GP_UMMA_PROF
       const long long t_e1 = clock64();
 #endif
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
         uint32_t v[32];
-        tmem_ld32(tm + lane_addr + TM_D1 + g * 32, v);
+        tmem_ld_16x256b_x8(tm + lane_addr + TM_D1 + hf * 64, v);
         tmem_wait_ld();
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = fmaxf(fmaf(__uint_as_float(v[2 * i]), p.c.inv_s1, p.c.b1[g * 32 + 2 * i]), 0.f);
-          const float b = fmaxf(fmaf(__uint_as_float(v[2 * i + 1]), p.c.inv_s1, p.c.b1[g * 32 + 2 * i + 1]), 0.f);
-          split2(a, b, hi[i], lo[i]);
+        for (int i = 0; i < 8; ++i) {
+          split2(fmaxf(__uint_as_float(v[4 * i]) * p.c.inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) * p.c.inv_s1, 0.f),
+                 hi[2 * i], lo[2 * i]);
+          split2(fmaxf(__uint_as_float(v[4 * i + 2]) * p.c.inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) * p.c.inv_s1, 0.f),
+                 hi[2 * i + 1], lo[2 * i + 1]);
         }
-        tmem_st16(tm + lane_addr + TM_HHI + g * 16, hi);
-        tmem_st16(tm + lane_addr + TM_HLO + g * 16, lo);
+        tmem_st_16x128b_x8(tm + lane_addr + TM_HHI + hf * 32, hi);
+        tmem_st_16x128b_x8(tm + lane_addr + TM_HLO + hf * 32, lo);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -420,230 +449,260 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         mbar_arrive_cluster(&bars->hop_full, 0);
         mbar_arrive_cluster(&bars->d1_empty, 0);
       }
-
 #if GP_UMMA_PROF
       prof[2] += clock64() - t_e1;
       const long long t_e2 = clock64();
 #endif
-      // ---------------- Epi2: gate + scores ----------------
-      float sc_[KB];
+
+      // ---------------- Epi2: gate + scores (each thread: 2 rows x 32 units per tile) ----------------
+      float sa[KB], sb[KB];
 #pragma unroll
-      for (int k = 0; k < KB; ++k) sc_[k] = p.c.bw[k];
-      const float* cstp = reinterpret_cast<const float*>(smem + sm.cst);
-      const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
+      for (int k = 0; k < KB; ++k) sa[k] = sb[k] = 0.f;
+      // one 32-unit quarter of the gate: V columns [0, 32), U columns [32, 64) of a D2 buffer; this thread owns
+      // units unit0 + 8 ii + 2 cp + j (ii < 4, j < 2) of rows a and b
+      auto gate_quarter = [&](const uint32_t (&zv)[16], const uint32_t (&zu)[16], int unit0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        { PROF_T0(); mbar_wait_cluster(&bars->d2_full, (uint32_t)(2 * t + h) & 1u); PROF_ADD(1); }
-        tc_fence_after();
+        for (int ii = 0; ii < 4; ++ii) {
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          uint32_t zv[32], zu[32];
-          tmem_ld32(tm + lane_addr + TM_D2 + sub * 32, zv);
-          tmem_ld32(tm + lane_addr + TM_D2 + 64 + sub * 32, zu);
-          tmem_wait_ld();
-          if (sub == 1) {   // this half of D2 is in registers: the MMA warp may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars->d2_empty, 0);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int u = h * 64 + sub * 32 + i;
-            constexpr int CREC = cst_rec(KB);
+          for (int j = 0; j < 2; ++j) {
+            const float* rec = cstp + (unit0 + ii * 8 + cp * 2 + j) * CREC;
             float cr[CREC];
             if constexpr (CREC == 10) {
 #pragma unroll
-              for (int j = 0; j < 5; ++j) *reinterpret_cast<float2*>(&cr[2 * j]) = *reinterpret_cast<const float2*>(cstp + u * CREC + 2 * j);
+              for (int w = 0; w < 5; ++w) *reinterpret_cast<float2*>(&cr[2 * w]) = *reinterpret_cast<const float2*>(rec + 2 * w);
             } else {
 #pragma unroll
-              for (int j = 0; j < CREC / 4; ++j) *reinterpret_cast<float4*>(&cr[4 * j]) = *reinterpret_cast<const float4*>(cstp + u * CREC + 4 * j);
+              for (int w = 0; w < CREC / 4; ++w) *reinterpret_cast<float4*>(&cr[4 * w]) = *reinterpret_cast<const float4*>(rec + 4 * w);
             }
-            // tanh(a) * sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)),  Ea = e^-2a, Eb = e^-b  (exponents clamped at 40);
-            // scales and biases are pre-multiplied into the exponent domain
-            const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[i]), cva, cr[KB]), 57.7f));
-            const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[i]), cua, cr[KB + 1]), 57.7f));
-            const float gte = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
+            // tanh(a) sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)), Ea = e^-2a, Eb = e^-b (exponents clamped at 40);
+            // D2 holds Sg z: the scales and biases are folded into the exponent-domain constants
+            {
+              const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[4 * ii + j]), cva, cr[KB]), 57.7f));
+              const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[4 * ii + j]), cua, cr[KB + 1]), 57.7f));
+              const float g = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
 #pragma unroll
-            for (int k = 0; k < KB; ++k) sc_[k] = fmaf(gte, cr[k], sc_[k]);
+              for (int k = 0; k < KB; ++k) sa[k] = fmaf(g, cr[k], sa[k]);
+            }
+            {
+              const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[4 * ii + 2 + j]), cva, cr[KB]), 57.7f));
+              const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[4 * ii + 2 + j]), cua, cr[KB + 1]), 57.7f));
+              const float g = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
+#pragma unroll
+              for (int k = 0; k < KB; ++k) sb[k] = fmaf(g, cr[k], sb[k]);
+            }
           }
         }
+      };
+#pragma unroll 1
+      for (int qr = 0; qr < 4; ++qr) {
+        const int b = qr & 1;
+        { PROF_T0(); mbar_wait_cluster(&bars->d2_full[b], (uint32_t)(2 * t + (qr >> 1)) & 1u); PROF_ADD(1); }
+        tc_fence_after();
+        uint32_t zv[16], zu[16];
+        tmem_ld_16x256b_x4(tm + lane_addr + TM_D2 + b * 64, zv);
+        tmem_ld_16x256b_x4(tm + lane_addr + TM_D2 + b * 64 + 32, zu);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&bars->d2_empty[b], 0);   // buffer b is in registers: the MMA warp may refill it
+        gate_quarter(zv, zu, qr * 32);
       }
-
+      // the 4 threads of a row group hold disjoint unit subsets: finish the dot products
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], 1);
+        sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 1);
+        sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], 2);
+        sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 2);
+        sa[k] += p.c.bw[k];
+        sb[k] += p.c.bw[k];
+      }
 #if GP_UMMA_PROF
       prof[3] += clock64() - t_e2;
       const long long t_e3 = clock64();
 #endif
-      // ---------------- raw scores out ----------------
-      if (p.mp.a_out != nullptr && valid) {
+
+      // ---------------- raw scores out: thread (rg, cp) stores branches cp and cp + 4 of its two rows ----------------
+      if (p.mp.a_out != nullptr) {
+        float* ao = p.mp.a_out + seg.row_off[s_cur];
 #pragma unroll
-        for (int k = 0; k < KB; ++k)
-          if (k < K) p.mp.a_out[(size_t)k * p.mp.a_ld + seg.row_off[s_cur] + row_in_bag] = sc_[k];
+        for (int k = 0; k < KB; ++k) {
+          if (k < K && (k & 3) == cp) {
+            if (valid_a) ao[(size_t)k * p.mp.a_ld + row_a] = sa[k];
+            if (valid_b) ao[(size_t)k * p.mp.a_ld + row_b] = sb[k];
+          }
+        }
       }
 
-      // ---------------- candidates (top-n rows per branch stay out of the sums) + online softmax ----------------
-      float pk[KB], scale[KB];
-      unsigned my_new = 0u;          // bit k: this lane's row entered branch k's list this tile
-      int my_slot[KB];
-      float ev_w[KB];                // lane e: weight of the e-th entry evicted from branch k this tile
-      int ev_slot[KB], n_ev[KB];
+      // ---------------- candidates + online softmax ----------------
+      // "representative" lanes: cp == 0 speaks for row a of its group, cp == 1 for row b
+      float pa[KB], pb[KB];
+      unsigned ex_a = 0u, ex_b = 0u;       // bit k: row a / b of this row group was parked for branch k this tile
+      int slot_a[KB], slot_b[KB];
+      int n_ev[KB], ev_slot[KB];
+      float ev_w[KB];                      // lane e: e-th entry evicted from branch k this tile (score, then weight)
+      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)seg_id * K * cap * L;
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         n_ev[k] = 0;
         ev_w[k] = -INFINITY;
         ev_slot[k] = 0;
-        my_slot[k] = 0;
-        if (k < K && nm > 0) {
+        slot_a[k] = slot_b[k] = 0;
+      }
+      if (nm > 0) {
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        if (k < K) {
+          const float my_s = cp == 0 ? sa[k] : sb[k];
+          const bool my_valid = cp == 0 ? valid_a : (cp == 1 ? valid_b : false);
+          const int my_row = (int)(cp == 0 ? row_a : row_b);
           int cnt = c_cnt[k];
-          const float tau = cnt == nm ? __shfl_sync(0xffffffffu, c_s[k], nm - 1) : -INFINITY;
-          unsigned bal = __ballot_sync(0xffffffffu, valid && (cnt < nm || sc_[k] > tau));
-          unsigned freed = 0u;
+          // threshold = smallest score in a full list
+          float tau = -INFINITY;
+          int tau_lane = 0;
+          if (cnt == nm) {
+            tau = lane < cnt ? c_s[k] : INFINITY;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+            tau_lane = __ffs(__ballot_sync(0xffffffffu, lane < cnt && c_s[k] == tau)) - 1;
+          }
+          unsigned bal = __ballot_sync(0xffffffffu, my_valid && (cnt < nm || my_s > tau));
           while (bal) {
             const int src = __ffs(bal) - 1;
             bal &= bal - 1;
-            const float s_new = __shfl_sync(0xffffffffu, sc_[k], src);
-            if (cnt == nm) {
-              const float last_s = __shfl_sync(0xffffffffu, c_s[k], nm - 1);
-              if (!(s_new > last_s)) continue;
-              const int last_sl = __shfl_sync(0xffffffffu, c_sl[k], nm - 1);
-              if (last_sl >= 0) {
-                if (lane == n_ev[k]) { ev_w[k] = last_s; ev_slot[k] = last_sl; }
-                freed |= 1u << last_sl;
+            const float s_new = __shfl_sync(0xffffffffu, my_s, src);
+            const int r_new = __shfl_sync(0xffffffffu, my_row, src);
+            int dst;
+            if (cnt < nm) {
+              dst = cnt++;
+            } else {
+              if (!(s_new > tau)) continue;
+              dst = tau_lane;
+              // the evicted entry rejoins the sums this tile unless it is itself a row of this tile
+              const int old_i = __shfl_sync(0xffffffffu, c_i[k], dst);
+              const bool same_tile = old_i >= (int)(tp.row_in_bag + lane_base) && old_i < (int)(tp.row_in_bag + lane_base + 16);
+              if (same_tile) {
+                const int orow = old_i - (int)(tp.row_in_bag + lane_base);     // 0..15: un-park it
+                if (rg == (orow & 7)) { if (orow < 8) ex_a &= ~(1u << k); else ex_b &= ~(1u << k); }
+              } else {
+                if (lane == n_ev[k]) { ev_w[k] = tau; ev_slot[k] = dst; }
                 ++n_ev[k];
               }
             }
-            const int pos = __popc(__ballot_sync(0xffffffffu, lane < cnt && c_s[k] >= s_new));
-            const float up_s = __shfl_up_sync(0xffffffffu, c_s[k], 1);
-            const int up_i = __shfl_up_sync(0xffffffffu, c_i[k], 1);
-            const int up_sl = __shfl_up_sync(0xffffffffu, c_sl[k], 1);
-            if (lane > pos) { c_s[k] = up_s; c_i[k] = up_i; c_sl[k] = up_sl; }
-            if (lane == pos) { c_s[k] = s_new; c_i[k] = (int)(tp.row_in_bag + ew * 32 + src); c_sl[k] = -1 - src; }
-            if (cnt < nm) ++cnt;
+            if (lane == dst) { c_s[k] = s_new; c_i[k] = r_new; }
+            {   // park the new row: every thread of its row group learns the slot
+              const int nrow = r_new - (int)(tp.row_in_bag + lane_base);
+              if (rg == (nrow & 7)) {
+                if (nrow < 8) { ex_a |= 1u << k; slot_a[k] = dst; } else { ex_b |= 1u << k; slot_b[k] = dst; }
+              }
+            }
+            if (cnt == nm) {
+              tau = lane < cnt ? c_s[k] : INFINITY;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+              tau_lane = __ffs(__ballot_sync(0xffffffffu, lane < cnt && c_s[k] == tau)) - 1;
+            }
           }
-          const bool is_new = lane < cnt && c_sl[k] < 0;
-          const unsigned newmask = __ballot_sync(0xffffffffu, is_new);
-          const unsigned freemask = c_free[k] | freed;
-          int row_of_new = -1, slot_of_new = 0;
-          if (is_new) {
-            unsigned fm = freemask;
-            const int rank = __popc(newmask & ((1u << lane) - 1u));
-            for (int i = 0; i < rank; ++i) fm &= fm - 1;
-            slot_of_new = __ffs(fm) - 1;
-            row_of_new = -1 - c_sl[k];
-            c_sl[k] = slot_of_new;
-          }
-          // tell the lane that owns each new row which slot its h row goes to
-          unsigned nmk = newmask;
-          while (nmk) {
-            const int e = __ffs(nmk) - 1;
-            nmk &= nmk - 1;
-            const int rr = __shfl_sync(0xffffffffu, row_of_new, e);
-            const int sl = __shfl_sync(0xffffffffu, slot_of_new, e);
-            if (lane == rr) { my_new |= 1u << k; my_slot[k] = sl; }
-          }
-          unsigned inuse = 0u;
-          for (int i = 0; i < cnt; ++i) inuse |= 1u << __shfl_sync(0xffffffffu, c_sl[k], i);
-          c_free[k] = (nm >= 32 ? 0xffffffffu : ((1u << nm) - 1u)) & ~inuse;
           c_cnt[k] = cnt;
         }
-        // online softmax over the rows that take part
-        const bool take = valid && !((my_new >> k) & 1u);
-        float tmax = take ? sc_[k] : -INFINITY;
-        tmax = fmaxf(tmax, ev_w[k]);
-        tmax = warp_max(tmax);
-        const float m_new = fmaxf(m_run[k], tmax);
-        scale[k] = (m_run[k] == -INFINITY) ? 0.f : __expf(m_run[k] - m_new);
-        pk[k] = (take && m_new != -INFINITY) ? __expf(sc_[k] - m_new) : 0.f;
-        float lsum = pk[k];
+      }
+      }
+      // softmax numerators against the FIXED reference 0: scores are bounded by B_k = sum_u |ww[k][u]| + |bw[k]|
+      // (|tanh * sigmoid| < 1) and acmil_gp_pack only enables this kernel when B_k <= 77, so exp(s) can neither
+      // overflow nor flush to zero and no running max / rescale / cross-lane traffic is needed per tile.
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const bool take_a = valid_a && !((ex_a >> k) & 1u), take_b = valid_b && !((ex_b >> k) & 1u);
+        pa[k] = take_a ? ex2_approx(sa[k] * LOG2E) : 0.f;
+        pb[k] = take_b ? ex2_approx(sb[k] * LOG2E) : 0.f;
+        if (cp == 0) l_run[k] += pa[k] + pb[k];       // each row once; lanes are summed at flush
         if (lane < n_ev[k]) {
-          ev_w[k] = __expf(ev_w[k] - m_new);
-          lsum += ev_w[k];
+          ev_w[k] = ex2_approx(ev_w[k] * LOG2E);
+          l_run[k] += ev_w[k];
         } else {
           ev_w[k] = 0.f;
         }
-        lsum = warp_sum(lsum);
-        l_run[k] = l_run[k] * scale[k] + lsum;
-        m_run[k] = m_new;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) acc[g][k] *= scale[k];
       }
-      {
+      if (cp < 2) {   // p of row a (cp 0) / row b (cp 1) -> smem for the pool
         float4 p0, p1;
-        p0.x = pk[0];
-        p0.y = KB > 1 ? pk[KB > 1 ? 1 : 0] : 0.f;
-        p0.z = KB > 2 ? pk[KB > 2 ? 2 : 0] : 0.f;
-        p0.w = KB > 3 ? pk[KB > 3 ? 3 : 0] : 0.f;
-        p1.x = KB > 4 ? pk[KB > 4 ? 4 : 0] : 0.f;
-        p1.y = KB > 5 ? pk[KB > 5 ? 5 : 0] : 0.f;
-        p1.z = KB > 6 ? pk[KB > 6 ? 6 : 0] : 0.f;
-        p1.w = KB > 7 ? pk[KB > 7 ? 7 : 0] : 0.f;
-        *reinterpret_cast<float4*>(psw + lane * 8) = p0;
-        *reinterpret_cast<float4*>(psw + lane * 8 + 4) = p1;
+        p0.x = cp ? pb[0] : pa[0];
+        p0.y = KB > 1 ? (cp ? pb[KB > 1 ? 1 : 0] : pa[KB > 1 ? 1 : 0]) : 0.f;
+        p0.z = KB > 2 ? (cp ? pb[KB > 2 ? 2 : 0] : pa[KB > 2 ? 2 : 0]) : 0.f;
+        p0.w = KB > 3 ? (cp ? pb[KB > 3 ? 3 : 0] : pa[KB > 3 ? 3 : 0]) : 0.f;
+        p1.x = KB > 4 ? (cp ? pb[KB > 4 ? 4 : 0] : pa[KB > 4 ? 4 : 0]) : 0.f;
+        p1.y = KB > 5 ? (cp ? pb[KB > 5 ? 5 : 0] : pa[KB > 5 ? 5 : 0]) : 0.f;
+        p1.z = KB > 6 ? (cp ? pb[KB > 6 ? 6 : 0] : pa[KB > 6 ? 6 : 0]) : 0.f;
+        p1.w = KB > 7 ? (cp ? pb[KB > 7 ? 7 : 0] : pa[KB > 7 ? 7 : 0]) : 0.f;
+        const int prow = rg + 8 * cp;
+        *reinterpret_cast<float4*>(psw + prow * 8) = p0;
+        *reinterpret_cast<float4*>(psw + prow * 8 + 4) = p1;
       }
-      __syncwarp();
-
 #if GP_UMMA_PROF
       prof[4] += clock64() - t_e3;
       const long long t_e4 = clock64();
 #endif
-      // entries that fell out of a list this tile rejoin the sums; their h rows were parked in scratch by
-      // an earlier tile and must be read BEFORE this tile's new entries reuse the freed slots
-      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)seg_id * K * cap * L;
+      // entries that fell out of a list this tile rejoin the sums; read their parked rows BEFORE this tile's
+      // new entries overwrite the same slots
+      if (nm > 0) {
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         if (k < K) {
           for (int e = 0; e < n_ev[k]; ++e) {
             const float w = __shfl_sync(0xffffffffu, ev_w[k], e);
             const int sl = __shfl_sync(0xffffffffu, ev_slot[k], e);
-            if (par == 0) {
+            if (rs == 0) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) acc[g][k] = fmaf(w, cand_h[((size_t)k * cap + sl) * L + g * 16 + jf], acc[g][k]);
             }
           }
         }
       }
+      }
       __syncwarp();
 
-      // ---------------- pool: acc[k][:] += sum_rows p[row][k] h[row][:]  (h re-read from the TMEM operand) ----------------
+      // ---------------- pool: acc[k][:] += sum_rows p[row][k] h[row][:]  (h = hi + lo of the TMEM operand) ----------------
+      const bool parking = (ex_a | ex_b) != 0u;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint32_t hh[8], hl[8];
-        tmem_ld8(tm + lane_addr + TM_HHI + g * 8, hh);
-        tmem_ld8(tm + lane_addr + TM_HLO + g * 8, hl);
+      for (int g = 0; g < 8; ++g) {     // 16-feature chunk g (unrolled: acc[g] must stay in registers; keep the body small)
+        uint32_t hh[4], hl[4];
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + g * 8, hh);
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + g * 8, hl);
         tmem_wait_ld();
-        float f[16];
+        // this thread holds features 8 ii + 2 cp + {0,1} of the chunk for rows rg (a) and rg + 8 (b)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
-          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hl[i]));
-          f[2 * i] = a.x + b.x;
-          f[2 * i + 1] = a.y + b.y;
-        }
-        const int sw = (lane >> 1) & 3;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(tbuf + lane * 16 + ((c ^ sw) << 2)) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-        if (my_new) {   // park this row's h where the reduce kernel (or a later late-add) finds it
-#pragma unroll
-          for (int k = 0; k < KB; ++k)
-            if ((my_new >> k) & 1u) {
-              float* dst = cand_h + ((size_t)k * cap + my_slot[k]) * L + g * 16;
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+        for (int ii = 0; ii < 2; ++ii) {
+          const float2 ah = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * ii]));
+          const float2 al = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * ii]));
+          const float2 bh = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * ii + 1]));
+          const float2 bl = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * ii + 1]));
+          const float2 fa = make_float2(ah.x + al.x, ah.y + al.y), fb = make_float2(bh.x + bl.x, bh.y + bl.y);
+          const int fcol = ii * 8 + cp * 2;
+          const int fsw = fcol ^ (((rg >> 1) & 1) << 3);     // rows of equal parity land in different bank groups
+          *reinterpret_cast<float2*>(tbuf + rg * 16 + fsw) = fa;
+          *reinterpret_cast<float2*>(tbuf + (rg + 8) * 16 + fsw) = fb;
+          if (parking) {   // park rows that entered a list this tile
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+              if ((ex_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * cap + sel_k(slot_a, k)) * L + g * 16 + fcol) = fa;
+              if ((ex_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * cap + sel_k(slot_b, k)) * L + g * 16 + fcol) = fb;
             }
+          }
         }
         __syncwarp();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + par;
-          const float hv = tbuf[rr * 16 + ((((jf >> 2) ^ ((rr >> 1) & 3))) << 2) + (jf & 3)];
-          const float4 p0 = *reinterpret_cast<const float4*>(psw + rr * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // row rs * 8 + (i ^ rs): the two row subsets read rows of opposite parity; all address math is in the
+          // four lane-constant bases (even/odd i x swizzle phase) plus an immediate
+          const float* tb = (i & 1) ? (((i >> 1) & 1) ? tO1 : tO0) : (((i >> 1) & 1) ? tE1 : tE0);
+          const float* pp = (i & 1) ? pO : pE;
+          const float hv = tb[i * 16];
+          const float4 p0 = *reinterpret_cast<const float4*>(pp + i * 8);
           acc[g][0] = fmaf(p0.x, hv, acc[g][0]);
           if (KB > 1) acc[g][KB > 1 ? 1 : 0] = fmaf(p0.y, hv, acc[g][KB > 1 ? 1 : 0]);
           if (KB > 2) acc[g][KB > 2 ? 2 : 0] = fmaf(p0.z, hv, acc[g][KB > 2 ? 2 : 0]);
           if (KB > 3) acc[g][KB > 3 ? 3 : 0] = fmaf(p0.w, hv, acc[g][KB > 3 ? 3 : 0]);
           if (KB > 4) {
-            const float4 p1 = *reinterpret_cast<const float4*>(psw + rr * 8 + 4);
+            const float4 p1 = *reinterpret_cast<const float4*>(pp + i * 8 + 4);
             acc[g][KB > 4 ? 4 : 0] = fmaf(p1.x, hv, acc[g][KB > 4 ? 4 : 0]);
             if (KB > 5) acc[g][KB > 5 ? 5 : 0] = fmaf(p1.y, hv, acc[g][KB > 5 ? 5 : 0]);
             if (KB > 6) acc[g][KB > 6 ? 6 : 0] = fmaf(p1.z, hv, acc[g][KB > 6 ? 6 : 0]);
@@ -672,8 +731,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 // ------------------------------------------------------------------------------------------------
 // weight images: per CTA c of the pair
 //   W1 part (hi, then lo): for kb in [0, DIN/64): tile [64 rows = features 64c..64c+63][64 k] K-major SWIZZLE_128B (8 KB)
-//   Wg part (hi, then lo): Wg = Wv for c == 0, Wu for c == 1: for h in {0,1}, kb in {0,1}:
-//                          tile [64 rows = units 64h..64h+63][64 k = features 64kb..] (8 KB)
+//   Wg part (hi, then lo): Wg = Wv for c == 0, Wu for c == 1: for quarter in 0..3, kb in {0,1}:
+//                          tile [32 rows = units 32q..32q+31][64 k = features 64kb..] (4 KB)
 // values are scaled by the power of two in scales[] before the split (undone in the epilogue)
 __global__ void umma_absmax_kernel(const float* __restrict__ w, size_t n, float* out) {
   float m = 0.f;
@@ -717,8 +776,8 @@ __global__ void umma_pack_kernel(acmil_gp_shape sh, acmil_gp_weights w, const fl
       const int u = (int)(jj >> 7), k = (int)(jj & 127);          // Wg[u][k]
       v = (is_u ? w.d_wu[jj] * su : w.d_wv[jj] * sv);
       cta = is_u ? 1u : 0u;
-      const uint32_t tile = (uint32_t)((u >> 6) * 2 + (k >> 6)) * 8192u;
-      const uint32_t inner = sw128_offset((uint32_t)(u & 63), (uint32_t)((k & 63) >> 3)) + (uint32_t)(k & 7) * 2u;
+      const uint32_t tile = (uint32_t)((u >> 5) * 2 + (k >> 6)) * 4096u;          // [quarter][k block]: 32 rows x 128 B
+      const uint32_t inner = sw128_offset((uint32_t)(u & 31), (uint32_t)((k & 63) >> 3)) + (uint32_t)(k & 7) * 2u;
       off_hi = 2u * w1_part_bytes + tile + inner;
       off_lo = 2u * w1_part_bytes + 32768u + tile + inner;
     }
@@ -806,7 +865,14 @@ int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned ch
       consts->inv_scale[i] = 1.f / sc;
     }
     consts->inv_scale[3] = 1.f;
-    consts->valid = ACMIL_ABI_VERSION;
+    // the tcgen05 kernel's softmax uses the fixed reference 0: needs |score| <= 77 for every possible input
+    float bound = 0.f;
+    for (int k = 0; k < s.n_branch; ++k) {
+      float bk = fabsf(consts->bw[k]);
+      for (int u = 0; u < 128; ++u) bk += fabsf(consts->ww[k][u]);
+      if (!(bk <= bound)) bound = bk;   // NaN-propagating max
+    }
+    consts->valid = (bound <= 77.f) ? ACMIL_ABI_VERSION : 0;
   }
   return ACMIL_OK;
 }
@@ -834,11 +900,11 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
   if ((int64_t)total_pt * (sm_count / 2 + 1) >= (int64_t)0x7fffffff) return -1;   // 32-bit partition arithmetic
   int ncl = sm_count / 2;
   if (ncl > total_pt) ncl = total_pt;
-  if (cap > 0 && ncl * 8 * cap > GP_MAX_SEG_CAND) ncl = GP_MAX_SEG_CAND / (8 * cap);   // reduce kernel's smem bound
+  if (cap > 0 && ncl * 16 * cap > GP_MAX_SEG_CAND) ncl = GP_MAX_SEG_CAND / (16 * cap);   // reduce kernel's smem bound
   if (ncl < 1) ncl = 1;
   t->u_nclusters = ncl;
   t->n_masked_cap = cap;
-  // segments: 8 per (cluster, bag) pair that intersects
+  // segments: 16 per (cluster, bag) pair that intersects (2 CTAs x 8 epilogue warps)
   int seg = 0;
   for (int s = 0; s < b.n_slides; ++s) {
     t->seg_begin[s] = seg;
@@ -853,7 +919,7 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
       }
     }
     t->u_cfirst[s] = first < 0 ? 0 : first;
-    seg += 8 * count;
+    seg += 16 * count;
   }
   t->seg_begin[b.n_slides] = seg;
   t->n_seg = seg;
