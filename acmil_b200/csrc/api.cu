@@ -78,7 +78,7 @@ int plan(const acmil_gp_shape& s, const acmil_gp_batch& b, int impl, GpSegTable*
     ACMIL_REQUIRE(gp_umma_build_plan(b, sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
   else
     ACMIL_REQUIRE(gp_build_segments(b, 64, 4 * sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
-  *wl = gp_workspace_layout(s, seg->n_seg, seg->n_masked_cap);
+  *wl = gp_workspace_layout(s, *seg);
   return ACMIL_OK;
 }
 
@@ -211,8 +211,9 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
                 "a_ld smaller than the number of rows");
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
   int use = pick_impl(*shape, impl);
-  if (impl == ACMIL_IMPL_AUTO && use == ACMIL_IMPL_UMMA && !(consts && consts->valid == ACMIL_ABI_VERSION))
-    use = ACMIL_IMPL_FFMA;   // no host constants supplied: stay on the general kernel
+  if (impl == ACMIL_IMPL_AUTO && use == ACMIL_IMPL_UMMA &&
+      (!(consts && consts->valid == ACMIL_ABI_VERSION) || (shape->n_branch > 6 && batch->n_masked > 0)))
+    use = ACMIL_IMPL_FFMA;   // no host constants supplied / masking with > 6 branches: stay on the general kernel
   ACMIL_REQUIRE(use != ACMIL_IMPL_UMMA || gp_umma_supported(*shape), ACMIL_E_UNSUPPORTED,
                 "tcgen05 kernel does not support this shape");
   GpMainParams p;

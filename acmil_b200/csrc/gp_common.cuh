@@ -89,6 +89,11 @@ struct GpSegTable {
   // tcgen05 kernel only: bags are cut into 256-row pair-tiles, cluster c owns the global pair-tiles
   // [c * u_total_pt / u_nclusters, (c + 1) * u_total_pt / u_nclusters); every (cluster, bag) it touches
   // produces 16 segments (2 CTAs x 8 epilogue warps): seg_begin[s] + (c - u_cfirst[s]) * 16 + cta * 8 + warp
+  // candidate bookkeeping: lists live per "candidate holder" = group of cand_div consecutive segments
+  // (FFMA: every segment; tcgen05: one per CTA and bag = 8 segments); each holder owns cand lists of
+  // n_masked_cap entries per branch and rec_cap parked h rows per branch
+  int32_t cand_div;
+  int32_t rec_cap;
   int32_t u_nclusters;
   int32_t u_total_pt;
   int32_t u_pt_begin[SMAX + 1];
@@ -127,28 +132,38 @@ static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int 
   t->seg_begin[b.n_slides] = seg;
   t->n_seg = seg;
   t->n_masked_cap = cap;
+  t->cand_div = 1;
+  t->rec_cap = cap;
   return 0;
 }
 
 // ----------------------------------------------------------------------------- workspace
 // per segment and branch:  part[seg][k][L+2] = {m, l, acc[L]}
-//   cand_cnt[seg][k]; cand_score/idx/slot[seg][k][cap]; cand_h[seg][k][cap][L]
+// per candidate holder cb = seg / cand_div and branch:
+//   cand_cnt[cb][k]; cand_score/idx/slot[cb][k][cap] (the holder's top-n list; slot = index of the parked row)
+//   rec_score/rec_idx[cb][k][rec_cap] (every row ever parked; tcgen05 kernel only); cand_h[cb][k][rec_cap][L]
+//   flags[0] != 0: a holder ran out of parking slots (results are poisoned with NaN by the reduce kernel)
 struct GpWorkspace {
-  size_t part, cand_cnt, cand_score, cand_idx, cand_slot, cand_h;  // byte offsets
+  size_t part, cand_cnt, cand_score, cand_idx, cand_slot, rec_score, rec_idx, cand_h, flags;  // byte offsets
   size_t total_bytes;
 };
 
-static inline GpWorkspace gp_workspace_layout(const acmil_gp_shape& s, int n_seg, int cap) {
+static inline GpWorkspace gp_workspace_layout(const acmil_gp_shape& s, const GpSegTable& t) {
   GpWorkspace w;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
   const size_t K = s.n_branch, L = s.d_inner;
-  w.part = take((size_t)n_seg * K * (L + 2) * 4);
-  w.cand_cnt = take((size_t)n_seg * K * 4);
-  w.cand_score = take((size_t)n_seg * K * cap * 4);
-  w.cand_idx = take((size_t)n_seg * K * cap * 4);
-  w.cand_slot = take((size_t)n_seg * K * cap * 4);
-  w.cand_h = take((size_t)n_seg * K * cap * L * 4);
+  const size_t n_seg = t.n_seg, cap = t.n_masked_cap, rcap = t.rec_cap;
+  const size_t ncb = (n_seg + t.cand_div - 1) / (t.cand_div > 0 ? t.cand_div : 1);
+  w.part = take(n_seg * K * (L + 2) * 4);
+  w.cand_cnt = take(ncb * K * 4);
+  w.cand_score = take(ncb * K * cap * 4);
+  w.cand_idx = take(ncb * K * cap * 4);
+  w.cand_slot = take(ncb * K * cap * 4);
+  w.rec_score = take(t.cand_div > 1 ? ncb * K * rcap * 4 : 0);
+  w.rec_idx = take(t.cand_div > 1 ? ncb * K * rcap * 4 : 0);
+  w.cand_h = take(ncb * K * rcap * L * 4);
+  w.flags = take(256);
   w.total_bytes = o + 256;
   return w;
 }

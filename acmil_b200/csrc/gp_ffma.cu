@@ -488,6 +488,7 @@ int gp_launch_main_ffma(const GpMainParams& p, cudaStream_t st) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_main_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, 16, st));
   gp_main_ffma_kernel<<<p.seg.n_seg, FT, smem, st>>>(p);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());

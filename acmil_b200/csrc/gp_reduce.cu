@@ -78,9 +78,10 @@ __global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ G
   const int FC = L / 32;
   const int fc = blockIdx.x % FC, k = (blockIdx.x / FC) % K, s = blockIdx.x / (FC * K);
   const int seg0 = p.seg.seg_begin[s], nseg = p.seg.seg_begin[s + 1] - seg0;
-  const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap;
+  const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap, rcap = p.seg.rec_cap, cdiv = p.seg.cand_div;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncand = nseg * nm;
+  const int cb0 = seg0 / cdiv, ncb = nseg / cdiv;      // candidate holders of this bag
+  const int ncand = ncb * nm;
 
   float* c_score = reinterpret_cast<float*>(dsm);
   int* c_idx = reinterpret_cast<int*>(c_score + ncand);
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ G
   int my_valid = 0;
   for (int c = tid; c < ncand; c += RT) {
     const int sg = c / nm, i = c % nm;
-    const size_t g = ((size_t)(seg0 + sg) * K + k) * cap + i;
-    const bool live = i < g_cnt[(size_t)(seg0 + sg) * K + k];
+    const size_t g = ((size_t)(cb0 + sg) * K + k) * cap + i;
+    const bool live = i < g_cnt[(size_t)(cb0 + sg) * K + k];
     c_score[c] = live ? g_score[g] : -INFINITY;
     c_idx[c] = live ? g_idx[g] : 0x7fffffff;
     c_slot[c] = live ? g_slot[g] : -1;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ G
   for (int c = warp; c < ncand; c += RT / 32) {
     if (c_slot[c] >= 0 && !c_sel[c]) {
       const int sg = c / nm;
-      a = fmaf(expf(c_score[c] - mstar), g_h[(((size_t)(seg0 + sg) * K + k) * cap + c_slot[c]) * L + jf], a);
+      a = fmaf(expf(c_score[c] - mstar), g_h[(((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L + jf], a);
     }
   }
   wsum[warp][lane] = a;
@@ -169,13 +170,14 @@ __global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ G
     if (i < nsel) {
       const int c = sel_pos[i];
       const int sg = c / nm;
-      hv = g_h[(((size_t)(seg0 + sg) * K + k) * cap + c_slot[c]) * L + jf];
+      hv = g_h[(((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L + jf];
     }
     rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = hv;
   }
   if (fc == 0) {
     if (tid == 0) {
-      rec[p.rec.m() + k] = mstar;
+      const int overflow = *reinterpret_cast<const int*>(p.ws + p.wl.flags);
+      rec[p.rec.m() + k] = overflow ? NAN : mstar;      // a holder ran out of parking slots: fail loudly
       rec[p.rec.l() + k] = lstar;
       reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
     }
@@ -463,7 +465,7 @@ int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_recor
   if (S == 0) return ACMIL_OK;
   int max_cand = 0;
   for (int s = 0; s < S; ++s) {
-    const int c = (mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]) * mp.seg.nm[s];
+    const int c = (mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]) / mp.seg.cand_div * mp.seg.nm[s];
     if (c > max_cand) max_cand = c;
   }
   const size_t smem = (size_t)max_cand * 16 + 16;

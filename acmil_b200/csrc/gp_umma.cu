@@ -66,14 +66,30 @@ struct UmmaParams {
   uint32_t w1_part_bytes;      // bytes of one (hi or lo) W1 half image
 };
 
-// smem carve-up (offsets from the 1024-aligned base)
-struct SmemMap {
-  uint32_t w1, wg, stage, tbuf, ps, cst, bars, total;
+// Top-n tracking per CTA and bag (training-mode masking).  Epilogue warp k is the "manager" of branch k: per tile
+// every warp publishes its rows' scores in shared memory, the managers compare all 128 rows of the tile with the
+// CTA's current n-th best (list kept in the manager's registers: lane i = entry i) and flag the rows that enter.
+// A flagged row is "parked": kept out of the sums, its score / index / h row appended to scratch.  At the end of
+// the bag the parked rows that did not stay in the CTA's top n are added back by the CTA; the n survivors go to
+// the reduce kernel.  Nothing is ever subtracted, no locks, and the record order is deterministic.
+constexpr int REC_CAP = 128;   // parked rows per (CTA, bag, branch); expected ~ n (1 + ln(tiles)) + 25
+struct CandShared {
+  unsigned char flag[128][8];        // per tile row and branch: 0 = takes part in the sums, r + 1 = parked in record r
+  unsigned active[KMAX][REC_CAP / 32];   // bag end: records that are still in the manager's list
+  int cnt[KMAX];                     // bag end: live list entries
+  int app[KMAX];                     // bag end: records appended
 };
+
 // per-unit record of gate constants in smem: {ww[0..KB-1], bv', bu'} padded to CREC floats, where
 // bv' = -2 log2e bv and bu' = -log2e bu are the biases in the exponent domain
 __host__ __device__ constexpr int cst_rec(int kb) { return kb <= 2 ? 4 : (kb <= 6 ? 8 : 10); }
-__host__ __device__ inline SmemMap smem_map(int din) {
+
+// smem carve-up (offsets from the 1024-aligned base)
+struct SmemMap {
+  uint32_t w1, wg, stage, tbuf, ps, cst, cand, bars, total;
+};
+
+__host__ __device__ inline SmemMap smem_map(int din, int kb) {
   SmemMap m;
   m.w1 = 0;
   m.wg = (uint32_t)(din / 64) * 8192u * 2u;
@@ -81,7 +97,8 @@ __host__ __device__ inline SmemMap smem_map(int din) {
   m.tbuf = m.stage + NSTAGE * STAGE_BYTES;
   m.ps = m.tbuf + 8 * 1024;
   m.cst = m.ps + 8 * 512;
-  m.bars = m.cst + 128 * 10 * 4;
+  m.cand = m.cst + 128 * (uint32_t)cst_rec(kb) * 4;
+  m.bars = m.cand + (kb > 6 ? 128u : (uint32_t)sizeof(CandShared));   // K > 6: no masking on this kernel
   m.total = m.bars + 256;
   return m;
 }
@@ -127,7 +144,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int DIN = p.mp.sh.d_in;
   const int NCH = DIN / KC;
-  const SmemMap sm = smem_map(DIN);
+  const SmemMap sm = smem_map(DIN, KB);
   Bars* bars = reinterpret_cast<Bars*>(smem + sm.bars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t cta = cluster_ctarank();
@@ -347,29 +364,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
 
     float l_run[KB], acc[8][KB];     // l_run: per-lane partial of sum exp(score)
-    // candidate lists (unsorted): lane i holds entry i of every branch, its h row is parked in scratch slot i
-    float c_s[KB];
-    int c_i[KB], c_cnt[KB];
-    int s_cur = -1, s_hint = 0, nm = 0, seg_id = 0;
+    CandShared* cs = reinterpret_cast<CandShared*>(smem + sm.cand);
+    const int rcap = seg.rec_cap;
+    float* sc_all = reinterpret_cast<float*>(smem + sm.ps);     // [8 warps][16 rows][8]: scores, later softmax numerators
+    // manager state of branch e_idx (meaningful for e_idx < K): unsorted top-n list, lane i = entry i
+    float mg_s = INFINITY, mg_tau = -INFINITY;
+    int mg_rec = 0, mg_cnt = 0, mg_app = 0, mg_tau_lane = 0;
+    int s_cur = -1, s_hint = 0, nm = 0, seg_id = 0, cb = 0;
     int64_t n_rows = 0;
 
     auto reset_stream = [&](int s) {
       s_cur = s;
-      nm = seg.nm[s];
+      nm = KB > 6 ? 0 : seg.nm[s];
       n_rows = seg.row_off[s + 1] - seg.row_off[s];
       seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 16 + (int)cta * 8 + e_idx;
+      cb = (seg_id - e_idx) >> 3;      // candidate holder of this CTA and bag
+      mg_s = INFINITY;
+      mg_tau = -INFINITY;
+      mg_rec = mg_cnt = mg_app = mg_tau_lane = 0;
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         l_run[k] = 0.f;
-        c_s[k] = INFINITY;      // lanes >= cnt never win the "minimum" search
-        c_i[k] = 0x7fffffff;
-        c_cnt[k] = 0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) acc[g][k] = 0.f;
       }
     };
+    // end of a bag (all 8 epilogue warps call this together)
     auto flush_stream = [&]() {
       if (s_cur < 0) return;
+      if (nm > 0) {
+        const float* rsc = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
+        const int* rix = reinterpret_cast<const int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+        const float* rh = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
+        if (e_idx < K) {     // managers publish which records are still in their list and hand it to the reduce kernel
+          const int k = e_idx;
+#pragma unroll
+          for (int w = 0; w < REC_CAP / 32; ++w) {
+            const unsigned m = __reduce_or_sync(0xffffffffu, (lane < mg_cnt && (mg_rec >> 5) == w) ? (1u << (mg_rec & 31)) : 0u);
+            if (lane == 0) cs->active[k][w] = m;
+          }
+          if (lane == 0) { cs->cnt[k] = mg_cnt; cs->app[k] = mg_app; }
+          int* g_cnt = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt) + (size_t)cb * K;
+          float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)cb * K * cap;
+          int* g_idx = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_idx) + (size_t)cb * K * cap;
+          int* g_slot = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_slot) + (size_t)cb * K * cap;
+          if (lane == 0) g_cnt[k] = mg_cnt;
+          if (lane < cap) {
+            const bool live = lane < mg_cnt;
+            g_score[k * cap + lane] = live ? mg_s : -INFINITY;
+            g_idx[k * cap + lane] = live ? rix[(size_t)k * rcap + mg_rec] : 0x7fffffff;
+            g_slot[k * cap + lane] = live ? mg_rec : 0;
+          }
+        }
+        __threadfence_block();
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // every warp is past the bag's last tile, lists are published
+        // parked rows that did not stay in the CTA's top n rejoin the sums (every 8th record per warp)
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          if (k < K) {
+            const int app = cs->app[k];
+            for (int rec = e_idx; rec < app; rec += 8) {
+              if ((cs->active[k][rec >> 5] >> (rec & 31)) & 1u) continue;
+              const float wgt = ex2_approx(rsc[(size_t)k * rcap + rec] * LOG2E);
+              if (lane == 0) l_run[k] += wgt;
+              if (rs == 0) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) acc[g][k] = fmaf(wgt, rh[((size_t)k * rcap + rec) * L + g * 16 + jf], acc[g][k]);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the shared words may be reused by the next bag
+      } else if (cap > 0 && e_idx == 0 && lane < K) {
+        reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt)[(size_t)cb * K + lane] = 0;
+      }
       float* part = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.part) + (size_t)seg_id * K * (L + 2);
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
@@ -383,24 +451,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           for (int g = 0; g < 8; ++g) {
             const float v = acc[g][k] + __shfl_xor_sync(0xffffffffu, acc[g][k], 16);   // two row subsets
             if (rs == 0) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = v;
-          }
-        }
-      }
-      if (cap > 0) {
-        int* g_cnt = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt) + (size_t)seg_id * K;
-        float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)seg_id * K * cap;
-        int* g_idx = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_idx) + (size_t)seg_id * K * cap;
-        int* g_slot = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_slot) + (size_t)seg_id * K * cap;
-#pragma unroll
-        for (int k = 0; k < KB; ++k) {
-          if (k < K) {
-            if (lane == 0) g_cnt[k] = c_cnt[k];
-            if (lane < cap) {
-              const bool live = lane < c_cnt[k];
-              g_score[k * cap + lane] = live ? c_s[k] : -INFINITY;
-              g_idx[k * cap + lane] = live ? c_i[k] : 0x7fffffff;
-              g_slot[k * cap + lane] = lane;
-            }
           }
         }
       }
@@ -534,78 +584,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         }
       }
 
-      // ---------------- candidates + online softmax ----------------
-      // "representative" lanes: cp == 0 speaks for row a of its group, cp == 1 for row b
+      // ---------------- candidates: rows that beat the CTA's n-th best score are parked ----------------
       float pa[KB], pb[KB];
-      unsigned ex_a = 0u, ex_b = 0u;       // bit k: row a / b of this row group was parked for branch k this tile
+      unsigned ex_a = 0u, ex_b = 0u;       // bit k: row a / b of this row group is parked for branch k
       int slot_a[KB], slot_b[KB];
-      int n_ev[KB], ev_slot[KB];
-      float ev_w[KB];                      // lane e: e-th entry evicted from branch k this tile (score, then weight)
-      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)seg_id * K * cap * L;
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        n_ev[k] = 0;
-        ev_w[k] = -INFINITY;
-        ev_slot[k] = 0;
-        slot_a[k] = slot_b[k] = 0;
-      }
+      for (int k = 0; k < KB; ++k) slot_a[k] = slot_b[k] = 0;
       if (nm > 0) {
-#pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        if (k < K) {
-          const float my_s = cp == 0 ? sa[k] : sb[k];
-          const bool my_valid = cp == 0 ? valid_a : (cp == 1 ? valid_b : false);
-          const int my_row = (int)(cp == 0 ? row_a : row_b);
-          int cnt = c_cnt[k];
-          // threshold = smallest score in a full list
-          float tau = -INFINITY;
-          int tau_lane = 0;
-          if (cnt == nm) {
-            tau = lane < cnt ? c_s[k] : INFINITY;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-            tau_lane = __ffs(__ballot_sync(0xffffffffu, lane < cnt && c_s[k] == tau)) - 1;
-          }
-          unsigned bal = __ballot_sync(0xffffffffu, my_valid && (cnt < nm || my_s > tau));
-          while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float s_new = __shfl_sync(0xffffffffu, my_s, src);
-            const int r_new = __shfl_sync(0xffffffffu, my_row, src);
-            int dst;
-            if (cnt < nm) {
-              dst = cnt++;
-            } else {
-              if (!(s_new > tau)) continue;
-              dst = tau_lane;
-              // the evicted entry rejoins the sums this tile unless it is itself a row of this tile
-              const int old_i = __shfl_sync(0xffffffffu, c_i[k], dst);
-              const bool same_tile = old_i >= (int)(tp.row_in_bag + lane_base) && old_i < (int)(tp.row_in_bag + lane_base + 16);
-              if (same_tile) {
-                const int orow = old_i - (int)(tp.row_in_bag + lane_base);     // 0..15: un-park it
-                if (rg == (orow & 7)) { if (orow < 8) ex_a &= ~(1u << k); else ex_b &= ~(1u << k); }
-              } else {
-                if (lane == n_ev[k]) { ev_w[k] = tau; ev_slot[k] = dst; }
-                ++n_ev[k];
-              }
-            }
-            if (lane == dst) { c_s[k] = s_new; c_i[k] = r_new; }
-            {   // park the new row: every thread of its row group learns the slot
-              const int nrow = r_new - (int)(tp.row_in_bag + lane_base);
-              if (rg == (nrow & 7)) {
-                if (nrow < 8) { ex_a |= 1u << k; slot_a[k] = dst; } else { ex_b |= 1u << k; slot_b[k] = dst; }
-              }
-            }
-            if (cnt == nm) {
-              tau = lane < cnt ? c_s[k] : INFINITY;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-              tau_lane = __ffs(__ballot_sync(0xffffffffu, lane < cnt && c_s[k] == tau)) - 1;
-            }
-          }
-          c_cnt[k] = cnt;
+        // 1. publish this warp's scores ([16 rows][8]) and clear its rows' flags
+        if (cp < 2) {
+          float4 s0, s1;
+          s0.x = cp ? sb[0] : sa[0];
+          s0.y = KB > 1 ? (cp ? sb[KB > 1 ? 1 : 0] : sa[KB > 1 ? 1 : 0]) : 0.f;
+          s0.z = KB > 2 ? (cp ? sb[KB > 2 ? 2 : 0] : sa[KB > 2 ? 2 : 0]) : 0.f;
+          s0.w = KB > 3 ? (cp ? sb[KB > 3 ? 3 : 0] : sa[KB > 3 ? 3 : 0]) : 0.f;
+          s1.x = KB > 4 ? (cp ? sb[KB > 4 ? 4 : 0] : sa[KB > 4 ? 4 : 0]) : 0.f;
+          s1.y = KB > 5 ? (cp ? sb[KB > 5 ? 5 : 0] : sa[KB > 5 ? 5 : 0]) : 0.f;
+          s1.z = s1.w = 0.f;
+          const int prow = rg + 8 * cp;
+          *reinterpret_cast<float4*>(psw + prow * 8) = s0;
+          *reinterpret_cast<float4*>(psw + prow * 8 + 4) = s1;
+          *reinterpret_cast<uint2*>(&cs->flag[lane_base + prow][0]) = make_uint2(0u, 0u);
         }
-      }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // 2. manager of branch k = e_idx looks at all 128 rows of the tile, in row order
+        if (e_idx < K) {
+          const int k = e_idx;
+          float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
+          int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+          auto find_min = [&]() {
+            mg_tau = mg_s;       // lanes >= cnt hold +inf
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mg_tau = fminf(mg_tau, __shfl_xor_sync(0xffffffffu, mg_tau, o));
+            mg_tau_lane = __ffs(__ballot_sync(0xffffffffu, mg_s == mg_tau)) - 1;
+          };
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {      // tile rows 32 i + lane: owned by epilogue warps i (lanes 0-15) and i + 4
+            const int trow = 32 * i + lane;
+            const float sv = sc_all[(i + 4 * (lane >> 4)) * 128 + (lane & 15) * 8 + k];
+            const bool ok = tp.row_in_bag + trow < n_rows;
+            unsigned bal = __ballot_sync(0xffffffffu, ok && (mg_cnt < nm || sv > mg_tau));
+            while (bal) {
+              const int src = __ffs(bal) - 1;
+              bal &= bal - 1;
+              const float s_new = __shfl_sync(0xffffffffu, sv, src);
+              if (mg_cnt == nm && !(s_new > mg_tau)) continue;
+              if (mg_app >= rcap) {       // out of parking slots: poison the result (the reduce kernel writes NaN)
+                if (lane == 0) atomicExch(reinterpret_cast<int*>(p.mp.ws + p.mp.wl.flags), 1);
+                continue;
+              }
+              const int rec = mg_app++;
+              const int dst = mg_cnt < nm ? mg_cnt++ : mg_tau_lane;
+              if (lane == dst) { mg_s = s_new; mg_rec = rec; }
+              if (lane == 0) {
+                rsc[(size_t)k * rcap + rec] = s_new;
+                rix[(size_t)k * rcap + rec] = (int)tp.row_in_bag + 32 * i + src;
+                cs->flag[32 * i + src][k] = (unsigned char)(rec + 1);
+              }
+              if (mg_cnt == nm) find_min();
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // 3. every thread learns which of its two rows are parked, and where
+        {
+          const uint2 fa = *reinterpret_cast<const uint2*>(&cs->flag[lane_base + rg][0]);
+          const uint2 fb = *reinterpret_cast<const uint2*>(&cs->flag[lane_base + rg + 8][0]);
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            const unsigned va = ((k < 4 ? fa.x : fa.y) >> (8 * (k & 3))) & 0xffu;
+            const unsigned vb = ((k < 4 ? fb.x : fb.y) >> (8 * (k & 3))) & 0xffu;
+            if (va) { ex_a |= 1u << k; slot_a[k] = (int)va - 1; }
+            if (vb) { ex_b |= 1u << k; slot_b[k] = (int)vb - 1; }
+          }
+        }
       }
       // softmax numerators against the FIXED reference 0: scores are bounded by B_k = sum_u |ww[k][u]| + |bw[k]|
       // (|tanh * sigmoid| < 1) and acmil_gp_pack only enables this kernel when B_k <= 77, so exp(s) can neither
@@ -616,12 +668,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         pa[k] = take_a ? ex2_approx(sa[k] * LOG2E) : 0.f;
         pb[k] = take_b ? ex2_approx(sb[k] * LOG2E) : 0.f;
         if (cp == 0) l_run[k] += pa[k] + pb[k];       // each row once; lanes are summed at flush
-        if (lane < n_ev[k]) {
-          ev_w[k] = ex2_approx(ev_w[k] * LOG2E);
-          l_run[k] += ev_w[k];
-        } else {
-          ev_w[k] = 0.f;
-        }
       }
       if (cp < 2) {   // p of row a (cp 0) / row b (cp 1) -> smem for the pool
         float4 p0, p1;
@@ -641,27 +687,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       prof[4] += clock64() - t_e3;
       const long long t_e4 = clock64();
 #endif
-      // entries that fell out of a list this tile rejoin the sums; read their parked rows BEFORE this tile's
-      // new entries overwrite the same slots
-      if (nm > 0) {
+      // ---------------- pool: acc[k][:] += sum_rows p[row][k] h[row][:]  (h = hi + lo of the TMEM operand) ----------------
+      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
+      float* t0 = nullptr;
+      float* t1 = nullptr;
+      bool t0b = false, t1b = false;
+      unsigned rest_a = 0u, rest_b = 0u;
+      if (ex_a | ex_b) {
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        if (k < K) {
-          for (int e = 0; e < n_ev[k]; ++e) {
-            const float w = __shfl_sync(0xffffffffu, ev_w[k], e);
-            const int sl = __shfl_sync(0xffffffffu, ev_slot[k], e);
-            if (rs == 0) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) acc[g][k] = fmaf(w, cand_h[((size_t)k * cap + sl) * L + g * 16 + jf], acc[g][k]);
-            }
+        for (int k = 0; k < KB; ++k) {
+          if ((ex_a >> k) & 1u) {
+            float* q = cand_h + ((size_t)k * rcap + slot_a[k]) * L;
+            if (t0 == nullptr) { t0 = q; t0b = false; } else if (t1 == nullptr) { t1 = q; t1b = false; } else rest_a |= 1u << k;
+          }
+          if ((ex_b >> k) & 1u) {
+            float* q = cand_h + ((size_t)k * rcap + slot_b[k]) * L;
+            if (t0 == nullptr) { t0 = q; t0b = true; } else if (t1 == nullptr) { t1 = q; t1b = true; } else rest_b |= 1u << k;
           }
         }
       }
-      }
-      __syncwarp();
-
-      // ---------------- pool: acc[k][:] += sum_rows p[row][k] h[row][:]  (h = hi + lo of the TMEM operand) ----------------
-      const bool parking = (ex_a | ex_b) != 0u;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {     // 16-feature chunk g (unrolled: acc[g] must stay in registers; keep the body small)
         uint32_t hh[4], hl[4];
@@ -680,11 +724,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           const int fsw = fcol ^ (((rg >> 1) & 1) << 3);     // rows of equal parity land in different bank groups
           *reinterpret_cast<float2*>(tbuf + rg * 16 + fsw) = fa;
           *reinterpret_cast<float2*>(tbuf + (rg + 8) * 16 + fsw) = fb;
-          if (parking) {   // park rows that entered a list this tile
+          // park rows that entered a list this tile: two precomputed targets cover practically every case
+          if (t0 != nullptr) *reinterpret_cast<float2*>(t0 + g * 16 + fcol) = t0b ? fb : fa;
+          if (t1 != nullptr) *reinterpret_cast<float2*>(t1 + g * 16 + fcol) = t1b ? fb : fa;
+          if (rest_a | rest_b) {   // a row group parked in more than two (row, branch) pairs: generic path
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
-              if ((ex_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * cap + sel_k(slot_a, k)) * L + g * 16 + fcol) = fa;
-              if ((ex_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * cap + sel_k(slot_b, k)) * L + g * 16 + fcol) = fb;
+              if ((rest_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_a, k)) * L + g * 16 + fcol) = fa;
+              if ((rest_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_b, k)) * L + g * 16 + fcol) = fb;
             }
           }
         }
@@ -900,10 +947,12 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
   if ((int64_t)total_pt * (sm_count / 2 + 1) >= (int64_t)0x7fffffff) return -1;   // 32-bit partition arithmetic
   int ncl = sm_count / 2;
   if (ncl > total_pt) ncl = total_pt;
-  if (cap > 0 && ncl * 16 * cap > GP_MAX_SEG_CAND) ncl = GP_MAX_SEG_CAND / (16 * cap);   // reduce kernel's smem bound
+  if (cap > 0 && ncl * 2 * cap > GP_MAX_SEG_CAND) ncl = GP_MAX_SEG_CAND / (2 * cap);   // reduce kernel's smem bound
   if (ncl < 1) ncl = 1;
   t->u_nclusters = ncl;
   t->n_masked_cap = cap;
+  t->cand_div = 8;                      // one candidate holder per CTA and bag = 8 epilogue-warp segments
+  t->rec_cap = cap > 0 ? REC_CAP : 0;
   // segments: 16 per (cluster, bag) pair that intersects (2 CTAs x 8 epilogue warps)
   int seg = 0;
   for (int s = 0; s < b.n_slides; ++s) {
@@ -957,9 +1006,12 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  const size_t smem = smem_map(s.d_in).total + 1024;
-  const int grid = p.seg.u_nclusters * 2;
   const int K = s.n_branch;
+  ACMIL_REQUIRE(K <= 6 || p.seg.n_masked_cap == 0, ACMIL_E_UNSUPPORTED,
+                "tcgen05 kernel: masking with more than 6 branches is not supported (use ACMIL_IMPL_FFMA)");
+  const size_t smem = smem_map(s.d_in, K == 1 ? 1 : (K <= 5 ? 5 : 8)).total + 1024;
+  const int grid = p.seg.u_nclusters * 2;
+  ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, 16, st));
   if (K == 1) return launch_kb<1>(up, grid, smem, st);
   if (K <= 5) return launch_kb<5>(up, grid, smem, st);
   return launch_kb<8>(up, grid, smem, st);
