@@ -88,7 +88,8 @@ struct GpSegTable {
   int32_t nm[SMAX];              // candidates tracked per branch = min(n_masked, local rows)
   // tcgen05 kernel only: bags are cut into 256-row pair-tiles, cluster c owns the global pair-tiles
   // [c * u_total_pt / u_nclusters, (c + 1) * u_total_pt / u_nclusters); every (cluster, bag) it touches
-  // produces 16 segments (2 CTAs x 8 epilogue warps): seg_begin[s] + (c - u_cfirst[s]) * 16 + cta * 8 + warp
+  // produces 2 segments (one per CTA; its 8 epilogue warps merge their partials in shared memory):
+  // seg_begin[s] + (c - u_cfirst[s]) * 2 + cta
   // candidate bookkeeping: lists live per "candidate holder" = group of cand_div consecutive segments
   // (FFMA: every segment; tcgen05: one per CTA and bag = 8 segments); each holder owns cand lists of
   // n_masked_cap entries per branch and rec_cap parked h rows per branch
@@ -160,8 +161,8 @@ static inline GpWorkspace gp_workspace_layout(const acmil_gp_shape& s, const GpS
   w.cand_score = take(ncb * K * cap * 4);
   w.cand_idx = take(ncb * K * cap * 4);
   w.cand_slot = take(ncb * K * cap * 4);
-  w.rec_score = take(t.cand_div > 1 ? ncb * K * rcap * 4 : 0);
-  w.rec_idx = take(t.cand_div > 1 ? ncb * K * rcap * 4 : 0);
+  w.rec_score = take(ncb * K * rcap * 4);
+  w.rec_idx = take(ncb * K * rcap * 4);
   w.cand_h = take(ncb * K * rcap * L * 4);
   w.flags = take(256);
   w.total_bytes = o + 256;

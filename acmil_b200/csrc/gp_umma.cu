@@ -22,6 +22,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "gp_common.cuh"
 #include "sm100.cuh"
 
@@ -233,36 +235,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       const uint32_t w1_hi = smem_u32(smem + sm.w1), w1_lo = w1_hi + p.w1_part_bytes;
       const uint32_t wg_hi = smem_u32(smem + sm.wg), wg_lo = wg_hi + 32768u;
       uint32_t xc = 0;  // x-operand chunks consumed so far (ring position / phase)
-      auto g1_chunks = [&](int t, int c_begin, int c_end) {
-        for (int c = c_begin; c < c_end; ++c, ++xc) {
-          if (c == 0 && t > 0) {  // D1 of the previous tile must have been drained by the epilogue
-            { PROF_T0(); mbar_wait_cluster(&bars->d1_empty, (uint32_t)(t - 1) & 1u); PROF_ADD(1); }
-            tc_fence_after();
-          }
-          const uint32_t q = xc % NXOP, ph = (xc / NXOP) & 1u;
-          { PROF_T0(); mbar_wait_cluster(&bars->xop_full[q], ph); PROF_ADD(2); }
-          tc_fence_after();
-          const uint32_t xa_hi = tm + TM_X + q * 32, xa_lo = xa_hi + 16;
-          const uint32_t boff = (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 64u;
+      // chunk c of tile t of the projection GEMM; returns false (nothing issued) when its inputs are not there yet
+      auto g1_try = [&](int t, int c) -> bool {
+        if (c == 0 && t > 0 && !mbar_test_wait(&bars->d1_empty, (uint32_t)(t - 1) & 1u)) return false;   // D1 drained?
+        const uint32_t q = xc % NXOP, ph = (xc / NXOP) & 1u;
+        if (!mbar_test_wait(&bars->xop_full[q], ph)) return false;
+        tc_fence_after();
+        const uint32_t xa_hi = tm + TM_X + q * 32, xa_lo = xa_hi + 16;
+        const uint32_t boff = (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 64u;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
-            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
-            umma_ts<2>(tm + TM_D1, xa_lo + ks * 8, bhi, idesc, 1u);
-            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, blo, idesc, 1u);
-          }
-          umma_commit_2sm(&bars->xop_empty[q], 3);
-          if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
+          umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
+          umma_ts<2>(tm + TM_D1, xa_lo + ks * 8, bhi, idesc, 1u);
+          umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, blo, idesc, 1u);
         }
+        umma_commit_2sm(&bars->xop_empty[q], 3);
+        if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
+        ++xc;
+        return true;
       };
       const uint32_t idesc64 = umma_idesc_f16(256, 64);
       // gate GEMM in four 32-unit quarters (N = 64: 32 V + 32 U columns) ping-ponging between two D2 buffers,
       // so the epilogue works on one quarter while the tensor core produces the next
-      auto g2_quarter = [&](int t, int qr) {
+      auto g2_try = [&](int t, int qr) -> bool {
         const int b = qr & 1;
-        if (qr == 0) { PROF_T0(); mbar_wait_cluster(&bars->hop_full, (uint32_t)t & 1u); PROF_ADD(3); }
+        if (qr == 0 && !mbar_test_wait(&bars->hop_full, (uint32_t)t & 1u)) return false;
         const uint32_t n_use = 2u * (uint32_t)t + (uint32_t)(qr >> 1);      // how often buffer b was used before
-        if (n_use > 0) { PROF_T0(); mbar_wait_cluster(&bars->d2_empty[b], (n_use - 1u) & 1u); PROF_ADD(4); }
+        if (n_use > 0 && !mbar_test_wait(&bars->d2_empty[b], (n_use - 1u) & 1u)) return false;
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -273,14 +273,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, blo, idesc64, 1u);
         }
         umma_commit_2sm(&bars->d2_full[b], 3);
+        return true;
       };
-      g1_chunks(0, 0, NCH);
+      // issue order: the gate quarters of tile t have priority (the epilogue is waiting for them); chunks of the
+      // next tile's projection fill the gaps while the epilogue drains a D2 buffer
+      for (int c = 0; c < NCH;) c += g1_try(0, c) ? 1 : 0;
       for (int t = 0; t < T; ++t) {
-        g2_quarter(t, 0);
-        g2_quarter(t, 1);
-        g2_quarter(t, 2);
-        g2_quarter(t, 3);
-        if (t + 1 < T) g1_chunks(t + 1, 0, NCH);
+        int qr = 0, c = 0;
+        const int nc = (t + 1 < T) ? NCH : 0;
+        while (qr < 4 || c < nc) {
+          if (qr < 4 && g2_try(t, qr)) { ++qr; continue; }
+          if (c < nc && g1_try(t + 1, c)) { ++c; continue; }
+        }
       }
 #if GP_UMMA_PROF
       prof[7] = clock64() - t_start;
@@ -377,8 +381,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       s_cur = s;
       nm = KB > 6 ? 0 : seg.nm[s];
       n_rows = seg.row_off[s + 1] - seg.row_off[s];
-      seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 16 + (int)cta * 8 + e_idx;
-      cb = (seg_id - e_idx) >> 3;      // candidate holder of this CTA and bag
+      seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 2 + (int)cta;   // one segment per CTA and bag
+      cb = seg_id;                     // ... which is also its candidate holder
       mg_s = INFINITY;
       mg_tau = -INFINITY;
       mg_rec = mg_cnt = mg_app = mg_tau_lane = 0;
@@ -438,19 +442,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       } else if (cap > 0 && e_idx == 0 && lane < K) {
         reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt)[(size_t)cb * K + lane] = 0;
       }
-      float* part = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.part) + (size_t)seg_id * K * (L + 2);
+      // fold the two row subsets / the lanes of each warp, then tree-merge the 8 warps' partials through shared
+      // memory (the transpose + numerator buffers are idle here): one record per CTA and bag
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
-        if (k < K) {
-          const float lt = warp_sum(l_run[k]);
-          if (lane == 0) {
-            part[(size_t)k * (L + 2) + 0] = 0.f;     // softmax reference point of this kernel
-            part[(size_t)k * (L + 2) + 1] = lt;
-          }
+        l_run[k] = warp_sum(l_run[k]);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float v = acc[g][k] + __shfl_xor_sync(0xffffffffu, acc[g][k], 16);   // two row subsets
-            if (rs == 0) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = v;
+        for (int g = 0; g < 8; ++g) acc[g][k] += __shfl_xor_sync(0xffffffffu, acc[g][k], 16);
+      }
+      {
+        float* xbuf = reinterpret_cast<float*>(smem + sm.tbuf);          // 12 KB: tbuf (8 KB) + ps (4 KB)
+        constexpr int PF = KB * 129;                                     // floats of one warp partial: {l, acc[128]} per branch
+        constexpr int MAXSLOT = (12288 / 4) / PF >= 4 ? 4 : ((12288 / 4) / PF >= 2 ? 2 : 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");                   // everybody is done with tbuf / ps
+#pragma unroll 1
+        for (int stride = 4; stride >= 1; stride >>= 1) {
+#pragma unroll 1
+          for (int base = 0; base < stride; base += MAXSLOT) {
+            const int w_lo = stride + base, w_hi = stride + min(base + MAXSLOT, stride);
+            if (e_idx >= w_lo && e_idx < w_hi) {
+              float* slot = xbuf + (e_idx - w_lo) * PF;
+#pragma unroll
+              for (int k = 0; k < KB; ++k) {
+                if (lane == 0) slot[k * 129] = l_run[k];
+                if (rs == 0) {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g) slot[k * 129 + 1 + g * 16 + jf] = acc[g][k];
+                }
+              }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (e_idx >= base && e_idx < base + (w_hi - w_lo)) {
+              const float* slot = xbuf + (e_idx - base) * PF;
+#pragma unroll
+              for (int k = 0; k < KB; ++k) {
+                l_run[k] += slot[k * 129];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) acc[g][k] += slot[k * 129 + 1 + g * 16 + jf];
+              }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+        }
+      }
+      if (e_idx == 0) {
+        float* part = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.part) + (size_t)seg_id * K * (L + 2);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          if (k < K) {
+            if (lane == 0) {
+              part[(size_t)k * (L + 2) + 0] = 0.f;     // softmax reference point of this kernel
+              part[(size_t)k * (L + 2) + 1] = l_run[k];
+            }
+            if (rs == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = acc[g][k];
+            }
           }
         }
       }
@@ -706,12 +753,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
       }
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {     // 16-feature chunk g (unrolled: acc[g] must stay in registers; keep the body small)
-        uint32_t hh[4], hl[4];
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + g * 8, hh);
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + g * 8, hl);
-        tmem_wait_ld();
+      // 16-feature chunks, TMEM loads of chunk g + 1 in flight while chunk g is transposed and accumulated
+      auto pool_chunk = [&](const uint32_t (&hh)[4], const uint32_t (&hl)[4], auto gc) {
+        constexpr int g = decltype(gc)::value;
         // this thread holds features 8 ii + 2 cp + {0,1} of the chunk for rows rg (a) and rg + 8 (b)
 #pragma unroll
         for (int ii = 0; ii < 2; ++ii) {
@@ -757,6 +801,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
         __syncwarp();
+      };
+      {
+        uint32_t hhA[4], hlA[4], hhB[4], hlB[4];
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI, hhA);
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO, hlA);
+#define POOL_PAIR(G)                                                            \
+        tmem_wait_ld();                                                         \
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + ((G) + 1) * 8, hhB);       \
+        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + ((G) + 1) * 8, hlB);       \
+        pool_chunk(hhA, hlA, std::integral_constant<int, (G)>{});               \
+        tmem_wait_ld();                                                         \
+        if ((G) + 2 < 8) {                                                      \
+          tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + ((G) + 2) * 8, hhA);     \
+          tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + ((G) + 2) * 8, hlA);     \
+        }                                                                       \
+        pool_chunk(hhB, hlB, std::integral_constant<int, (G) + 1>{});
+        POOL_PAIR(0)
+        POOL_PAIR(2)
+        POOL_PAIR(4)
+        POOL_PAIR(6)
+#undef POOL_PAIR
       }
 #if GP_UMMA_PROF
       prof[5] += clock64() - t_e4;
@@ -951,9 +1016,9 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
   if (ncl < 1) ncl = 1;
   t->u_nclusters = ncl;
   t->n_masked_cap = cap;
-  t->cand_div = 8;                      // one candidate holder per CTA and bag = 8 epilogue-warp segments
+  t->cand_div = 1;                      // one segment (and candidate holder) per CTA and bag
   t->rec_cap = cap > 0 ? REC_CAP : 0;
-  // segments: 16 per (cluster, bag) pair that intersects (2 CTAs x 8 epilogue warps)
+  // segments: 2 per (cluster, bag) pair that intersects (one per CTA)
   int seg = 0;
   for (int s = 0; s < b.n_slides; ++s) {
     t->seg_begin[s] = seg;
@@ -968,7 +1033,7 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
       }
     }
     t->u_cfirst[s] = first < 0 ? 0 : first;
-    seg += 16 * count;
+    seg += 2 * count;
   }
   t->seg_begin[b.n_slides] = seg;
   t->n_seg = seg;
