@@ -66,27 +66,30 @@ __device__ float block_sum(float v, float* red) {
   return r;
 }
 
-__global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
+// One CTA of 1024 threads per (bag, branch).  Latency is what matters here (a few hundred KB at most):
+// warp 0 selects the rank's top-n candidates while warps 1..31 merge the segment partials, then all 32 warps
+// add the unselected candidates back; each warp covers the 128 features with one float4 per lane.
+constexpr int RR = 1024;
+__global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ float r_s[RT / 32];
-  __shared__ int r_i[RT / 32], r_p[RT / 32];
-  __shared__ float red[RT / 32];
-  __shared__ float wsum[RT / 32][32];
+  __shared__ float red[RR / 32];
   __shared__ int sel_pos[NMAX];
+  __shared__ int s_nsel;
 
   const int L = p.sh.d_inner, K = p.sh.n_branch;
-  const int FC = L / 32;
-  const int fc = blockIdx.x % FC, k = (blockIdx.x / FC) % K, s = blockIdx.x / (FC * K);
+  const int k = blockIdx.x % K, s = blockIdx.x / K;
   const int seg0 = p.seg.seg_begin[s], nseg = p.seg.seg_begin[s + 1] - seg0;
   const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap, rcap = p.seg.rec_cap, cdiv = p.seg.cand_div;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cb0 = seg0 / cdiv, ncb = nseg / cdiv;      // candidate holders of this bag
   const int ncand = ncb * nm;
+  const int nq = L / 4;                                // float4 groups per row (<= 128 for L <= 512)
 
   float* c_score = reinterpret_cast<float*>(dsm);
   int* c_idx = reinterpret_cast<int*>(c_score + ncand);
   int* c_slot = c_idx + ncand;
   int* c_sel = c_slot + ncand;
+  float4* wacc = reinterpret_cast<float4*>(dsm + (((size_t)ncand * 16 + 15) / 16) * 16);   // [32 warps][nq]
 
   const float* part = reinterpret_cast<const float*>(p.ws + p.wl.part);
   const int* g_cnt = reinterpret_cast<const int*>(p.ws + p.wl.cand_cnt);
@@ -95,102 +98,126 @@ __global__ void __launch_bounds__(RT) gp_reduce_kernel(const __grid_constant__ G
   const int* g_slot = reinterpret_cast<const int*>(p.ws + p.wl.cand_slot);
   const float* g_h = reinterpret_cast<const float*>(p.ws + p.wl.cand_h);
 
-  // ---- 1. gather this (bag, branch)'s candidates ----
-  int my_valid = 0;
-  for (int c = tid; c < ncand; c += RT) {
+  // ---- 1. candidates of this (bag, branch) -> smem; reference point m* = max over everything ----
+  float mx = -INFINITY;
+  for (int c = tid; c < ncand; c += RR) {
     const int sg = c / nm, i = c % nm;
     const size_t g = ((size_t)(cb0 + sg) * K + k) * cap + i;
     const bool live = i < g_cnt[(size_t)(cb0 + sg) * K + k];
-    c_score[c] = live ? g_score[g] : -INFINITY;
+    const float sc = live ? g_score[g] : -INFINITY;
+    c_score[c] = sc;
     c_idx[c] = live ? g_idx[g] : 0x7fffffff;
     c_slot[c] = live ? g_slot[g] : -1;
     c_sel[c] = 0;
-    my_valid += live ? 1 : 0;
+    mx = fmaxf(mx, sc);
   }
-  const int total = (int)(block_sum((float)my_valid, red) + 0.5f);
-  const int nsel = min(nm, total);
+  for (int sg = tid; sg < nseg; sg += RR) mx = fmaxf(mx, part[((size_t)(seg0 + sg) * K + k) * (L + 2)]);
+  const float mstar = block_max(mx, red);      // (contains a __syncthreads: the smem lists are visible)
 
-  // ---- 2. this rank's top-nsel (sorted: score desc, index asc) ----
-  for (int round = 0; round < nsel; ++round) {
-    float bs = -INFINITY;
-    int bi = 0x7fffffff, bp = -1;
-    for (int c = tid; c < ncand; c += RT) {
-      if (c_slot[c] >= 0 && !c_sel[c] && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
-        bs = c_score[c]; bi = c_idx[c]; bp = c;
+  float4 a4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ls = 0.f;
+  int nsel = 0;
+  if (warp == 0) {
+    // ---- 2a. this rank's top-n (sorted: score desc, index asc), warp-level only ----
+    int live = 0;
+    for (int c = lane; c < ncand; c += 32) live += c_slot[c] >= 0 ? 1 : 0;
+    live = (int)(warp_sum((float)live) + 0.5f);
+    nsel = min(nm, live);
+    for (int round = 0; round < nsel; ++round) {
+      float bs = -INFINITY;
+      int bi = 0x7fffffff, bp = -1;
+      for (int c = lane; c < ncand; c += 32) {
+        if (c_slot[c] >= 0 && !c_sel[c] && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
+          bs = c_score[c]; bi = c_idx[c]; bp = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
+      }
+      if (lane == 0) { sel_pos[round] = bp; c_sel[bp] = 1; }
+      __syncwarp();
+    }
+  } else {
+    // ---- 2b. segment partials (independent loads, 4 in flight per lane) ----
+    for (int sg = warp - 1; sg < nseg; sg += RR / 32 - 1) {
+      const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
+      const float m = pr[0];
+      const float w = m == -INFINITY ? 0.f : expf(m - mstar);
+      if (lane == 0) ls += w * pr[1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qd = lane + 32 * j;
+        if (qd < nq) {
+          const float2 u0 = *reinterpret_cast<const float2*>(pr + 2 + qd * 4);      // rows are 8-byte aligned (L + 2 floats)
+          const float2 u1 = *reinterpret_cast<const float2*>(pr + 2 + qd * 4 + 2);
+          a4[j].x = fmaf(w, u0.x, a4[j].x); a4[j].y = fmaf(w, u0.y, a4[j].y);
+          a4[j].z = fmaf(w, u1.x, a4[j].z); a4[j].w = fmaf(w, u1.y, a4[j].w);
+        }
       }
     }
-    const int win = block_argbest(bs, bi, bp, r_s, r_i, r_p);
-    if (tid == 0) { sel_pos[round] = win; c_sel[win] = 1; }
-    __syncthreads();
   }
+  if (tid == 0) s_nsel = nsel;      // known to warp 0 only
+  __syncthreads();
+  nsel = s_nsel;
 
-  // ---- 3. m*, l ----
-  float mx = -INFINITY;
-  for (int sg = tid; sg < nseg; sg += RT) mx = fmaxf(mx, part[((size_t)(seg0 + sg) * K + k) * (L + 2)]);
-  for (int c = tid; c < ncand; c += RT)
-    if (c_slot[c] >= 0 && !c_sel[c]) mx = fmaxf(mx, c_score[c]);
-  const float mstar = block_max(mx, red);
-  float ls = 0.f;
-  for (int sg = tid; sg < nseg; sg += RT) {
-    const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
-    if (pr[0] != -INFINITY) ls += expf(pr[0] - mstar) * pr[1];
-  }
-  for (int c = tid; c < ncand; c += RT)
-    if (c_slot[c] >= 0 && !c_sel[c]) ls += expf(c_score[c] - mstar);
-  const float lstar = block_sum(ls, red);
-
-  // ---- 4. acc for this 32-feature chunk ----
-  const int jf = fc * 32 + lane;
-  float a = 0.f;
-  for (int sg = warp; sg < nseg; sg += RT / 32) {
-    const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
-    const float m = pr[0];
-    if (m != -INFINITY) a = fmaf(expf(m - mstar), pr[2 + jf], a);
-  }
-  for (int c = warp; c < ncand; c += RT / 32) {
+  // ---- 3. candidates that were not selected rejoin the sums ----
+  for (int c = warp; c < ncand; c += RR / 32) {
     if (c_slot[c] >= 0 && !c_sel[c]) {
       const int sg = c / nm;
-      a = fmaf(expf(c_score[c] - mstar), g_h[(((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L + jf], a);
+      const float w = expf(c_score[c] - mstar);
+      if (lane == 0) ls += w;
+      const float* hr = g_h + (((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qd = lane + 32 * j;
+        if (qd < nq) {
+          const float4 u = *reinterpret_cast<const float4*>(hr + qd * 4);
+          a4[j].x = fmaf(w, u.x, a4[j].x); a4[j].y = fmaf(w, u.y, a4[j].y);
+          a4[j].z = fmaf(w, u.z, a4[j].z); a4[j].w = fmaf(w, u.w, a4[j].w);
+        }
+      }
     }
   }
-  wsum[warp][lane] = a;
-  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int qd = lane + 32 * j;
+    if (qd < nq) wacc[warp * nq + qd] = a4[j];
+  }
+  const float lstar = block_sum(ls, red);
 
   float* rec = p.record + (size_t)s * p.rec.stride();
-  if (warp == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < RT / 32; ++w) t += wsum[w][lane];
-    rec[p.rec.acc() + (size_t)k * L + jf] = t;
+  for (int qd = tid; qd < nq; qd += RR) {      // fixed-order sum over the 32 warps: deterministic
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < RR / 32; ++w) {
+      const float4 u = wacc[w * nq + qd];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* dst = rec + p.rec.acc() + (size_t)k * L + qd * 4;
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
   }
-  // ---- 5. rank list ----
+  // ---- 4. rank list: scores, global indices and h rows of the selected candidates ----
   const int nmc = p.rec.nmc;
-  for (int i = warp; i < nmc; i += RT / 32) {
-    float hv = 0.f;
-    if (i < nsel) {
-      const int c = sel_pos[i];
-      const int sg = c / nm;
-      hv = g_h[(((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L + jf];
+  for (int i = warp; i < nmc; i += RR / 32) {
+    const bool on = i < nsel;
+    const int c = on ? sel_pos[i] : 0;
+    const float* hr = on ? g_h + (((size_t)(cb0 + c / nm) * K + k) * rcap + c_slot[c]) * L : nullptr;
+    for (int jf = lane; jf < L; jf += 32) rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = on ? hr[jf] : 0.f;
+    if (lane == 0) {
+      rec[p.rec.score() + (size_t)k * nmc + i] = on ? c_score[c] : -INFINITY;
+      reinterpret_cast<int*>(rec)[p.rec.idx() + (size_t)k * nmc + i] = on ? c_idx[c] + (int)p.seg.shard_begin[s] : 0x7fffffff;
     }
-    rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = hv;
   }
-  if (fc == 0) {
-    if (tid == 0) {
-      const int overflow = *reinterpret_cast<const int*>(p.ws + p.wl.flags);
-      rec[p.rec.m() + k] = overflow ? NAN : mstar;      // a holder ran out of parking slots: fail loudly
-      rec[p.rec.l() + k] = lstar;
-      reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
-    }
-    for (int i = tid; i < nmc; i += RT) {
-      float sc = -INFINITY;
-      int gi = 0x7fffffff;
-      if (i < nsel) {
-        sc = c_score[sel_pos[i]];
-        gi = c_idx[sel_pos[i]] + (int)p.seg.shard_begin[s];
-      }
-      rec[p.rec.score() + (size_t)k * nmc + i] = sc;
-      reinterpret_cast<int*>(rec)[p.rec.idx() + (size_t)k * nmc + i] = gi;
-    }
+  if (tid == 0) {
+    const int overflow = *reinterpret_cast<const int*>(p.ws + p.wl.flags);
+    rec[p.rec.m() + k] = overflow ? NAN : mstar;      // a holder ran out of parking slots: fail loudly
+    rec[p.rec.l() + k] = lstar;
+    reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
   }
 }
 
@@ -271,51 +298,67 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
           p.a_out[(size_t)k * p.a_ld + p.row_off[s] + loc] = MASK_FILL;
       }
     }
-  }
-  __syncthreads();
-
-  // ---- 2. per branch: m*, l*, afeat ----
-  for (int k = 0; k < K; ++k) {
-    float mx = -INFINITY;
-    for (int r = tid; r < P; r += RT) mx = fmaxf(mx, recp(r)[p.rec.m() + k]);
-    for (int e = tid; e < ne; e += RT) {
-      const int f = e_flag[k * ne + e];
-      if (f == 1 || f == 2) mx = fmaxf(mx, e_score[k * ne + e]);
-      if (f == 3) mx = fmaxf(mx, MASK_FILL);
-    }
-    const float mstar = block_max(mx, red);
-    float ls = 0.f;
-    for (int r = tid; r < P; r += RT) {
-      const float* rc = recp(r);
-      if (rc[p.rec.m() + k] != -INFINITY) ls += expf(rc[p.rec.m() + k] - mstar) * rc[p.rec.l() + k];
-    }
-    for (int e = tid; e < ne; e += RT) {
-      const int f = e_flag[k * ne + e];
-      if (f == 1 || f == 2) ls += expf(e_score[k * ne + e] - mstar);
-      if (f == 3) ls += expf(MASK_FILL - mstar);
-    }
-    const float lstar = block_sum(ls, red);
-    if (tid == 0) { s_m[k] = mstar; s_l[k] = lstar; }
-    for (int jf = tid; jf < L; jf += RT) {
-      float a = 0.f;
-      for (int r = 0; r < P; ++r) {
-        const float* rc = recp(r);
-        const float m = rc[p.rec.m() + k];
-        if (m != -INFINITY) a = fmaf(expf(m - mstar), rc[p.rec.acc() + (size_t)k * L + jf], a);
-      }
-      for (int e = 0; e < ne; ++e) {
+    // ---- 2. same warp: m*, l*, afeat of branch k (no block-level synchronisation per branch) ----
+    __syncwarp();
+    {
+      float mx = -INFINITY;
+      for (int r = lane; r < P; r += 32) mx = fmaxf(mx, recp(r)[p.rec.m() + k]);
+      for (int e = lane; e < ne; e += 32) {
         const int f = e_flag[k * ne + e];
-        if (f == 0) continue;
-        const float sc = f == 3 ? MASK_FILL : e_score[k * ne + e];
-        const float w = expf(sc - mstar);
-        if (w != 0.f) {
-          const int r = e / nmc, i = e % nmc;
-          a = fmaf(w, recp(r)[p.rec.h() + ((size_t)k * nmc + i) * L + jf], a);
+        if (f == 1 || f == 2) mx = fmaxf(mx, e_score[k * ne + e]);
+        if (f == 3) mx = fmaxf(mx, MASK_FILL);
+      }
+      const float mstar = warp_max(mx);
+      float ls = 0.f;
+      for (int r = lane; r < P; r += 32) {
+        const float* rc = recp(r);
+        if (rc[p.rec.m() + k] != -INFINITY) ls += expf(rc[p.rec.m() + k] - mstar) * rc[p.rec.l() + k];
+      }
+      for (int e = lane; e < ne; e += 32) {
+        const int f = e_flag[k * ne + e];
+        float w = 0.f;
+        if (f == 1 || f == 2) w = expf(e_score[k * ne + e] - mstar);
+        if (f == 3) w = expf(MASK_FILL - mstar);
+        e_score[k * ne + e] = w;            // from here on the slot holds the entry's softmax numerator
+        ls += w;
+      }
+      const float lstar = warp_sum(ls);
+      if (lane == 0) { s_m[k] = mstar; s_l[k] = lstar; }
+      __syncwarp();
+      const float inv_l = 1.f / lstar;
+      for (int j0 = 0; j0 < L; j0 += 128) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < P; ++r) {
+          const float* rc = recp(r);
+          const float m = rc[p.rec.m() + k];
+          const float w = m == -INFINITY ? 0.f : expf(m - mstar);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jf = j0 + lane + 32 * j;
+            if (jf < L) a[j] = fmaf(w, rc[p.rec.acc() + (size_t)k * L + jf], a[j]);
+          }
+        }
+        for (int e = 0; e < ne; ++e) {
+          const float w = e_score[k * ne + e];
+          if (w != 0.f) {
+            const float* hr = recp(e / nmc) + p.rec.h() + ((size_t)k * nmc + e % nmc) * L;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int jf = j0 + lane + 32 * j;
+              if (jf < L) a[j] = fmaf(w, hr[jf], a[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jf = j0 + lane + 32 * j;
+          if (jf < L) {
+            const float v = a[j] * inv_l;
+            af[(size_t)k * L + jf] = v;
+            if (p.out.d_afeat) p.out.d_afeat[((size_t)s * K + k) * L + jf] = v;
+          }
         }
       }
-      const float v = a / lstar;
-      af[(size_t)k * L + jf] = v;
-      if (p.out.d_afeat) p.out.d_afeat[((size_t)s * K + k) * L + jf] = v;
     }
   }
   __syncthreads();
@@ -461,21 +504,21 @@ int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_recor
   p.seg = mp.seg;
   p.rec = rec;
   p.record = d_record;
-  const int S = mp.seg.n_slides, K = mp.sh.n_branch, FC = mp.sh.d_inner / 32;
+  const int S = mp.seg.n_slides, K = mp.sh.n_branch;
   if (S == 0) return ACMIL_OK;
   int max_cand = 0;
   for (int s = 0; s < S; ++s) {
     const int c = (mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]) / mp.seg.cand_div * mp.seg.nm[s];
     if (c > max_cand) max_cand = c;
   }
-  const size_t smem = (size_t)max_cand * 16 + 16;
-  ACMIL_REQUIRE(smem <= 200 * 1024, ACMIL_E_INVALID, "reduce: too many candidates per bag (%d)", max_cand);
+  const size_t smem = (((size_t)max_cand * 16 + 15) / 16) * 16 + (size_t)(RR / 32) * mp.sh.d_inner * 4 + 32;
+  ACMIL_REQUIRE(smem <= 220 * 1024, ACMIL_E_INVALID, "reduce: too many candidates per bag (%d)", max_cand);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gp_reduce_kernel<<<S * K * FC, RT, smem, st>>>(p);
+  gp_reduce_kernel<<<S * K, RR, smem, st>>>(p);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
