@@ -82,7 +82,8 @@ struct CandShared {
   int app[KMAX];                     // bag end: records appended
 };
 
-// per-unit record of gate constants in smem: {ww[0..KB-1], bv', bu'} padded to CREC floats, where
+// gate constants in smem, one record of 2 CREC floats per pair of adjacent units (2c, 2c+1), laid out as fp32 pairs
+// for the packed FFMA2 path: {ww[k][2c], ww[k][2c+1]} for k < KB, then the bv' pair and the bu' pair, where
 // bv' = -2 log2e bv and bu' = -log2e bu are the biases in the exponent domain
 __host__ __device__ constexpr int cst_rec(int kb) { return kb <= 2 ? 4 : (kb <= 6 ? 8 : 10); }
 
@@ -178,11 +179,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
   {
     constexpr int CREC = cst_rec(KB);
     float* cst = reinterpret_cast<float*>(smem + sm.cst);
-    for (int u = tid; u < 128; u += UT) {
+    for (int u = tid; u < 128; u += UT) {      // record of the unit pair (2c, 2c+1): {ww[k][2c], ww[k][2c+1]}_k, bv' pair, bu' pair
+      float* rec = cst + (u >> 1) * (2 * CREC) + (u & 1);
 #pragma unroll
-      for (int k = 0; k < KB; ++k) cst[u * CREC + k] = p.c.ww[k][u];
-      cst[u * CREC + KB] = p.c.bv[u] * (-2.f * LOG2E);
-      cst[u * CREC + KB + 1] = p.c.bu[u] * (-LOG2E);
+      for (int k = 0; k < KB; ++k) rec[2 * k] = p.c.ww[k][u];
+      rec[2 * KB] = p.c.bv[u] * (-2.f * LOG2E);
+      rec[2 * KB + 2] = p.c.bu[u] * (-LOG2E);
     }
   }
   if (warp == 2) {
@@ -552,40 +554,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #endif
 
       // ---------------- Epi2: gate + scores (each thread: 2 rows x 32 units per tile) ----------------
-      float sa[KB], sb[KB];
+      // packed fp32 (FFMA2 / FADD2 / FMUL2): each 64-bit value holds the two adjacent units a thread owns in a row
+      uint64_t sa2[KB], sb2[KB];
 #pragma unroll
-      for (int k = 0; k < KB; ++k) sa[k] = sb[k] = 0.f;
+      for (int k = 0; k < KB; ++k) sa2[k] = sb2[k] = 0ull;
       // one 32-unit quarter of the gate: V columns [0, 32), U columns [32, 64) of a D2 buffer; this thread owns
-      // units unit0 + 8 ii + 2 cp + j (ii < 4, j < 2) of rows a and b
+      // units unit0 + 8 ii + 2 cp + {0, 1} (ii < 4) of rows a and b
       auto gate_quarter = [&](const uint32_t (&zv)[16], const uint32_t (&zu)[16], int unit0) {
+        const uint64_t cva2 = pack2(cva, cva), cua2 = pack2(cua, cua), one2 = pack2(1.f, 1.f), mone2 = pack2(-1.f, -1.f);
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
+          const float* rec = cstp + ((unit0 >> 1) + ii * 4 + cp) * (2 * CREC);
+          uint64_t cr2[CREC];      // [0, KB): score weights, KB: bv', KB + 1: bu'
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float* rec = cstp + (unit0 + ii * 8 + cp * 2 + j) * CREC;
-            float cr[CREC];
-            if constexpr (CREC == 10) {
+          for (int w = 0; w < CREC / 2; ++w) {
+            const float4 v = *reinterpret_cast<const float4*>(rec + 4 * w);
+            cr2[2 * w] = pack2(v.x, v.y);
+            cr2[2 * w + 1] = pack2(v.z, v.w);
+          }
+          // tanh(a) sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)), Ea = e^-2a, Eb = e^-b.  Ea's exponent is clamped so
+          // that (1 - Ea) stays finite; Eb may overflow to +inf: the quotient is then (finite) * 0 = 0, the limit.
+          // D2 holds Sg z: the scales and biases are folded into the exponent-domain constants
 #pragma unroll
-              for (int w = 0; w < 5; ++w) *reinterpret_cast<float2*>(&cr[2 * w]) = *reinterpret_cast<const float2*>(rec + 2 * w);
+          for (int r = 0; r < 2; ++r) {
+            const uint64_t xa = fma2(pack2(__uint_as_float(zv[4 * ii + 2 * r]), __uint_as_float(zv[4 * ii + 2 * r + 1])), cva2, cr2[KB]);
+            const uint64_t xb = fma2(pack2(__uint_as_float(zu[4 * ii + 2 * r]), __uint_as_float(zu[4 * ii + 2 * r + 1])), cua2, cr2[KB + 1]);
+            const uint64_t ea = pack2(ex2_approx(fminf(lo2(xa), 57.7f)), ex2_approx(fminf(hi2(xa), 57.7f)));
+            const uint64_t eb = pack2(ex2_approx(lo2(xb)), ex2_approx(hi2(xb)));
+            const uint64_t den = mul2(add2(ea, one2), add2(eb, one2));
+            const uint64_t g = mul2(fma2(ea, mone2, one2), pack2(rcp_approx(lo2(den)), rcp_approx(hi2(den))));
+            if (r == 0) {
+#pragma unroll
+              for (int k = 0; k < KB; ++k) sa2[k] = fma2(g, cr2[k], sa2[k]);
             } else {
 #pragma unroll
-              for (int w = 0; w < CREC / 4; ++w) *reinterpret_cast<float4*>(&cr[4 * w]) = *reinterpret_cast<const float4*>(rec + 4 * w);
-            }
-            // tanh(a) sigmoid(b) = (1 - Ea) / ((1 + Ea)(1 + Eb)), Ea = e^-2a, Eb = e^-b (exponents clamped at 40);
-            // D2 holds Sg z: the scales and biases are folded into the exponent-domain constants
-            {
-              const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[4 * ii + j]), cva, cr[KB]), 57.7f));
-              const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[4 * ii + j]), cua, cr[KB + 1]), 57.7f));
-              const float g = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
-#pragma unroll
-              for (int k = 0; k < KB; ++k) sa[k] = fmaf(g, cr[k], sa[k]);
-            }
-            {
-              const float ea = ex2_approx(fminf(fmaf(__uint_as_float(zv[4 * ii + 2 + j]), cva, cr[KB]), 57.7f));
-              const float eb = ex2_approx(fminf(fmaf(__uint_as_float(zu[4 * ii + 2 + j]), cua, cr[KB + 1]), 57.7f));
-              const float g = (1.f - ea) * rcp_approx((1.f + ea) * (1.f + eb));
-#pragma unroll
-              for (int k = 0; k < KB; ++k) sb[k] = fmaf(g, cr[k], sb[k]);
+              for (int k = 0; k < KB; ++k) sb2[k] = fma2(g, cr2[k], sb2[k]);
             }
           }
         }
@@ -604,9 +607,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         if (lane == 0) mbar_arrive_cluster(&bars->d2_empty[b], 0);   // buffer b is in registers: the MMA warp may refill it
         gate_quarter(zv, zu, qr * 32);
       }
-      // the 4 threads of a row group hold disjoint unit subsets: finish the dot products
+      // even + odd units, then the 4 threads of a row group hold disjoint unit subsets: finish the dot products
+      float sa[KB], sb[KB];
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
+        sa[k] = lo2(sa2[k]) + hi2(sa2[k]);
+        sb[k] = lo2(sb2[k]) + hi2(sb2[k]);
         sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], 1);
         sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 1);
         sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], 2);

@@ -292,7 +292,10 @@ def run_ours(a):
     achieved = algo_bytes / (main_avg_ms * 1e-3) / 1e9 if main_avg_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        wl = tr.get("workload", {})
+        if wl.get("bags_per_launch") == a.slides and wl.get("rows_per_bag") == a.rows and wl.get("d_feat") == D_FEAT:
+            traffic = tr.get(a.mode, {}).get("dram_bytes_per_launch")      # ncu capture of this exact launch shape
     except Exception:
         pass
     line = {
