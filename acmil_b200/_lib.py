@@ -57,7 +57,29 @@ class GpOutputs(C.Structure):
         "d_sub", "d_slide", "d_afeat", "d_bag_feat", "d_lse_m", "d_lse_l", "d_topk_idx", "d_masked_idx")]
 
 
-# every symbol include/acmil_b200.h declares: (restype, argtypes)
+class GemmDesc(C.Structure):
+    """acmil_gemm_desc (include/acmil_transmil.h)."""
+    _fields_ = ([(n, C.c_void_p) for n in ("a", "b", "c", "ct", "bias", "addend", "split_ws")]
+                + [(n, C.c_int32) for n in ("m", "n", "k", "batch")]
+                + [(n, C.c_int64) for n in ("lda", "ldb", "ldc", "ldct", "ld_addend", "a_batch_stride", "b_batch_stride",
+                                            "c_batch_stride", "ct_batch_stride", "addend_batch_stride")]
+                + [("col_block_width", C.c_int32), ("k_split", C.c_int32), ("col_block_stride", C.c_int64),
+                   ("alpha", C.c_float), ("beta", C.c_float), ("diag", C.c_float), ("relu", C.c_int32),
+                   ("precise", C.c_int32), ("reserved", C.c_int32 * 3)])
+
+
+class NystromShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "n", "dim", "heads", "dim_head", "num_landmarks", "pinv_iterations", "residual", "conv_kernel",
+        "n_out", "padded_out", "precise")] + [("reserved", C.c_int32 * 4)]
+
+
+class NystromWeights(C.Structure):
+    _fields_ = [("d_ln_w", C.c_void_p), ("d_ln_b", C.c_void_p), ("ln_eps", C.c_float), ("reserved", C.c_int32),
+                ("d_wqkv", C.c_void_p), ("d_wout", C.c_void_p), ("d_bout", C.c_void_p), ("d_wconv", C.c_void_p)]
+
+
+# every symbol include/*.h declares: (restype, argtypes)
 _SIZE_P = C.POINTER(C.c_size_t)
 SYMBOLS = {
     "acmil_last_error": (C.c_char_p, []),
@@ -79,6 +101,15 @@ SYMBOLS = {
     "acmil_gp_attn_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "acmil_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    # include/acmil_transmil.h
+    "acmil_gemm_nt": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "acmil_layernorm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_int64, C.c_void_p]),
+    "acmil_nystrom_workspace_bytes": (C.c_int, [C.POINTER(NystromShape), _SIZE_P]),
+    "acmil_nystrom_attn_fwd": (C.c_int, [C.POINTER(NystromShape), C.POINTER(NystromWeights), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_ppeg_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lock = threading.Lock()

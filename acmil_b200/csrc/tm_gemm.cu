@@ -1,0 +1,370 @@
+// tm_gemm.cu -- batched fp32 "NT" GEMM on tcgen05 for the TransMIL / Nystrom path:
+//
+//      C[b] = alpha * A[b] (M x K)  *  B[b]^T (N x K)   (+ diag * I) (+ bias[col]) (+ addend) (relu)
+//
+// Both operands are fp32, K contiguous (nn.Linear weights, q/k/v rows, attention rows).  The reference computes every one
+// of these products in IEEE fp32 (torch.matmul / einsum / nn.Linear: nystrom_attention.py:83,119-121,135,147 and
+// transMIL.py:61,89), so the tensor-core path is an error-compensated TF32 split
+//      a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo ,   a_hi = a & 0xFFFFE000 (a valid TF32), a_lo = a - a_hi (exact)
+// i.e. 3 kind::tf32 MMAs per product with fp32 accumulation in TMEM (~2^-21 relative).  PRECISE = false runs one
+// MMA on the raw operands (plain TF32, ~2^-10).
+//
+// One CTA per 128 x BN output tile, 192 threads:
+//   warp 0     TMA producer: 128 x 32 fp32 boxes of A and B (SWIZZLE_128B, 3-D maps: K, rows, batch), 3-stage ring
+//   warp 1     MMA issuer (one elected thread), accumulator in TMEM, tcgen05.commit frees the ring stage
+//   warps 2-5  split each landed stage in place into hi (masked) and lo tiles, then run the epilogue:
+//              thread = row (tcgen05.ld 32x32b), scale / diagonal / bias / addend / relu, optional second store of the
+//              transposed tile (the Moore-Penrose iteration needs every product in both orientations).
+#include <cuda.h>
+
+#include "acmil_transmil.h"
+#include "gp_common.cuh"
+#include "sm100.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int GT = 192;          // threads per CTA
+constexpr int BM = 128;          // tile rows
+constexpr int KC = 32;           // fp32 columns per stage = one 128-byte swizzle row
+constexpr int NST = 3;           // ring stages
+constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 16 KB
+
+struct GemmParams {
+  CUtensorMap ta, tb;            // (K, rows, batch) fp32
+  float* c;
+  float* ct;                     // optional transposed copy: ct[b] + col * ldct + row
+  const float* bias;             // [N] or null
+  const float* addend;           // optional, addressed like a plain row-major C with ld = ld_add
+  int M, N, K;
+  int a_batched, b_batched;      // 0: the operand is shared by all batch entries
+  long long c_batch_stride, ldc;
+  int cbw;                       // column blocks: element (row, col) of batch b lives at
+  long long cbs;                 //   c + b * c_batch_stride + (col / cbw) * cbs + row * ldc + col % cbw
+  long long ct_batch_stride, ldct;
+  long long add_batch_stride, ld_add;
+  float alpha, beta, diag;
+  int relu;
+  int vec_ok;                    // float4 stores are legal for c
+  int ksplit;                    // > 1: blockIdx.z = batch * ksplit + split; raw partial tiles go to split_ws
+  int k_per_split;               // multiple of KC
+  float* split_ws;               // [batch * ksplit][M][N]
+};
+
+struct Bars {
+  uint64_t full[NST];            // TMA bytes landed
+  uint64_t split[NST];           // hi/lo tiles written (4 converter warps)
+  uint64_t empty[NST];           // MMAs that read the stage have completed
+  uint64_t acc_full;
+  uint32_t tmem;
+};
+
+__host__ __device__ constexpr uint32_t tf32_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// smem: per stage {A hi, B hi, A lo, B lo}; B tiles hold BN rows
+template <int BN>
+__host__ __device__ constexpr uint32_t stage_bytes(bool precise) {
+  return (TILE_BYTES + (uint32_t)BN * KC * 4) * (precise ? 2u : 1u);
+}
+
+template <int BN, bool PRECISE>
+__global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t B_BYTES = (uint32_t)BN * KC * 4;
+  constexpr uint32_t STAGE = stage_bytes<BN>(PRECISE);
+  Bars* bars = reinterpret_cast<Bars*>(smem + NST * STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int bz = p.ksplit > 1 ? blockIdx.z / p.ksplit : blockIdx.z;
+  const int kbeg = p.ksplit > 1 ? (blockIdx.z % p.ksplit) * p.k_per_split : 0;
+  const int kend = p.ksplit > 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
+  const int nchunk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 4);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.ta);
+    tma_prefetch_desc(&p.tb);
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(&bars->tmem, BN < 32 ? 32 : BN);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = bars->tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < nchunk; ++c) {
+        const int s = c % NST;
+        const uint32_t ph = (uint32_t)(c / NST) & 1u;
+        mbar_wait(&bars->empty[s], ph ^ 1u);
+        unsigned char* st = smem + s * STAGE;
+        mbar_expect_tx(&bars->full[s], TILE_BYTES + B_BYTES);
+        tma_load_3d(st, &p.ta, kbeg + c * KC, m0, p.a_batched ? bz : 0, &bars->full[s]);
+        tma_load_3d(st + TILE_BYTES, &p.tb, kbeg + c * KC, n0, p.b_batched ? bz : 0, &bars->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tf32_idesc(BM, BN);
+      for (int c = 0; c < nchunk; ++c) {
+        const int s = c % NST;
+        const uint32_t ph = (uint32_t)(c / NST) & 1u;
+        mbar_wait(PRECISE ? &bars->split[s] : &bars->full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES;
+        const uint32_t a_lo = b_hi + B_BYTES, b_lo = a_lo + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row
+          const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+          if constexpr (PRECISE) {
+            umma_tf32(tm, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
+            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
+          } else {
+            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+          }
+        }
+        umma_commit(&bars->empty[s]);
+      }
+      if (nchunk > 0) umma_commit(&bars->acc_full);
+      else mbar_arrive(&bars->acc_full);          // empty K range (k-split tail): the tile is all zeros
+    }
+  } else {
+    const int cw = warp - 2;                     // 0..3
+    if constexpr (PRECISE) {
+      // hi/lo split in place: same swizzled position in the lo tile, so no address arithmetic beyond the offset
+      const int ct = cw * 32 + lane;             // 0..127
+      constexpr int NV = (TILE_BYTES + B_BYTES) / 16;      // float4 slots of {A, B}
+      for (int c = 0; c < nchunk; ++c) {
+        const int s = c % NST;
+        const uint32_t ph = (uint32_t)(c / NST) & 1u;
+        mbar_wait(&bars->full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE);
+        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE + TILE_BYTES + B_BYTES);
+#pragma unroll 4
+        for (int i = ct; i < NV; i += 128) {
+          const float4 v = hi[i];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          hi[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->split[s]);
+      }
+    }
+    // ---------------- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 ----------------
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    float* crow = p.c ? p.c + (size_t)bz * p.c_batch_stride + (size_t)row * p.ldc : nullptr;
+    const float* arow = p.addend ? p.addend + (size_t)bz * p.add_batch_stride + (size_t)row * p.ld_add : nullptr;
+    float* ctb = p.ct ? p.ct + (size_t)bz * p.ct_batch_stride + row : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_wait_ld();
+      if (n0 + c0 >= p.N) continue;
+      if (p.ksplit > 1) {
+        if (row_ok) {
+          float* dst = p.split_ws + ((size_t)blockIdx.z * p.M + row) * p.N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
+        }
+        continue;
+      }
+      float r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + c0 + j;
+        float t = p.alpha * __uint_as_float(v[j]);
+        if (p.diag != 0.f && col == row) t += p.diag;
+        if (p.bias && col < p.N) t += p.bias[col];
+        r[j] = t;
+      }
+      if (row_ok) {
+        if (arow) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) r[j] = fmaf(p.beta, arow[n0 + c0 + j], r[j]);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
+        }
+        if (crow) {
+          if (p.vec_ok && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int col = n0 + c0 + j;
+              float* dst = crow + (size_t)(col / p.cbw) * p.cbs + col % p.cbw;
+              *reinterpret_cast<float4*>(dst) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
+            }
+          }
+        }
+        if (ctb) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tm, BN < 32 ? 32 : BN);
+}
+
+// k-split: sum the partial tiles in a fixed order, then the same epilogue terms
+__global__ void __launch_bounds__(256) tm_gemm_split_reduce_kernel(const __grid_constant__ GemmParams p, int batch) {
+  const size_t total = (size_t)batch * p.M * p.N;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int col = (int)(e % p.N);
+    const int row = (int)((e / p.N) % p.M);
+    const int bz = (int)(e / ((size_t)p.M * p.N));
+    float acc = 0.f;
+    for (int s = 0; s < p.ksplit; ++s) acc += p.split_ws[(((size_t)bz * p.ksplit + s) * p.M + row) * p.N + col];
+    float t = p.alpha * acc;
+    if (p.diag != 0.f && col == row) t += p.diag;
+    if (p.bias) t += p.bias[col];
+    if (p.addend) t = fmaf(p.beta, p.addend[(size_t)bz * p.add_batch_stride + (size_t)row * p.ld_add + col], t);
+    if (p.relu) t = fmaxf(t, 0.f);
+    if (p.c) p.c[(size_t)bz * p.c_batch_stride + (size_t)(col / p.cbw) * p.cbs + (size_t)row * p.ldc + col % p.cbw] = t;
+    if (p.ct) p.ct[(size_t)bz * p.ct_batch_stride + (size_t)col * p.ldct + row] = t;
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn tm_get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeFn)ptr;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const float* base, int rows, int K, long long ld, int batch, long long batch_stride, int box_rows,
+             const char* what) {
+  EncodeFn enc = tm_get_encode();
+  ACMIL_REQUIRE(enc != nullptr, ACMIL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  ACMIL_REQUIRE(((uintptr_t)base & 15) == 0 && ld % 4 == 0 && (batch <= 1 || batch_stride % 4 == 0), ACMIL_E_INVALID,
+                "gemm: operand %s must be 16-byte aligned with leading dimensions that are multiples of 4 floats", what);
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * ld) * 4};
+  cuuint32_t box[3] = {KC, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed for %s (%d)", what, (int)r);
+  return ACMIL_OK;
+}
+
+template <int BN, bool PRECISE>
+int launch(const GemmParams& gp, int batch, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = (size_t)NST * stage_bytes<BN>(PRECISE) + sizeof(Bars) + 1024;
+  if (!configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_gemm_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((gp.N + BN - 1) / BN, (gp.M + BM - 1) / BM, batch * (gp.ksplit > 1 ? gp.ksplit : 1));
+  tm_gemm_kernel<BN, PRECISE><<<grid, GT, smem, st>>>(gp);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  if (gp.ksplit > 1) {
+    const size_t total = (size_t)batch * gp.M * gp.N;
+    tm_gemm_split_reduce_kernel<<<(unsigned)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, st>>>(gp, batch);
+    ++g_acmil_launches;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+  }
+  return ACMIL_OK;
+}
+
+}  // namespace
+
+int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0 && d.batch > 0, ACMIL_E_INVALID, "gemm: empty problem (%d x %d x %d, batch %d)", d.m,
+                d.n, d.k, d.batch);
+  ACMIL_REQUIRE(d.a && d.b && (d.c || d.ct), ACMIL_E_INVALID, "gemm: null operand");
+  const int ksplit = d.k_split > 1 ? d.k_split : 1;
+  ACMIL_REQUIRE((long long)d.batch * ksplit <= 65535 && (d.m + BM - 1) / BM <= 65535, ACMIL_E_INVALID, "gemm: grid too large");
+  ACMIL_REQUIRE(ksplit == 1 || d.split_ws != nullptr, ACMIL_E_INVALID, "gemm: k_split needs split_ws");
+  GemmParams gp{};
+  const int bn = d.n <= 64 ? 64 : 128;
+  int rc = make_map(&gp.ta, d.a, d.m, d.k, d.lda, d.a_batch_stride ? d.batch : 1, d.a_batch_stride, BM, "A");
+  if (rc) return rc;
+  rc = make_map(&gp.tb, d.b, d.n, d.k, d.ldb, d.b_batch_stride ? d.batch : 1, d.b_batch_stride, bn, "B");
+  if (rc) return rc;
+  gp.c = d.c; gp.ct = d.ct; gp.bias = d.bias; gp.addend = d.addend;
+  gp.M = d.m; gp.N = d.n; gp.K = d.k;
+  gp.a_batched = d.a_batch_stride != 0; gp.b_batched = d.b_batch_stride != 0;
+  gp.c_batch_stride = d.c_batch_stride; gp.ldc = d.ldc;
+  gp.cbw = d.col_block_width > 0 ? d.col_block_width : d.n;
+  gp.cbs = d.col_block_width > 0 ? d.col_block_stride : 0;
+  gp.ct_batch_stride = d.ct_batch_stride; gp.ldct = d.ldct;
+  gp.add_batch_stride = d.addend_batch_stride; gp.ld_add = d.ld_addend;
+  gp.alpha = d.alpha; gp.beta = d.beta; gp.diag = d.diag; gp.relu = d.relu;
+  gp.ksplit = ksplit;
+  gp.k_per_split = ((((d.k + KC - 1) / KC) + ksplit - 1) / ksplit) * KC;
+  gp.split_ws = d.split_ws;
+  gp.vec_ok = d.c != nullptr && ((uintptr_t)d.c & 15) == 0 && d.ldc % 4 == 0 && gp.cbw % 4 == 0 && gp.cbs % 4 == 0 &&
+              d.c_batch_stride % 4 == 0;
+  if (d.precise) return bn == 64 ? launch<64, true>(gp, d.batch, st) : launch<128, true>(gp, d.batch, st);
+  return bn == 64 ? launch<64, false>(gp, d.batch, st) : launch<128, false>(gp, d.batch, st);
+}
+
+extern "C" int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream) {
+  ACMIL_REQUIRE(desc != nullptr, ACMIL_E_INVALID, "gemm: null descriptor");
+  return tm_gemm(*desc, (cudaStream_t)stream);
+}

@@ -1,0 +1,519 @@
+// tm_ops.cu -- the non-GEMM kernels of the TransMIL / Nystrom path and the composite forward:
+//   NystromAttention.forward (architecture/nystrom_attention.py:67-140, mask = None, return_attn = False)
+//   PPEG.forward             (architecture/transMIL.py:38-45)
+//   nn.LayerNorm             (architecture/transMIL.py:11, 58)
+// All products run through tm_gemm (3xTF32 on tcgen05); this file holds the memory-bound glue.
+#include <algorithm>
+#include <utility>
+
+#include "acmil_transmil.h"
+#include "gp_common.cuh"
+
+int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim, one warp per row (two-pass variance like the reference's fp32 kernel).
+// w == nullptr: plain copy (no norm).
+__global__ void __launch_bounds__(256) tm_layernorm_kernel(const float* __restrict__ x, long long ldx, long long rows, int dim,
+                                                           const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                                           float* __restrict__ out, long long ldo) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float* orow = out + row * ldo;
+  if (w == nullptr) {
+    for (int j = lane; j < dim; j += 32) orow[j] = xr[j];
+    return;
+  }
+  float s = 0.f;
+  for (int j = lane; j < dim; j += 32) s += xr[j];
+  const float mean = warp_sum(s) / (float)dim;
+  float v = 0.f;
+  for (int j = lane; j < dim; j += 32) {
+    const float t = xr[j] - mean;
+    v = fmaf(t, t, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)dim + eps);
+  for (int j = lane; j < dim; j += 32) orow[j] = (xr[j] - mean) * rstd * w[j] + (b ? b[j] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// landmarks: dst[hd][j][:] = sum_{t < l} src[hd][j * l + t][:] / l      (nystrom_attention.py:98-114)
+__global__ void __launch_bounds__(256) tm_landmark_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_pad, int m,
+                                                          int l, int d) {
+  const int j = blockIdx.x, hd = blockIdx.y;
+  const float* s = src + ((size_t)hd * n_pad + (size_t)j * l) * d;
+  // threads: (dd, part); the parts' partial sums are combined through smem in a fixed order
+  __shared__ float red[256];
+  const int parts = 256 / d > 0 ? 256 / d : 1;
+  const int dd = threadIdx.x % d, part = threadIdx.x / d;
+  float acc = 0.f;
+  if (part < parts)
+    for (int t = part; t < l; t += parts) acc += s[(size_t)t * d + dd];
+  red[threadIdx.x] = part < parts ? acc : 0.f;
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * d + threadIdx.x];
+    dst[((size_t)hd * m + j) * d + threadIdx.x] = t / (float)l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// in-place softmax over rows of length len <= 1024: one warp per row, the row lives in registers
+__global__ void __launch_bounds__(256) tm_softmax_small_kernel(float* __restrict__ a, long long rows, int len) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = a + row * len;
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < len ? r[j] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = lane + 32 * i < len ? expf(v[i] - mx) : 0.f;
+    s += v[i];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (lane + 32 * i < len) r[lane + 32 * i] = v[i] / s;
+}
+
+// in-place softmax over long rows: one CTA per row, three passes (the row stays in L2)
+__global__ void __launch_bounds__(1024) tm_softmax_long_kernel(float* __restrict__ a, long long len) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  float* r = a + (size_t)blockIdx.x * len;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (long long j = tid; j < len; j += 1024) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_max(red[lane]);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  mx = bc;
+  float s = 0.f;
+  for (long long j = tid; j < len; j += 1024) {
+    const float e = expf(r[j] - mx);
+    r[j] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_sum(red[lane]);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  s = bc;
+  for (long long j = tid; j < len; j += 1024) r[j] = r[j] / s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Moore-Penrose start value (nystrom_attention.py:12-19): z0 = x^T / (max_i sum_j |x_ij| * max_j sum_i |x_ij|),
+// the maxima taken over ALL batch entries and heads (torch.max of the whole tensor).
+__global__ void __launch_bounds__(256) tm_pinv_sums_kernel(const float* __restrict__ x, int m, int* __restrict__ scal) {
+  const float* xh = x + (size_t)blockIdx.x * m * m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float best = 0.f;
+  if (blockIdx.y == 0) {      // row sums: a warp per row
+    for (int i = warp; i < m; i += 8) {
+      float s = 0.f;
+      for (int j = lane; j < m; j += 32) s += fabsf(xh[(size_t)i * m + j]);
+      best = fmaxf(best, warp_sum(s));
+    }
+  } else {                    // column sums: a thread per column
+    for (int j = tid; j < m; j += 256) {
+      float s = 0.f;
+      for (int i = 0; i < m; ++i) s += fabsf(xh[(size_t)i * m + j]);
+      best = fmaxf(best, s);
+    }
+    best = warp_max(best);
+  }
+  if (lane == 0) atomicMax(&scal[blockIdx.y], __float_as_int(best));      // non-negative floats order like ints
+}
+
+__global__ void __launch_bounds__(256) tm_pinv_init_kernel(const float* __restrict__ x, int m, const int* __restrict__ scal,
+                                                           float* __restrict__ z, float* __restrict__ zt) {
+  __shared__ float tile[32][33];
+  const float denom = __int_as_float(scal[0]) * __int_as_float(scal[1]);
+  const size_t base = (size_t)blockIdx.z * m * m;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;
+    float v = 0.f;
+    if (i < m && j < m) {
+      v = x[base + (size_t)i * m + j] / denom;
+      zt[base + (size_t)i * m + j] = v;      // z^T = x / denom
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + tx;
+    if (i < m && j < m) z[base + (size_t)j * m + i] = tile[tx][r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depth-wise residual conv of the values along the sequence (nystrom_attention.py:62-65, 137-138):
+//   merged[b][i][c] += sum_t w[c / d][t] * v[b][c][i + t - ks/2]     with v stored transposed, vt[b][c][i]
+// tile: 32 channels x 64 positions per CTA; reads are coalesced along i, writes along c
+constexpr int CONV_TP = 64;
+__global__ void __launch_bounds__(256) tm_resconv_kernel(const float* __restrict__ vt, const float* __restrict__ w,
+                                                         float* __restrict__ merged, int n_pad, int inner, int d, int ks,
+                                                         int row0, int nrows) {
+  extern __shared__ float tile[];                 // [32][span], span odd
+  const int half = ks / 2;
+  const int span = (CONV_TP + ks - 1) | 1;
+  const int i0 = row0 + blockIdx.x * CONV_TP, c0 = blockIdx.y * 32, bz = blockIdx.z;
+  const float* vb = vt + ((size_t)bz * inner + c0) * n_pad;
+  for (int e = threadIdx.x; e < 32 * (CONV_TP + ks - 1); e += 256) {
+    const int c = e / (CONV_TP + ks - 1), o = e % (CONV_TP + ks - 1);
+    const int i = i0 + o - half;
+    tile[c * span + o] = (c0 + c < inner && i >= 0 && i < n_pad) ? vb[(size_t)c * n_pad + i] : 0.f;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  if (c0 + cx >= inner) return;
+  const float* wh = w + (size_t)((c0 + cx) / d) * ks;
+  for (int o = py; o < CONV_TP; o += 8) {
+    const int i = i0 + o;
+    if (i >= row0 + nrows) break;
+    float acc = 0.f;
+    for (int t = 0; t < ks; ++t) acc = fmaf(__ldg(wh + t), tile[cx * span + o + t], acc);
+    merged[((size_t)bz * n_pad + i) * inner + c0 + cx] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PPEG (transMIL.py:38-45): out = feat + conv7(feat) + conv5(feat) + conv3(feat) on the [gh, gw] token grid,
+// channels last.  The three depth-wise kernels and the identity are summed into one 7x7 stencil per channel
+// (exact up to fp32 summation order).  thread = (channel, position run); 49 weights in registers.
+__global__ void __launch_bounds__(256) tm_ppeg_kernel(const float* __restrict__ x, int gh, int gw, int C, const float* __restrict__ w7,
+                                                      const float* __restrict__ b7, const float* __restrict__ w5,
+                                                      const float* __restrict__ b5, const float* __restrict__ w3,
+                                                      const float* __restrict__ b3, float* __restrict__ out, int pos_per_cta) {
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx, bz = blockIdx.z;
+  const size_t tok = (size_t)gh * gw + 1;
+  const float* xb = x + (size_t)bz * tok * C;
+  float* ob = out + (size_t)bz * tok * C;
+  if (c >= C) return;
+  if (blockIdx.x == 0 && py == 0) ob[c] = xb[c];      // class token passes through
+  float wk[49];
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      float t = w7[(size_t)c * 49 + dy * 7 + dx];
+      if (dy >= 1 && dy <= 5 && dx >= 1 && dx <= 5) t += w5[(size_t)c * 25 + (dy - 1) * 5 + (dx - 1)];
+      if (dy >= 2 && dy <= 4 && dx >= 2 && dx <= 4) t += w3[(size_t)c * 9 + (dy - 2) * 3 + (dx - 2)];
+      if (dy == 3 && dx == 3) t += 1.f;
+      wk[dy * 7 + dx] = t;
+    }
+  const float bias = b7[c] + b5[c] + b3[c];
+  const float* feat = xb + C;
+  const int p0 = blockIdx.x * pos_per_cta;
+  for (int o = py; o < pos_per_cta; o += 8) {
+    const int pos = p0 + o;
+    if (pos >= gh * gw) break;
+    const int y = pos / gw, xx = pos % gw;
+    float acc = bias;
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+      const int yy = y + dy - 3;
+      if (yy < 0 || yy >= gh) continue;
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const int xq = xx + dx - 3;
+        if (xq < 0 || xq >= gw) continue;
+        acc = fmaf(wk[dy * 7 + dx], feat[((size_t)yy * gw + xq) * C + c], acc);
+      }
+    }
+    ob[(size_t)(1 + pos) * C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct NysLayout {      // float offsets into the workspace
+  size_t xn, q, k, vt, ql, kl, a2, y, yt, t1t, t2t, za, zta, zb, ztb, kvt, wt, sbuf, merged, split, scal, total;
+  int n_pad, l, pad, inner, H;
+  int ksplit;
+};
+
+size_t align64(size_t v) { return (v + 63) & ~(size_t)63; }
+
+NysLayout nys_layout(const acmil_nystrom_shape& s) {
+  NysLayout L{};
+  const int m = s.num_landmarks;
+  L.l = (s.n + m - 1) / m;
+  L.n_pad = s.n % m ? m * L.l : s.n;
+  L.pad = L.n_pad - s.n;
+  L.inner = s.heads * s.dim_head;
+  L.H = s.batch * s.heads;
+  const size_t d = s.dim_head, np = L.n_pad, H = L.H;
+  // K split of the (attn3 v) product: enough CTAs to cover the GPU (2 tiles per batch entry otherwise)
+  L.ksplit = (int)std::max<size_t>(1, std::min<size_t>(64, (np / 32) / 48));
+  size_t o = 0;
+  auto take = [&](size_t n) { const size_t r = o; o += align64(n); return r; };
+  L.xn = take((size_t)s.batch * np * s.dim);
+  L.q = take(H * np * d);
+  L.k = take(H * np * d);
+  L.vt = take(H * d * np);
+  L.ql = take(H * m * d);
+  L.kl = take(H * m * d);
+  const size_t mm = H * (size_t)m * m;
+  L.a2 = take(mm); L.y = take(mm); L.yt = take(mm); L.t1t = take(mm); L.t2t = take(mm);
+  L.za = take(mm); L.zta = take(mm); L.zb = take(mm); L.ztb = take(mm);
+  L.kvt = take(H * d * m);
+  L.wt = take(H * d * m);
+  L.sbuf = take(H * np * m);
+  L.merged = take((size_t)s.batch * np * L.inner);
+  L.split = take((size_t)L.ksplit * H * d * m);
+  L.scal = take(64);
+  L.total = o;
+  return L;
+}
+
+int check_shape(const acmil_nystrom_shape& s) {
+  ACMIL_REQUIRE(s.batch >= 1 && s.n >= 1 && s.dim >= 4 && s.dim % 4 == 0, ACMIL_E_INVALID,
+                "nystrom: bad x shape [%d, %d, %d] (dim must be a multiple of 4)", s.batch, s.n, s.dim);
+  ACMIL_REQUIRE(s.heads >= 1 && s.dim_head >= 4 && s.dim_head % 4 == 0 && s.dim_head <= 256, ACMIL_E_INVALID,
+                "nystrom: dim_head %d must be a multiple of 4 in [4, 256]", s.dim_head);
+  ACMIL_REQUIRE(s.num_landmarks >= 4 && s.num_landmarks % 4 == 0 && s.num_landmarks <= 1024, ACMIL_E_INVALID,
+                "nystrom: num_landmarks %d must be a multiple of 4 in [4, 1024]", s.num_landmarks);
+  ACMIL_REQUIRE(s.pinv_iterations >= 0 && s.n_out >= 0 && s.n_out <= s.n, ACMIL_E_INVALID, "nystrom: bad pinv_iterations / n_out");
+  ACMIL_REQUIRE(!s.residual || (s.conv_kernel >= 1 && s.conv_kernel % 2 == 1 && s.conv_kernel <= 129), ACMIL_E_INVALID,
+                "nystrom: residual conv kernel %d must be odd and <= 129", s.conv_kernel);
+  ACMIL_REQUIRE((long long)s.batch * s.heads <= 1024, ACMIL_E_INVALID, "nystrom: batch * heads too large");
+  return ACMIL_OK;
+}
+
+acmil_gemm_desc gemm0(int precise) {
+  acmil_gemm_desc g{};
+  g.alpha = 1.f;
+  g.precise = precise;
+  return g;
+}
+
+}  // namespace
+
+extern "C" int acmil_layernorm_rows(const float* d_x, int64_t ldx, int64_t rows, int32_t dim, const float* d_w, const float* d_b,
+                                    float eps, float* d_out, int64_t ldo, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_x && d_out && rows >= 0 && dim >= 1, ACMIL_E_INVALID, "layernorm: bad arguments");
+  if (rows == 0) return ACMIL_OK;
+  tm_layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, rows, dim, d_w, d_b, eps, d_out, ldo);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32_t gw, int32_t c, const float* d_w7, const float* d_b7,
+                              const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3, float* d_out,
+                              void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_x && d_out && d_w7 && d_b7 && d_w5 && d_b5 && d_w3 && d_b3, ACMIL_E_INVALID, "ppeg: null pointer");
+  ACMIL_REQUIRE(batch >= 1 && gh >= 1 && gw >= 1 && c >= 1 && batch <= 65535, ACMIL_E_INVALID, "ppeg: bad shape");
+  const int ppc = 64;
+  dim3 grid((gh * gw + ppc - 1) / ppc, (c + 31) / 32, batch);
+  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, ppc);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_nystrom_workspace_bytes(const acmil_nystrom_shape* shape, size_t* bytes) {
+  ACMIL_REQUIRE(shape && bytes, ACMIL_E_INVALID, "nystrom: null argument");
+  const int rc = check_shape(*shape);
+  if (rc) return rc;
+  *bytes = nys_layout(*shape).total * sizeof(float);
+  return ACMIL_OK;
+}
+
+#define TM_RUN(expr)            \
+  do {                          \
+    const int _rc = (expr);     \
+    if (_rc) return _rc;        \
+  } while (0)
+
+extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const acmil_nystrom_weights* w, const float* d_x,
+                                      const float* d_residual, float* d_out, void* d_workspace, size_t workspace_bytes,
+                                      void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(shape && w && d_x && d_out && d_workspace, ACMIL_E_INVALID, "nystrom: null argument");
+  const acmil_nystrom_shape& s = *shape;
+  TM_RUN(check_shape(s));
+  ACMIL_REQUIRE(w->d_wqkv && w->d_wout && w->d_bout && (!s.residual || w->d_wconv), ACMIL_E_INVALID, "nystrom: null weight");
+  ACMIL_REQUIRE(((uintptr_t)d_workspace & 255) == 0, ACMIL_E_INVALID, "nystrom: workspace must be 256-byte aligned");
+  const NysLayout L = nys_layout(s);
+  ACMIL_REQUIRE(workspace_bytes >= L.total * sizeof(float), ACMIL_E_WORKSPACE, "nystrom: workspace %zu < %zu bytes", workspace_bytes,
+                L.total * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(d_workspace);
+  const int m = s.num_landmarks, d = s.dim_head, h = s.heads, H = L.H, np = L.n_pad, inner = L.inner, dim = s.dim;
+  const int P = s.precise;
+  float *xn = ws + L.xn, *q = ws + L.q, *k = ws + L.k, *vt = ws + L.vt, *ql = ws + L.ql, *kl = ws + L.kl;
+
+  // 1. (LayerNorm and) front zero padding so that the sequence splits into m landmark groups (:72-80)
+  for (int b = 0; b < s.batch; ++b) {
+    if (L.pad) ACMIL_CHECK_CUDA(cudaMemsetAsync(xn + (size_t)b * np * dim, 0, (size_t)L.pad * dim * sizeof(float), st));
+    TM_RUN(acmil_layernorm_rows(d_x + (size_t)b * s.n * dim, dim, s.n, dim, w->d_ln_w, w->d_ln_b, w->ln_eps,
+                                xn + ((size_t)b * np + L.pad) * dim, dim, stream));
+  }
+  // 2. q (scaled, :93), k as [b h] n d; v transposed as [b h] d n  (:83-84)
+  for (int b = 0; b < s.batch; ++b) {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = xn + (size_t)b * np * dim; g.lda = dim; g.m = np; g.k = dim; g.batch = 1;
+    g.b = w->d_wqkv; g.ldb = dim; g.n = inner;
+    g.c = q + (size_t)b * h * np * d; g.ldc = d; g.col_block_width = d; g.col_block_stride = (int64_t)np * d;
+    g.alpha = 1.f / sqrtf((float)d);
+    TM_RUN(tm_gemm(g, st));
+    g.b = w->d_wqkv + (size_t)inner * dim; g.c = k + (size_t)b * h * np * d; g.alpha = 1.f;
+    TM_RUN(tm_gemm(g, st));
+    acmil_gemm_desc gv = gemm0(P);
+    gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
+    gv.b = xn + (size_t)b * np * dim; gv.ldb = dim; gv.n = np;
+    gv.c = vt + (size_t)b * inner * np; gv.ldc = np;
+    TM_RUN(tm_gemm(gv, st));
+  }
+  // 3. landmarks = group means (:98-114)
+  {
+    dim3 grid(m, H);
+    tm_landmark_kernel<<<grid, 256, 0, st>>>(q, ql, np, m, L.l, d);
+    tm_landmark_kernel<<<grid, 256, 0, st>>>(k, kl, np, m, L.l, d);
+    g_acmil_launches += 2;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+  }
+  // 4. attn2 = softmax(q_l k_l^T) and its Moore-Penrose pseudo-inverse (:120, 134, 12-27)
+  float* a2 = ws + L.a2;
+  const int64_t mm = (int64_t)m * m;
+  {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = ql; g.lda = d; g.a_batch_stride = (int64_t)m * d; g.m = m; g.k = d; g.batch = H;
+    g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
+    g.c = a2; g.ldc = m; g.c_batch_stride = mm;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * m + 7) / 8), 256, 0, st>>>(a2, (long long)H * m, m);
+    ++g_acmil_launches;
+  }
+  float *z = ws + L.za, *zt = ws + L.zta, *z2 = ws + L.zb, *zt2 = ws + L.ztb;
+  {
+    int* scal = reinterpret_cast<int*>(ws + L.scal);
+    ACMIL_CHECK_CUDA(cudaMemsetAsync(scal, 0, 8, st));
+    tm_pinv_sums_kernel<<<dim3(H, 2), 256, 0, st>>>(a2, m, scal);
+    tm_pinv_init_kernel<<<dim3((m + 31) / 32, (m + 31) / 32, H), 256, 0, st>>>(a2, m, scal, z, zt);
+    g_acmil_launches += 2;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    // z <- 1/4 z (13 I - Y (15 I - Y (7 I - Y))),  Y = x z; written as
+    //   T1 = 7 Y - Y Y, T2 = 15 Y - Y T1, z' = 3.25 z - 0.25 z T2     (every product A B^T needs B transposed:
+    //   each GEMM also emits the transposed result that the next one consumes)
+    float *y = ws + L.y, *yt = ws + L.yt, *t1t = ws + L.t1t, *t2t = ws + L.t2t;
+    auto sq = [&](const float* A, const float* Bt, float* C, float* Ct, float alpha, const float* add, float beta) {
+      acmil_gemm_desc g = gemm0(P);
+      g.a = A; g.lda = m; g.a_batch_stride = mm; g.m = m; g.k = m; g.batch = H;
+      g.b = Bt; g.ldb = m; g.b_batch_stride = mm; g.n = m;
+      g.c = C; g.ldc = m; g.c_batch_stride = mm;
+      g.ct = Ct; g.ldct = m; g.ct_batch_stride = mm;
+      g.alpha = alpha; g.addend = add; g.ld_addend = m; g.addend_batch_stride = mm; g.beta = beta;
+      return tm_gemm(g, st);
+    };
+    for (int it = 0; it < s.pinv_iterations; ++it) {
+      TM_RUN(sq(a2, zt, y, yt, 1.f, nullptr, 0.f));
+      TM_RUN(sq(y, yt, nullptr, t1t, -1.f, y, 7.f));
+      TM_RUN(sq(y, t1t, nullptr, t2t, -1.f, y, 15.f));
+      TM_RUN(sq(z, t2t, z2, zt2, -0.25f, z, 3.25f));
+      std::swap(z, z2);
+      std::swap(zt, zt2);
+    }
+  }
+  // 5. attn3 = softmax_n(q_l k^T); (attn3 v)^T = v^T attn3^T   (:121, 133, 135)
+  float* sbuf = ws + L.sbuf;
+  {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = ql; g.lda = d; g.a_batch_stride = (int64_t)m * d; g.m = m; g.k = d; g.batch = H;
+    g.b = k; g.ldb = d; g.b_batch_stride = (int64_t)np * d; g.n = np;
+    g.c = sbuf; g.ldc = np; g.c_batch_stride = (int64_t)m * np;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_long_kernel<<<(unsigned)((size_t)H * m), 1024, 0, st>>>(sbuf, np);
+    ++g_acmil_launches;
+    acmil_gemm_desc g2 = gemm0(P);
+    g2.a = vt; g2.lda = np; g2.a_batch_stride = (int64_t)d * np; g2.m = d; g2.k = np; g2.batch = H;
+    g2.b = sbuf; g2.ldb = np; g2.b_batch_stride = (int64_t)m * np; g2.n = m;
+    g2.c = ws + L.kvt; g2.ldc = m; g2.c_batch_stride = (int64_t)d * m;
+    g2.k_split = L.ksplit; g2.split_ws = ws + L.split;
+    TM_RUN(tm_gemm(g2, st));
+  }
+  // 6. W^T = (attn3 v)^T pinv^T : out = attn1 (pinv (attn3 v)) -- the cheap association of (:135)
+  {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = ws + L.kvt; g.lda = m; g.a_batch_stride = (int64_t)d * m; g.m = d; g.k = m; g.batch = H;
+    g.b = z; g.ldb = m; g.b_batch_stride = mm; g.n = m;
+    g.c = ws + L.wt; g.ldc = m; g.c_batch_stride = (int64_t)d * m;
+    TM_RUN(tm_gemm(g, st));
+  }
+  // 7. rows that are needed downstream: all n_pad (padded_out), the last n, or the first n_out of those
+  const int r0 = s.padded_out ? 0 : L.pad;
+  const int nr = s.padded_out ? np : (s.n_out > 0 ? s.n_out : s.n);
+  float* merged = ws + L.merged;
+  {
+    // attn1 = softmax_m(q k_l^T) (:119), out = attn1 W, heads merged as b n (h d) (:141)
+    acmil_gemm_desc g = gemm0(P);
+    g.a = q + (size_t)r0 * d; g.lda = d; g.a_batch_stride = (int64_t)np * d; g.m = nr; g.k = d; g.batch = H;
+    g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
+    g.c = sbuf; g.ldc = m; g.c_batch_stride = (int64_t)nr * m;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * nr + 7) / 8), 256, 0, st>>>(sbuf, (long long)H * nr, m);
+    ++g_acmil_launches;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    for (int b = 0; b < s.batch; ++b) {
+      acmil_gemm_desc g2 = gemm0(P);
+      g2.a = sbuf + (size_t)b * h * nr * m; g2.lda = m; g2.a_batch_stride = (int64_t)nr * m; g2.m = nr; g2.k = m; g2.batch = h;
+      g2.b = ws + L.wt + (size_t)b * h * d * m; g2.ldb = m; g2.b_batch_stride = (int64_t)d * m; g2.n = d;
+      g2.c = merged + ((size_t)b * np + r0) * inner; g2.ldc = inner; g2.c_batch_stride = d;
+      TM_RUN(tm_gemm(g2, st));
+    }
+  }
+  // 8. + depth-wise conv of v (:137-138)
+  if (s.residual) {
+    const int ks = s.conv_kernel;
+    const size_t smem = (size_t)32 * ((CONV_TP + ks - 1) | 1) * sizeof(float);
+    dim3 grid((nr + CONV_TP - 1) / CONV_TP, (inner + 31) / 32, s.batch);
+    tm_resconv_kernel<<<grid, 256, smem, st>>>(vt, w->d_wconv, merged, np, inner, d, ks, r0, nr);
+    ++g_acmil_launches;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+  }
+  // 9. to_out (+ bias) on the kept rows, + residual (:142-143; transMIL.py:27)
+  for (int b = 0; b < s.batch; ++b) {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = merged + ((size_t)b * np + r0) * inner; g.lda = inner; g.m = nr; g.k = inner; g.batch = 1;
+    g.b = w->d_wout; g.ldb = inner; g.n = dim;
+    g.bias = w->d_bout;
+    const size_t out_rows = s.padded_out ? np : (s.n_out > 0 ? s.n_out : s.n);
+    g.c = d_out + (size_t)b * out_rows * dim; g.ldc = dim;
+    if (d_residual && !s.padded_out) {
+      g.addend = d_residual + (size_t)b * s.n * dim; g.ld_addend = dim; g.beta = 1.f;
+    }
+    TM_RUN(tm_gemm(g, st));
+  }
+  return ACMIL_OK;
+}

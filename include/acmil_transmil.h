@@ -1,0 +1,105 @@
+/*
+ * acmil_transmil -- C-ABI of the B200-native TransMIL / Nystrom-attention path (same library,
+ * libacmil_b200.so; same conventions as acmil_b200.h: 0 / negative ACMIL_E_* return codes with
+ * acmil_last_error(), d_* = caller-owned device memory, `stream` = cudaStream_t, no CPU path).
+ *
+ *   acmil_gemm_nt            <- every nn.Linear / einsum / matmul of the path
+ *                               (nystrom_attention.py:83,119-121,135,147; transMIL.py:61,89): fp32
+ *                               operands, error-compensated 3xTF32 on tcgen05 (fp32-faithful)
+ *   acmil_layernorm_rows     <- nn.LayerNorm(dim) of TransLayer.norm / TransMIL.norm (transMIL.py:11,27,58,86)
+ *   acmil_nystrom_workspace_bytes, acmil_nystrom_attn_fwd
+ *                            <- NystromAttention.forward, mask=None, return_attn=False
+ *                               (architecture/nystrom_attention.py:67-140 == pip nystrom-attention 0.0.12),
+ *                               optionally fused with the pre-LayerNorm and the residual add of
+ *                               TransLayer.forward (transMIL.py:25-28)
+ *   acmil_ppeg_fwd           <- PPEG.forward (transMIL.py:38-45)
+ */
+#ifndef ACMIL_TRANSMIL_H
+#define ACMIL_TRANSMIL_H
+
+#include "acmil_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C[b] = alpha * A[b] (m x k, row-major, ld = lda) * B[b]^T (n x k, ld = ldb)
+ *        (+ diag on row == col) (+ bias[col]) (+ beta * addend[b][row * ld_addend + col]) (relu)
+ * Element (row, col) of batch b is stored at
+ *   d_c  + b * c_batch_stride + (col / col_block_width) * col_block_stride + row * ldc + col % col_block_width
+ *   (col_block_width == 0: plain row-major), and, if d_ct != NULL, also transposed at
+ *   d_ct + b * ct_batch_stride + col * ldct + row.
+ * A batch stride of 0 shares the operand between batch entries.  All strides in floats; operand
+ * pointers 16-byte aligned, lda / ldb multiples of 4.  precise = 1: 3xTF32 split (fp32-faithful,
+ * ~2^-21), precise = 0: plain TF32 (~2^-10).  k_split > 1 partitions K over that many CTAs per tile
+ * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction). */
+typedef struct acmil_gemm_desc {
+  const float* a;
+  const float* b;
+  float* c;
+  float* ct;
+  const float* bias;
+  const float* addend;
+  float* split_ws;
+  int32_t m, n, k, batch;
+  int64_t lda, ldb, ldc, ldct, ld_addend;
+  int64_t a_batch_stride, b_batch_stride, c_batch_stride, ct_batch_stride, addend_batch_stride;
+  int32_t col_block_width;
+  int32_t k_split;
+  int64_t col_block_stride;
+  float alpha, beta, diag;
+  int32_t relu;
+  int32_t precise;
+  int32_t reserved[3];
+} acmil_gemm_desc;
+
+ACMIL_API int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream);
+
+/* out[r, :] = (x[r, :] - mean) / sqrt(var + eps) * w + b  (biased variance, like nn.LayerNorm). */
+ACMIL_API int acmil_layernorm_rows(const float* d_x, int64_t ldx, int64_t rows, int32_t dim, const float* d_w,
+                                   const float* d_b, float eps, float* d_out, int64_t ldo, void* stream);
+
+typedef struct acmil_nystrom_shape {
+  int32_t batch, n, dim;          /* x: [batch, n, dim] */
+  int32_t heads, dim_head;        /* inner = heads * dim_head */
+  int32_t num_landmarks;          /* m */
+  int32_t pinv_iterations;
+  int32_t residual;               /* depth-wise conv residual of the values */
+  int32_t conv_kernel;            /* 33 */
+  int32_t n_out;                  /* > 0: only the first n_out output rows are computed (TransMIL's second
+                                     layer is read at the class token only, transMIL.py:86); 0 = all n */
+  int32_t padded_out;             /* 1: d_out is [batch, n_pad, dim] = to_out(...) BEFORE the [:, -n:] slice,
+                                     no residual (the caller applies train-mode dropout, nystrom_attention.py:56-59,138) */
+  int32_t precise;                /* GEMM mode, see acmil_gemm_desc */
+  int32_t reserved[4];
+} acmil_nystrom_shape;
+
+typedef struct acmil_nystrom_weights {
+  const float* d_ln_w;            /* optional pre-LayerNorm (TransLayer.norm); NULL = x is used as is */
+  const float* d_ln_b;
+  float ln_eps;
+  int32_t reserved;
+  const float* d_wqkv;            /* to_qkv.weight   [3 * inner, dim] */
+  const float* d_wout;            /* to_out.0.weight [dim, inner] */
+  const float* d_bout;            /* to_out.0.bias   [dim] */
+  const float* d_wconv;           /* res_conv.weight [heads, 1, conv_kernel, 1] */
+} acmil_nystrom_weights;
+
+ACMIL_API int acmil_nystrom_workspace_bytes(const acmil_nystrom_shape* shape, size_t* bytes);
+
+/* d_out[b, i, :] = NystromAttention(LN(x))[b, i, :] + (d_residual ? d_residual[b, i, :] : 0). */
+ACMIL_API int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const acmil_nystrom_weights* w, const float* d_x,
+                                     const float* d_residual, float* d_out, void* d_workspace, size_t workspace_bytes,
+                                     void* stream);
+
+/* x, out: [batch, 1 + gh * gw, c]; row 0 (class token) is copied; the grid rows get
+ * feat + conv7(feat) + conv5(feat) + conv3(feat), depth-wise with zero padding (transMIL.py:31-45).
+ * Weights in nn.Conv2d layout [c, 1, k, k], biases [c]. */
+ACMIL_API int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32_t gw, int32_t c, const float* d_w7,
+                             const float* d_b7, const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3,
+                             float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACMIL_TRANSMIL_H */

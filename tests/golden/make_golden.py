@@ -173,7 +173,7 @@ def attmil_case(name, w_seed, x_seed, n):
     save(name, **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__":  # pragma: no cover
     # KAT1/2/3 of SURVEY.md section 4 (C1 shapes: N=1024, D_feat=384, D_inner=128)
     acmil_case("acmil_ga_k1_n1024", 1, 1234, 1024, 384, 128, 2, 1, 0, 0.0)
     acmil_case("acmil_ga_k5_n1024", 1, 1234, 1024, 384, 128, 2, 5, 10, 0.6, train_seed=7)

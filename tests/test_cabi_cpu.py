@@ -12,11 +12,11 @@ import torch
 
 from conftest import ROOT, golden_names, load_golden
 
-HEADER = os.path.join(ROOT, "include", "acmil_b200.h")
+HEADERS = [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h")]
 
 
 def declared_symbols():
-    src = open(HEADER).read()
+    src = "\n".join(open(h).read() for h in HEADERS)
     return sorted(set(re.findall(r"ACMIL_API\s+[\w\s\*]+?\b(acmil_\w+)\s*\(", src)))
 
 
@@ -41,6 +41,31 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.GpHeads) == 48
     assert C.sizeof(L.GpOutputs) == 64
     assert C.sizeof(L.GpConsts) == (3 * 128 + 8 * 128 + 8 + 4) * 4 + 16
+    # include/acmil_transmil.h
+    assert C.sizeof(L.GemmDesc) == 7 * 8 + 4 * 4 + 10 * 8 + 2 * 4 + 8 + 3 * 4 + 2 * 4 + 3 * 4
+    assert C.sizeof(L.NystromShape) == 16 * 4
+    assert C.sizeof(L.NystromWeights) == 7 * 8
+
+
+def test_transmil_host_entry_points_and_validation():
+    import acmil_b200._lib as L
+    lib = L.load()
+    shape = L.NystromShape(1, 50001, 512, 8, 64, 256, 6, 1, 33, 0, 0, 1)
+    n = C.c_size_t(0)
+    assert lib.acmil_nystrom_workspace_bytes(C.byref(shape), C.byref(n)) == 0
+    n_pad = 256 * 196
+    assert n_pad >= 50001 and n.value >= (3 * 512 + 512 + 8 * 256) * n_pad * 4      # q, k, v^T, xn, one similarity
+    bad = L.NystromShape(1, 100, 512, 8, 64, 254, 6, 1, 33, 0, 0, 1)
+    assert lib.acmil_nystrom_workspace_bytes(C.byref(bad), C.byref(n)) == -1
+    assert b"num_landmarks" in lib.acmil_last_error()
+    if not torch.cuda.is_available():      # no CPU path: compute entry points refuse loudly
+        g = L.GemmDesc()
+        g.a = g.b = g.c = 256
+        g.m = g.n = g.k = 128
+        g.batch = 1
+        g.lda = g.ldb = g.ldc = 128
+        assert lib.acmil_gemm_nt(C.byref(g), None) == -2
+        assert lib.acmil_layernorm_rows(C.c_void_p(256), 8, 1, 8, None, None, 1e-5, C.c_void_p(256), 8, None) == -2
 
 
 def test_host_only_entry_points_and_validation():

@@ -1,0 +1,178 @@
+"""GPU parity tests of the TransMIL / Nystrom path (through the C-ABI): the tcgen05 GEMM against fp64 matmul, the
+small kernels against torch, and the modules against golden vectors made by the reference itself and against
+the numpy oracle.  Tolerance per BASELINE.json north_star: logits within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, golden_x, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def load_into(module, w):
+    module.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return module.to(dev()).eval()
+
+
+@pytest.mark.parametrize("m,n,k,batch", [(128, 128, 32, 1), (300, 200, 100, 1), (1, 2, 64, 1), (257, 64, 512, 3),
+                                          (64, 256, 1000, 2), (1000, 48, 36, 1), (130, 130, 4, 2)])
+def test_gemm_nt_matches_fp64(m, n, k, batch):
+    from acmil_b200.transmil import gemm_nt
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(batch, m, k, generator=g)
+    b = torch.randn(batch, n, k, generator=g)
+    ref = (a.double() @ b.double().transpose(1, 2))
+    scale = float(ref.abs().max())
+    out = gemm_nt(a.to(dev()), b.to(dev())).cpu()
+    err = float((out.double() - ref).abs().max()) / scale
+    assert err < 2e-5, err                     # 3xTF32 (tensor-core fp32 accumulation truncates: ~k * 2^-24)
+    out1 = gemm_nt(a.to(dev()), b.to(dev()), precise=False).cpu()
+    err1 = float((out1.double() - ref).abs().max()) / scale
+    assert err1 < 5e-3 and (k < 16 or err1 > err)      # plain TF32 is the coarse mode
+
+
+def test_gemm_nt_epilogue_terms_and_layouts():
+    from acmil_b200.transmil import gemm_nt
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(2, 200, 72, generator=g), torch.randn(200, 72, generator=g)      # shared B
+    bias, add = torch.randn(200, generator=g), torch.randn(2, 200, 200, generator=g)
+    ref = torch.relu(-0.5 * (a.double() @ b.double().T) + 3.0 * torch.eye(200, dtype=torch.float64) + bias.double()
+                     + 0.25 * add.double())
+    out_t = torch.empty(2, 200, 200, device=dev())
+    out = gemm_nt(a.to(dev()), b.to(dev()), bias=bias.to(dev()), addend=add.to(dev()), alpha=-0.5, beta=0.25, diag=3.0,
+                  relu=True, out_t=out_t)
+    assert float((out.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    assert torch.equal(out_t, out.transpose(1, 2))
+    # K split (long reductions): same result up to summation order
+    a2, b2 = torch.randn(3, 64, 5000, generator=g), torch.randn(3, 96, 5000, generator=g)
+    ref2 = a2.double() @ b2.double().transpose(1, 2)
+    out2 = gemm_nt(a2.to(dev()), b2.to(dev()), k_split=7).cpu()
+    assert float((out2.double() - ref2).abs().max()) / float(ref2.abs().max()) < 2e-5
+    # strided output view (rows of a larger buffer)
+    buf = torch.zeros(2, 210, 200, device=dev())
+    gemm_nt(a.to(dev()), b.to(dev()), out=buf[:, 5:205])
+    ref3 = a.double() @ b.double().T
+    assert float((buf[:, 5:205].cpu().double() - ref3).abs().max()) < 2e-5 * float(ref3.abs().max())
+    assert float(buf[:, :5].abs().max()) == 0 and float(buf[:, 205:].abs().max()) == 0
+
+
+def test_gemm_rejects_bad_arguments():
+    from acmil_b200 import _lib as L
+    from acmil_b200.transmil import gemm_nt
+    with pytest.raises(RuntimeError):
+        gemm_nt(torch.randn(4, 8), torch.randn(4, 8).to(dev()))
+    with pytest.raises(ValueError):
+        gemm_nt(torch.randn(4, 8).to(dev()), torch.randn(4, 12).to(dev()))
+    with pytest.raises(L.AcmilError):      # lda not a multiple of 4 floats
+        gemm_nt(torch.randn(4, 6).to(dev()), torch.randn(4, 6).to(dev()))
+
+
+def test_layernorm_rows_matches_torch():
+    from acmil_b200.transmil import layernorm_rows
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1000, 512, generator=g) * 3 + 1
+    w, b = torch.rand(512, generator=g) + 0.5, torch.randn(512, generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (512,), w.double(), b.double(), 1e-5)
+    out = layernorm_rows(x.to(dev()), w.to(dev()), b.to(dev()), 1e-5).cpu()
+    assert float((out.double() - ref).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names("ppeg_"))
+def test_ppeg_matches_reference_golden(name):
+    from acmil_b200.transmil import PPEG
+    w, meta = load_golden(name)
+    dim, gh, gw = (int(v) for v in meta["meta_cfg"])
+    mod = load_into(PPEG(dim=dim), w)
+    with torch.no_grad():
+        y = mod(golden_x(meta).to(dev()), gh, gw).cpu().numpy()
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", golden_names("nystrom_"))
+def test_nystrom_attention_matches_reference_golden(name):
+    from acmil_b200.transmil import NystromAttention
+    w, meta = load_golden(name)
+    dim, dim_head, heads, m, ks, residual, iters = (int(v) for v in meta["meta_cfg"])
+    mod = load_into(NystromAttention(dim=dim, dim_head=dim_head, heads=heads, num_landmarks=m, pinv_iterations=iters,
+                                     residual=bool(residual), residual_conv_kernel=ks, dropout=0.1), w)
+    with torch.no_grad():
+        y = mod(golden_x(meta).to(dev())).cpu().numpy()
+    assert y.shape == meta["out"].shape
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("translayer_"))
+def test_trans_layer_matches_reference_golden(name):
+    from acmil_b200.transmil import TransLayer
+    w, meta = load_golden(name)
+    mod = load_into(TransLayer(dim=int(meta["meta_cfg"][0])), w)
+    x = golden_x(meta).to(dev())
+    with torch.no_grad():
+        y = mod(x).cpu().numpy()
+        y3 = mod(x, n_out=3).cpu().numpy()
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(y3, meta["out"][:, :3], rtol=1e-3, atol=2e-5)      # the rows-subset path of layer 2
+
+
+@pytest.mark.parametrize("name", golden_names("transmil_"))
+def test_transmil_matches_reference_golden(name):
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    w, meta = load_golden(name)
+    d_feat, d_inner, n_class = (int(v) for v in meta["meta_cfg"])
+    mod = load_into(TransMIL(Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class)), w)
+    with torch.no_grad():
+        y = mod(golden_x(meta).to(dev())).cpu().numpy()
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-3, atol=1e-4)      # north_star: logits within 1e-3
+
+
+def test_transmil_dim512_vs_oracle_and_plain_tf32_mode():
+    """BASELINE config 3 dims (D_feat 512, D_inner 512 -> 256 landmarks, 8 x 64 heads) at an oracle-sized n."""
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    from oracle import transmil as O
+    torch.manual_seed(3)
+    mod = TransMIL(Struct(D_feat=512, D_inner=512, n_class=2)).eval()
+    x = torch.randn(1, 3000, 512, generator=torch.Generator().manual_seed(4))
+    w = {k: v.numpy() for k, v in mod.state_dict().items()}
+    ref = O.transmil_forward(w, x.numpy())
+    mod = mod.to(dev())
+    with torch.no_grad():
+        y = mod(x.to(dev())).cpu().numpy()
+        np.testing.assert_allclose(y, ref, rtol=1e-3, atol=1e-4)
+        for layer in (mod.layer1, mod.layer2):
+            layer.attn.precise = False
+        y1 = mod(x.to(dev())).cpu().numpy()
+    assert np.isfinite(y1).all() and np.abs(y1 - ref).max() < 0.1      # coarse mode: sane, not parity-grade
+
+
+def test_transmil_full_size_runs_and_is_deterministic():
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    torch.manual_seed(5)
+    mod = TransMIL(Struct(D_feat=512, D_inner=512, n_class=2)).to(dev()).eval()
+    x = torch.randn(1, 50000, 512, device=dev(), generator=torch.Generator(device=dev()).manual_seed(6))
+    with torch.no_grad():
+        y0 = mod(x)
+        y1 = mod(x)
+    assert y0.shape == (1, 2) and bool(torch.isfinite(y0).all())
+    assert torch.equal(y0, y1)
+
+
+def test_forward_only_and_cuda_only_errors():
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import NystromAttention, TransMIL
+    mod = TransMIL(Struct(D_feat=32, D_inner=64, n_class=2)).to(dev())
+    with pytest.raises(NotImplementedError):
+        mod(torch.randn(1, 40, 32, device=dev()))              # parameters require grad, grad mode on
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            mod(torch.randn(1, 40, 32))                        # CPU tensor
+    att = NystromAttention(64, dim_head=8, heads=8, num_landmarks=32).to(dev())
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        att(torch.randn(1, 40, 64, device=dev()), mask=torch.ones(1, 40, dtype=torch.bool, device=dev()))
