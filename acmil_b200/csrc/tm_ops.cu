@@ -207,18 +207,23 @@ __global__ void __launch_bounds__(256) tm_resconv_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // PPEG (transMIL.py:38-45): out = feat + conv7(feat) + conv5(feat) + conv3(feat) on the [gh, gw] token grid,
 // channels last.  The three depth-wise kernels and the identity are summed into one 7x7 stencil per channel
-// (exact up to fp32 summation order).  thread = (channel, position run); 49 weights in registers.
+// (exact up to fp32 summation order).  CTA = 32 channels x (8 rows x 16 columns); a thread owns one channel and a run
+// of 16 outputs along x, so every loaded input feeds up to 7 FMAs from registers (9.6 loads per output, not 49) and
+// a warp's loads are 128-byte lines (32 consecutive channels of one token).
+constexpr int PPEG_TX = 16, PPEG_TY = 8;
 __global__ void __launch_bounds__(256) tm_ppeg_kernel(const float* __restrict__ x, int gh, int gw, int C, const float* __restrict__ w7,
                                                       const float* __restrict__ b7, const float* __restrict__ w5,
                                                       const float* __restrict__ b5, const float* __restrict__ w3,
-                                                      const float* __restrict__ b3, float* __restrict__ out, int pos_per_cta) {
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.y * 32 + cx, bz = blockIdx.z;
+                                                      const float* __restrict__ b3, float* __restrict__ out, int cblocks) {
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.z % cblocks) * 32 + cx, bz = blockIdx.z / cblocks;
   const size_t tok = (size_t)gh * gw + 1;
   const float* xb = x + (size_t)bz * tok * C;
   float* ob = out + (size_t)bz * tok * C;
   if (c >= C) return;
-  if (blockIdx.x == 0 && py == 0) ob[c] = xb[c];      // class token passes through
+  if (blockIdx.x == 0 && blockIdx.y == 0 && ty == 0) ob[c] = xb[c];      // class token passes through
+  const int y = blockIdx.y * PPEG_TY + ty, x0 = blockIdx.x * PPEG_TX;
+  if (y >= gh) return;
   float wk[49];
 #pragma unroll
   for (int dy = 0; dy < 7; ++dy)
@@ -232,25 +237,28 @@ __global__ void __launch_bounds__(256) tm_ppeg_kernel(const float* __restrict__ 
     }
   const float bias = b7[c] + b5[c] + b3[c];
   const float* feat = xb + C;
-  const int p0 = blockIdx.x * pos_per_cta;
-  for (int o = py; o < pos_per_cta; o += 8) {
-    const int pos = p0 + o;
-    if (pos >= gh * gw) break;
-    const int y = pos / gw, xx = pos % gw;
-    float acc = bias;
+  float acc[PPEG_TX];
 #pragma unroll
-    for (int dy = 0; dy < 7; ++dy) {
-      const int yy = y + dy - 3;
-      if (yy < 0 || yy >= gh) continue;
+  for (int o = 0; o < PPEG_TX; ++o) acc[o] = bias;
 #pragma unroll
-      for (int dx = 0; dx < 7; ++dx) {
-        const int xq = xx + dx - 3;
-        if (xq < 0 || xq >= gw) continue;
-        acc = fmaf(wk[dy * 7 + dx], feat[((size_t)yy * gw + xq) * C + c], acc);
-      }
+  for (int dy = 0; dy < 7; ++dy) {
+    const int yy = y + dy - 3;
+    if (yy < 0 || yy >= gh) continue;
+    float in[PPEG_TX + 6];
+    const float* rowp = feat + (size_t)yy * gw * C + c;
+#pragma unroll
+    for (int i = 0; i < PPEG_TX + 6; ++i) {
+      const int xq = x0 + i - 3;
+      in[i] = (xq >= 0 && xq < gw) ? rowp[(size_t)xq * C] : 0.f;
     }
-    ob[(size_t)(1 + pos) * C + c] = acc;
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+      for (int o = 0; o < PPEG_TX; ++o) acc[o] = fmaf(wk[dy * 7 + dx], in[o + dx], acc[o]);
   }
+#pragma unroll
+  for (int o = 0; o < PPEG_TX; ++o)
+    if (x0 + o < gw) ob[(size_t)(1 + y * gw + x0 + o) * C + c] = acc[o];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -334,9 +342,10 @@ extern "C" int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
   ACMIL_REQUIRE(d_x && d_out && d_w7 && d_b7 && d_w5 && d_b5 && d_w3 && d_b3, ACMIL_E_INVALID, "ppeg: null pointer");
   ACMIL_REQUIRE(batch >= 1 && gh >= 1 && gw >= 1 && c >= 1 && batch <= 65535, ACMIL_E_INVALID, "ppeg: bad shape");
-  const int ppc = 64;
-  dim3 grid((gh * gw + ppc - 1) / ppc, (c + 31) / 32, batch);
-  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, ppc);
+  const int cblocks = (c + 31) / 32;
+  ACMIL_REQUIRE((long long)cblocks * batch <= 65535 && (gh + PPEG_TY - 1) / PPEG_TY <= 65535, ACMIL_E_INVALID, "ppeg: grid too large");
+  dim3 grid((gw + PPEG_TX - 1) / PPEG_TX, (gh + PPEG_TY - 1) / PPEG_TY, cblocks * batch);
+  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, cblocks);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
