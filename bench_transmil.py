@@ -1,0 +1,186 @@
+#!/usr/bin/env python
+"""Secondary bench: TransMIL forward (BASELINE.json configs[2]: Nystrom attention, 256 landmarks, N = 50k, D = 512).
+
+Same JSON contract as bench.py (which dispatches here for `--workload transmil`): `value` = slides/s with bags
+resident in HBM (one slide per step, rotating bags larger than L2 in total), `roofline.bound` = "tensor" with
+`achieved` = useful FLOPs of the formulation that runs (2 M N K per product, the 3xTF32 split NOT counted) over the
+CUDA-event time, `peak` = MEASURED_PEAKS.json bf16 sustained TFLOP/s, `e2e` = TransMIL.forward from pinned host
+memory with the logits read back, `cpu_baseline` = oracle/torch_port.transmil_forward on the host cores.
+N > 1: independent replicas (one slide per rank per step; the sequence-parallel sharding of SURVEY 8e is not built).
+"""
+import json
+import math
+import os
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def transmil_flops(n, d_feat, dim, n_class=2, heads=8, iters=6):
+    """Useful FLOPs of one forward as implemented (cheap association, layer 2 evaluated at the class token only)."""
+    side = math.ceil(math.sqrt(n))
+    t = side * side + 1
+    m, d = dim // 2, dim // heads
+    l = math.ceil(t / m)
+    npad = m * l if t % m else t
+    f = 2.0 * n * d_feat * dim                                   # _fc1
+    for rows in (t, 1):                                          # rows of the attention output that are needed
+        f += 2.0 * npad * dim * 3 * dim                          # to_qkv
+        f += heads * 2.0 * m * m * d                             # sim2
+        f += heads * iters * 4 * 2.0 * m ** 3                    # Moore-Penrose iteration
+        f += heads * 2.0 * m * npad * d * 2                      # sim3, attn3 v
+        f += heads * 2.0 * d * m * m                             # W = pinv (attn3 v)
+        f += heads * 2.0 * rows * m * d * 2                      # sim1, attn1 W
+        f += 2.0 * rows * dim * dim                              # to_out
+        f += 2.0 * rows * dim * 33                               # res_conv
+    f += 2.0 * side * side * dim * 49                            # PPEG
+    f += 2.0 * dim * n_class
+    return f
+
+
+def cpu_rate(n, d_feat, dim, slides, warmup):
+    from oracle import torch_port as T
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    p = {k: v.detach() for k, v in TransMIL(Struct(D_feat=d_feat, D_inner=dim, n_class=2)).state_dict().items()}
+    x = torch.randn(1, n, d_feat)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + slides):
+            t0 = time.perf_counter()
+            T.transmil_forward(p, x)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return len(times) / sum(times), sum(times) / len(times)
+
+
+def config(a, world, cpu=False):
+    return {"workload": f"TransMIL D_feat={a.d_feat} D_inner={a.dim} ({a.dim // 2} landmarks, 8 heads), synthetic N(0,1) fp32 "
+                        f"bags of N={a.rows} rows (BASELINE.json configs[2]), eval-mode forward, 3xTF32",
+            "bags_per_step": 1 if cpu else world, "rows_per_bag": a.rows,
+            "parallelism": "cpu" if cpu else (f"{world} independent replicas" if world > 1 else "1 GPU"),
+            "l2_policy": "rotating resident bags; intermediates of one forward (>1 GB) exceed the 126 MB L2"}
+
+
+def run_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    rate, sec = cpu_rate(a.rows, a.d_feat, a.dim, max(1, min(a.steps, 3)), 1)
+    print(json.dumps({
+        "impl": "reference", "metric": "slides/sec (TransMIL, N=50k, D=512)", "value": rate, "unit": "slides/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(a, 1, cpu=True),
+        "cpu_baseline": {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{max(1, min(a.steps, 3))} bags of {a.rows}x{a.d_feat} after 1 warm-up (oracle/torch_port.py)"},
+        "e2e": {"value": rate, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_ours(a, ClockSampler):
+    import torch.distributed as dist
+    from acmil_b200 import Struct, _lib
+    from acmil_b200.transmil import TransMIL
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = TransMIL(Struct(D_feat=a.d_feat, D_inner=a.dim, n_class=2)).to(dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    bags = [torch.randn(1, a.rows, a.d_feat, device=dev, generator=gen) for _ in range(3)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(a.warmup, 3)):
+            y = model(bags[i % 3])
+        barrier()
+        l0 = _lib.launch_count()
+        model(bags[0])
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - l0
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            y = model(bags[i % 3])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        checksum = float(y.sum().item())
+        host = [torch.randn(1, a.rows, a.d_feat).pin_memory() for _ in range(2)]
+        xdev = torch.empty(1, a.rows, a.d_feat, device=dev)
+
+        def user_call(i):
+            xdev.copy_(host[i % 2], non_blocking=True)
+            return model(xdev).cpu()
+
+        user_call(0)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, a.e2e_steps)
+        for i in range(n_e2e):
+            user_call(i)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1345.7))
+    flops = transmil_flops(a.rows, a.d_feat, a.dim)
+    sec = ms * 1e-3 / a.steps
+    achieved = flops / sec / 1e12
+    line = {
+        "metric": "slides/sec (TransMIL, N=50k, D=512)", "value": world * a.steps / (ms * 1e-3), "unit": "slides/s",
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products)", "data": "synthetic",
+        "config": config(a, world),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "whole forward (tm_gemm_kernel dominates)",
+                     "algorithmic_flops_per_slide": flops,
+                     "reference_association_flops_per_slide": 470e9,
+                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1345.7") +
+                                    "; the fp32-faithful 3xTF32 split costs 6 bf16-equivalent MMAs per product, so 1/6 of"
+                                    " this peak is the ceiling of the formulation"},
+        "clocks": clocks,
+        "e2e": {"value": world * n_e2e / dt, "unit": "slides/s", "h2d_bytes_per_step": world * a.rows * a.d_feat * 4,
+                "d2h_bytes_per_step": world * 2 * 4, "api": "TransMIL.forward(x[1,N,D]) from pinned host memory, logits .cpu()",
+                "bags": n_e2e},
+        "gpu_launches": int(launches * a.steps), "checksum": checksum,
+    }
+    if not a.no_cpu_baseline:
+        rate, s1 = cpu_rate(a.rows, a.d_feat, a.dim, 2, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"2 bags of {a.rows}x{a.d_feat} fp32 after 1 warm-up (oracle/torch_port.transmil_forward)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()

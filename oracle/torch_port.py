@@ -57,3 +57,57 @@ def random_state(d_feat=384, d_inner=128, d_attn=128, k=5, n_class=2, seed=0):
         p[f"classifier.{c}.fc.weight"], p[f"classifier.{c}.fc.bias"] = lin(n_class, d_inner)
     p["Slide_classifier.fc.weight"], p["Slide_classifier.fc.bias"] = lin(n_class, d_inner)
     return p
+
+
+# ------------------------------------------------------------------------------------------ TransMIL
+def _nystrom_attention(p, pre, x, heads, m, iters=6):
+    """architecture/nystrom_attention.py:67-143 (mask=None, eval), torch ops in the reference's order."""
+    b, n, dim = x.shape
+    d = p[pre + "to_qkv.weight"].shape[0] // 3 // heads
+    rem = n % m
+    if rem > 0:
+        x = F.pad(x, (0, 0, m - rem, 0), value=0)                                                # :72-76
+    q, k, v = F.linear(x, p[pre + "to_qkv.weight"]).chunk(3, dim=-1)                             # :83
+    q, k, v = (t.reshape(b, -1, heads, d).transpose(1, 2) for t in (q, k, v))                    # :84
+    q = q * d ** -0.5                                                                            # :93
+    l = -(-n // m)
+    ql = q.reshape(b, heads, m, l, d).sum(3) / l                                                 # :98-114
+    kl = k.reshape(b, heads, m, l, d).sum(3) / l
+    a1 = torch.softmax(q @ kl.transpose(-1, -2), -1)                                             # :119-133
+    a2 = torch.softmax(ql @ kl.transpose(-1, -2), -1)
+    a3 = torch.softmax(ql @ k.transpose(-1, -2), -1)
+    ax = a2.abs()                                                                                # :12-27
+    z = a2.transpose(-1, -2) / (ax.sum(-1).max() * ax.sum(-2).max())
+    eye = torch.eye(m).unsqueeze(0)
+    for _ in range(iters):
+        xz = a2 @ z
+        z = 0.25 * z @ (13 * eye - (xz @ (15 * eye - (xz @ (7 * eye - xz)))))
+    out = (a1 @ z) @ (a3 @ v)                                                                    # :135
+    wc = p[pre + "res_conv.weight"]
+    out = out + F.conv2d(v, wc, padding=(wc.shape[2] // 2, 0), groups=heads)                     # :137-138
+    out = out.transpose(1, 2).reshape(b, -1, heads * d)                                          # :141
+    out = F.linear(out, p[pre + "to_out.0.weight"], p[pre + "to_out.0.bias"])                    # :142
+    return out[:, -n:]
+
+
+def transmil_forward(p: dict, x: torch.Tensor):
+    """architecture/transMIL.py:60-91, eval mode; p: reference-named state_dict; x [B, n, D_feat] -> logits."""
+    h = F.relu(F.linear(x, p["_fc1.0.weight"], p["_fc1.0.bias"]))                                # :61
+    n, dim = h.shape[1], h.shape[2]
+    side = int(-(-n ** 0.5 // 1))
+    while side * side < n:
+        side += 1
+    h = torch.cat([h, h[:, :side * side - n]], dim=1)                                            # :64-67
+    h = torch.cat([p["cls_token"].expand(h.shape[0], -1, -1), h], dim=1)                         # :70-72
+    for name in ("layer1.", "layer2."):
+        if name == "layer2.":                                                                    # :78 PPEG between the layers
+            cls, feat = h[:, :1], h[:, 1:]
+            g = feat.transpose(1, 2).reshape(h.shape[0], dim, side, side)
+            y = g
+            for cn, kk in (("proj", 7), ("proj1", 5), ("proj2", 3)):
+                y = y + F.conv2d(g, p[f"pos_layer.{cn}.weight"], p[f"pos_layer.{cn}.bias"], padding=kk // 2, groups=dim)
+            h = torch.cat([cls, y.flatten(2).transpose(1, 2)], dim=1)
+        xn = F.layer_norm(h, (dim,), p[name + "norm.weight"], p[name + "norm.bias"])             # :27
+        h = h + _nystrom_attention(p, name + "attn.", xn, 8, dim // 2)
+    h = F.layer_norm(h, (dim,), p["norm.weight"], p["norm.bias"])[:, 0]                          # :84
+    return F.linear(h, p["_fc2.weight"], p["_fc2.bias"])                                         # :87

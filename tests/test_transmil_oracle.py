@@ -69,3 +69,15 @@ def test_state_dict_and_init_parity_with_reference_fixture():
     for k, v in sd.items():
         assert tuple(v.shape) == w[k].shape, k
         np.testing.assert_array_equal(v.numpy(), w[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", golden_names("transmil_"))
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.transmil_forward is what bench.py times as the CPU baseline of this path."""
+    import torch
+    from oracle import torch_port as T
+    w, meta = load_golden(name)
+    p = {k: torch.from_numpy(v) for k, v in w.items()}
+    with torch.no_grad():
+        y = T.transmil_forward(p, golden_x(meta)).numpy()
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-5, atol=1e-6)
