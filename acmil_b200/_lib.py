@@ -64,8 +64,10 @@ class GemmDesc(C.Structure):
                 + [(n, C.c_int64) for n in ("lda", "ldb", "ldc", "ldct", "ld_addend", "a_batch_stride", "b_batch_stride",
                                             "c_batch_stride", "ct_batch_stride", "addend_batch_stride")]
                 + [("col_block_width", C.c_int32), ("k_split", C.c_int32), ("col_block_stride", C.c_int64),
-                   ("alpha", C.c_float), ("beta", C.c_float), ("diag", C.c_float), ("relu", C.c_int32),
-                   ("precise", C.c_int32), ("reserved", C.c_int32 * 3)])
+                   ("alpha", C.c_float), ("beta", C.c_float), ("diag", C.c_float), ("act", C.c_int32),
+                   ("precise", C.c_int32), ("batch_inner", C.c_int32), ("bias_per_row", C.c_int32), ("reserved", C.c_int32)]
+                + [(n, C.c_int64) for n in ("a_batch_stride2", "b_batch_stride2", "c_batch_stride2", "ct_batch_stride2",
+                                            "addend_batch_stride2")])
 
 
 class NystromShape(C.Structure):
@@ -77,6 +79,21 @@ class NystromShape(C.Structure):
 class NystromWeights(C.Structure):
     _fields_ = [("d_ln_w", C.c_void_p), ("d_ln_b", C.c_void_p), ("ln_eps", C.c_float), ("reserved", C.c_int32),
                 ("d_wqkv", C.c_void_p), ("d_wout", C.c_void_p), ("d_bout", C.c_void_p), ("d_wconv", C.c_void_p)]
+
+
+class VitShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "img", "patch", "in_ch", "dim", "depth", "heads", "mlp_dim", "n_class",
+                                         "precise")] + [("ln_eps", C.c_float), ("reserved", C.c_int32 * 5)]
+
+
+class VitBlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_ln1_w", "d_ln1_b", "d_qkv_w", "d_qkv_b", "d_proj_w", "d_proj_b", "d_ln2_w",
+                                          "d_ln2_b", "d_fc1_w", "d_fc1_b", "d_fc2_w", "d_fc2_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_cls_token", "d_pos_embed", "d_patch_w", "d_patch_b", "d_norm_w", "d_norm_b",
+                                          "d_head_w", "d_head_b")] + [("blocks", C.POINTER(VitBlockWeights))]
 
 
 # every symbol include/*.h declares: (restype, argtypes)
@@ -108,6 +125,10 @@ SYMBOLS = {
     "acmil_nystrom_workspace_bytes": (C.c_int, [C.POINTER(NystromShape), _SIZE_P]),
     "acmil_nystrom_attn_fwd": (C.c_int, [C.POINTER(NystromShape), C.POINTER(NystromWeights), C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_softmax_rows_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "acmil_vit_workspace_bytes": (C.c_int, [C.POINTER(VitShape), _SIZE_P]),
+    "acmil_vit_fwd": (C.c_int, [C.POINTER(VitShape), C.POINTER(VitWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_size_t, C.c_void_p]),
     "acmil_ppeg_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

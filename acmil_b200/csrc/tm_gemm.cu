@@ -31,7 +31,7 @@ constexpr int NST = 3;           // ring stages
 constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 16 KB
 
 struct GemmParams {
-  CUtensorMap ta, tb;            // (K, rows, batch) fp32
+  CUtensorMap ta, tb;            // (K, rows, batch_lo, batch_hi) fp32
   float* c;
   float* ct;                     // optional transposed copy: ct[b] + col * ldct + row
   const float* bias;             // [N] or null
@@ -44,7 +44,10 @@ struct GemmParams {
   long long ct_batch_stride, ldct;
   long long add_batch_stride, ld_add;
   float alpha, beta, diag;
-  int relu;
+  int act;                       // 0 none, 1 relu, 2 exact GELU
+  int bias_row;                  // bias indexed by row
+  int zdiv;                      // two-level batch: z_lo = z % zdiv, z_hi = z / zdiv
+  long long c_bs2, ct_bs2, add_bs2;
   int vec_ok;                    // float4 stores are legal for c
   int ksplit;                    // > 1: blockIdx.z = batch * ksplit + split; raw partial tiles go to split_ws
   int k_per_split;               // multiple of KC
@@ -71,11 +74,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ float act_apply_tm(float t, int act) {
+  if (act == 1) return fmaxf(t, 0.f);
+  if (act == 2) return 0.5f * t * (1.f + erff(t * 0.70710678118654752440f));      // nn.GELU() (exact)
+  return t;
 }
 
 // smem: per stage {A hi, B hi, A lo, B lo}; B tiles hold BN rows
@@ -98,6 +107,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
   const int kbeg = p.ksplit > 1 ? (blockIdx.z % p.ksplit) * p.k_per_split : 0;
   const int kend = p.ksplit > 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
   const int nchunk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
+  const int zlo = bz % p.zdiv, zhi = bz / p.zdiv;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
@@ -127,8 +137,8 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         mbar_wait(&bars->empty[s], ph ^ 1u);
         unsigned char* st = smem + s * STAGE;
         mbar_expect_tx(&bars->full[s], TILE_BYTES + B_BYTES);
-        tma_load_3d(st, &p.ta, kbeg + c * KC, m0, p.a_batched ? bz : 0, &bars->full[s]);
-        tma_load_3d(st + TILE_BYTES, &p.tb, kbeg + c * KC, n0, p.b_batched ? bz : 0, &bars->full[s]);
+        tma_load_4d(st, &p.ta, kbeg + c * KC, m0, p.a_batched ? zlo : 0, p.a_batched ? zhi : 0, &bars->full[s]);
+        tma_load_4d(st + TILE_BYTES, &p.tb, kbeg + c * KC, n0, p.b_batched ? zlo : 0, p.b_batched ? zhi : 0, &bars->full[s]);
       }
     }
   } else if (warp == 1) {
@@ -192,9 +202,10 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
     mbar_wait(&bars->acc_full, 0);
     tc_fence_after();
     const bool row_ok = row < p.M;
-    float* crow = p.c ? p.c + (size_t)bz * p.c_batch_stride + (size_t)row * p.ldc : nullptr;
-    const float* arow = p.addend ? p.addend + (size_t)bz * p.add_batch_stride + (size_t)row * p.ld_add : nullptr;
-    float* ctb = p.ct ? p.ct + (size_t)bz * p.ct_batch_stride + row : nullptr;
+    float* crow = p.c ? p.c + (size_t)zlo * p.c_batch_stride + (size_t)zhi * p.c_bs2 + (size_t)row * p.ldc : nullptr;
+    const float* arow =
+        p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
+    float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         const int col = n0 + c0 + j;
         float t = p.alpha * __uint_as_float(v[j]);
         if (p.diag != 0.f && col == row) t += p.diag;
-        if (p.bias && col < p.N) t += p.bias[col];
+        if (p.bias && col < p.N) t += p.bias_row ? (row_ok ? p.bias[row] : 0.f) : p.bias[col];
         r[j] = t;
       }
       if (row_ok) {
@@ -225,9 +236,9 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
           for (int j = 0; j < 32; ++j)
             if (n0 + c0 + j < p.N) r[j] = fmaf(p.beta, arow[n0 + c0 + j], r[j]);
         }
-        if (p.relu) {
+        if (p.act) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.f);
+          for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
         }
         if (crow) {
           if (p.vec_ok && n0 + c0 + 32 <= p.N) {
@@ -271,11 +282,12 @@ __global__ void __launch_bounds__(256) tm_gemm_split_reduce_kernel(const __grid_
     for (int s = 0; s < p.ksplit; ++s) acc += p.split_ws[(((size_t)bz * p.ksplit + s) * p.M + row) * p.N + col];
     float t = p.alpha * acc;
     if (p.diag != 0.f && col == row) t += p.diag;
-    if (p.bias) t += p.bias[col];
-    if (p.addend) t = fmaf(p.beta, p.addend[(size_t)bz * p.add_batch_stride + (size_t)row * p.ld_add + col], t);
-    if (p.relu) t = fmaxf(t, 0.f);
-    if (p.c) p.c[(size_t)bz * p.c_batch_stride + (size_t)(col / p.cbw) * p.cbs + (size_t)row * p.ldc + col % p.cbw] = t;
-    if (p.ct) p.ct[(size_t)bz * p.ct_batch_stride + (size_t)col * p.ldct + row] = t;
+    if (p.bias) t += p.bias[p.bias_row ? row : col];
+    const size_t zlo = (size_t)(bz % p.zdiv), zhi = (size_t)(bz / p.zdiv);
+    if (p.addend) t = fmaf(p.beta, p.addend[zlo * p.add_batch_stride + zhi * p.add_bs2 + (size_t)row * p.ld_add + col], t);
+    t = act_apply_tm(t, p.act);
+    if (p.c) p.c[zlo * p.c_batch_stride + zhi * p.c_bs2 + (size_t)(col / p.cbw) * p.cbs + (size_t)row * p.ldc + col % p.cbw] = t;
+    if (p.ct) p.ct[zlo * p.ct_batch_stride + zhi * p.ct_bs2 + (size_t)col * p.ldct + row] = t;
   }
 }
 
@@ -292,17 +304,22 @@ EncodeFn tm_get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap* m, const float* base, int rows, int K, long long ld, int batch, long long batch_stride, int box_rows,
-             const char* what) {
+int make_map(CUtensorMap* m, const float* base, int rows, int K, long long ld, int n_lo, long long stride_lo, int n_hi,
+             long long stride_hi, int box_rows, const char* what) {
   EncodeFn enc = tm_get_encode();
   ACMIL_REQUIRE(enc != nullptr, ACMIL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  ACMIL_REQUIRE(((uintptr_t)base & 15) == 0 && ld % 4 == 0 && (batch <= 1 || batch_stride % 4 == 0), ACMIL_E_INVALID,
-                "gemm: operand %s must be 16-byte aligned with leading dimensions that are multiples of 4 floats", what);
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * ld) * 4};
-  cuuint32_t box[3] = {KC, (cuuint32_t)box_rows, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+  ACMIL_REQUIRE(((uintptr_t)base & 15) == 0 && ld % 4 == 0 && (n_lo <= 1 || (stride_lo % 4 == 0 && stride_lo > 0)) &&
+                    (n_hi <= 1 || (stride_hi % 4 == 0 && stride_hi > 0)),
+                ACMIL_E_INVALID,
+                "gemm: operand %s must be 16-byte aligned with leading dimension and batch strides that are positive multiples of 4 floats",
+                what);
+  const long long dummy = (long long)rows * ld;
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(n_lo < 1 ? 1 : n_lo), (cuuint64_t)(n_hi < 1 ? 1 : n_hi)};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)(n_lo > 1 ? stride_lo : dummy) * 4,
+                           (cuuint64_t)(n_hi > 1 ? stride_hi : dummy) * 4};
+  cuuint32_t box[4] = {KC, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed for %s (%d)", what, (int)r);
@@ -342,19 +359,28 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   ACMIL_REQUIRE(ksplit == 1 || d.split_ws != nullptr, ACMIL_E_INVALID, "gemm: k_split needs split_ws");
   GemmParams gp{};
   const int bn = d.n <= 64 ? 64 : 128;
-  int rc = make_map(&gp.ta, d.a, d.m, d.k, d.lda, d.a_batch_stride ? d.batch : 1, d.a_batch_stride, BM, "A");
+  const int zdiv = d.batch_inner > 0 ? d.batch_inner : d.batch;
+  ACMIL_REQUIRE(d.batch % zdiv == 0, ACMIL_E_INVALID, "gemm: batch %d is not a multiple of batch_inner %d", d.batch, zdiv);
+  const int n_hi = d.batch / zdiv;
+  const bool a_b = d.a_batch_stride != 0 || d.a_batch_stride2 != 0, b_b = d.b_batch_stride != 0 || d.b_batch_stride2 != 0;
+  ACMIL_REQUIRE((!a_b || ((zdiv == 1 || d.a_batch_stride) && (n_hi == 1 || d.a_batch_stride2))) &&
+                    (!b_b || ((zdiv == 1 || d.b_batch_stride) && (n_hi == 1 || d.b_batch_stride2))),
+                ACMIL_E_INVALID, "gemm: a batched operand needs a non-zero stride on every batch level in use");
+  int rc = make_map(&gp.ta, d.a, d.m, d.k, d.lda, a_b ? zdiv : 1, d.a_batch_stride, a_b ? n_hi : 1, d.a_batch_stride2, BM, "A");
   if (rc) return rc;
-  rc = make_map(&gp.tb, d.b, d.n, d.k, d.ldb, d.b_batch_stride ? d.batch : 1, d.b_batch_stride, bn, "B");
+  rc = make_map(&gp.tb, d.b, d.n, d.k, d.ldb, b_b ? zdiv : 1, d.b_batch_stride, b_b ? n_hi : 1, d.b_batch_stride2, bn, "B");
   if (rc) return rc;
+  gp.zdiv = zdiv;
+  gp.c_bs2 = d.c_batch_stride2; gp.ct_bs2 = d.ct_batch_stride2; gp.add_bs2 = d.addend_batch_stride2;
   gp.c = d.c; gp.ct = d.ct; gp.bias = d.bias; gp.addend = d.addend;
   gp.M = d.m; gp.N = d.n; gp.K = d.k;
-  gp.a_batched = d.a_batch_stride != 0; gp.b_batched = d.b_batch_stride != 0;
+  gp.a_batched = a_b; gp.b_batched = b_b;
   gp.c_batch_stride = d.c_batch_stride; gp.ldc = d.ldc;
   gp.cbw = d.col_block_width > 0 ? d.col_block_width : d.n;
   gp.cbs = d.col_block_width > 0 ? d.col_block_stride : 0;
   gp.ct_batch_stride = d.ct_batch_stride; gp.ldct = d.ldct;
   gp.add_batch_stride = d.addend_batch_stride; gp.ld_add = d.ld_addend;
-  gp.alpha = d.alpha; gp.beta = d.beta; gp.diag = d.diag; gp.relu = d.relu;
+  gp.alpha = d.alpha; gp.beta = d.beta; gp.diag = d.diag; gp.act = d.act; gp.bias_row = d.bias_per_row;
   gp.ksplit = ksplit;
   gp.k_per_split = ((((d.k + KC - 1) / KC) + ksplit - 1) / ksplit) * KC;
   gp.split_ws = d.split_ws;

@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(256) tm_landmark_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------------
 // in-place softmax over rows of length len <= 1024: one warp per row, the row lives in registers
-__global__ void __launch_bounds__(256) tm_softmax_small_kernel(float* __restrict__ a, long long rows, int len) {
+__global__ void __launch_bounds__(256) tm_softmax_small_kernel(float* __restrict__ a, long long rows, int len, long long ld) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float* r = a + row * len;
+  float* r = a + row * ld;
   float v[32];
   float mx = -INFINITY;
 #pragma unroll
@@ -422,7 +422,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
     g.c = a2; g.ldc = m; g.c_batch_stride = mm;
     TM_RUN(tm_gemm(g, st));
-    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * m + 7) / 8), 256, 0, st>>>(a2, (long long)H * m, m);
+    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * m + 7) / 8), 256, 0, st>>>(a2, (long long)H * m, m, m);
     ++g_acmil_launches;
   }
   float *z = ws + L.za, *zt = ws + L.zta, *z2 = ws + L.zb, *zt2 = ws + L.ztb;
@@ -491,7 +491,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
     g.c = sbuf; g.ldc = m; g.c_batch_stride = (int64_t)nr * m;
     TM_RUN(tm_gemm(g, st));
-    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * nr + 7) / 8), 256, 0, st>>>(sbuf, (long long)H * nr, m);
+    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * nr + 7) / 8), 256, 0, st>>>(sbuf, (long long)H * nr, m, m);
     ++g_acmil_launches;
     ACMIL_CHECK_CUDA(cudaGetLastError());
     for (int b = 0; b < s.batch; ++b) {
@@ -522,6 +522,195 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     if (d_residual && !s.padded_out) {
       g.addend = d_residual + (size_t)b * s.n * dim; g.ld_addend = dim; g.beta = 1.f;
     }
+    TM_RUN(tm_gemm(g, st));
+  }
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_softmax_rows_inplace(float* d_a, int64_t ld, int64_t rows, int32_t len, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_a && rows >= 0 && len >= 1 && len <= 1024 && ld >= len, ACMIL_E_INVALID, "softmax_rows_inplace: bad arguments");
+  if (rows == 0) return ACMIL_OK;
+  tm_softmax_small_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_a, rows, len, ld);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+// ==========================================================================================
+// ViT patch encoder (models.py:138-149 -> timm 0.9.2 VisionTransformer.forward)
+namespace {
+
+// im2col for the stride = kernel = patch convolution: col[b * np + py * g + px][c * p * p + dy * p + dx]
+__global__ void __launch_bounds__(256) tm_im2col_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int S,
+                                                        int P) {
+  const int g = S / P, kk = C * P * P;
+  const size_t total4 = (size_t)B * g * g * kk / 4;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total4; e += (size_t)gridDim.x * 256) {
+    const int k = (int)((e * 4) % kk);
+    const size_t r = (e * 4) / kk;
+    const int px = (int)(r % g), py = (int)((r / g) % g), b = (int)(r / ((size_t)g * g));
+    const int c = k / (P * P), dy = (k / P) % P, dx = k % P;
+    const float4 v = *reinterpret_cast<const float4*>(img + (((size_t)b * C + c) * S + py * P + dy) * S + px * P + dx);
+    *reinterpret_cast<float4*>(col + e * 4) = v;
+  }
+}
+
+// x[b][0][:] = cls_token + pos_embed[0]
+__global__ void tm_cls_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int dim,
+                              long long img_stride) {
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) x[(size_t)blockIdx.x * img_stride + j] = cls[j] + pos[j];
+}
+
+struct VitLayout {
+  size_t x, xn, qk, vt, s, merged, hid, total;
+  int T, Tp, np;
+};
+
+VitLayout vit_layout(const acmil_vit_shape& s) {
+  VitLayout L{};
+  const int g = s.img / s.patch;
+  L.np = g * g;
+  L.T = L.np + 1;
+  L.Tp = (L.T + 3) & ~3;
+  const size_t rows = (size_t)s.batch * L.Tp, dh = s.dim / s.heads;
+  size_t o = 0;
+  auto take = [&](size_t n) { const size_t r = o; o += align64(n); return r; };
+  L.x = take(rows * s.dim);
+  L.xn = take(rows * s.dim);
+  L.qk = take(2 * rows * s.dim);
+  L.vt = take(rows * s.dim);
+  L.s = take((size_t)s.heads * s.batch * L.T * L.Tp);
+  L.merged = take(rows * s.dim);
+  L.hid = take(std::max(rows * s.mlp_dim, (size_t)s.batch * L.np * s.in_ch * s.patch * s.patch));
+  (void)dh;
+  L.total = o;
+  return L;
+}
+
+int vit_check(const acmil_vit_shape& s) {
+  ACMIL_REQUIRE(s.batch >= 1 && s.img >= s.patch && s.patch >= 4 && s.patch % 4 == 0 && s.img % s.patch == 0 && s.in_ch >= 1,
+                ACMIL_E_INVALID, "vit: bad image shape [%d, %d, %d, %d] / patch %d", s.batch, s.in_ch, s.img, s.img, s.patch);
+  ACMIL_REQUIRE(s.dim >= 4 && s.heads >= 1 && s.dim % s.heads == 0 && (s.dim / s.heads) % 4 == 0 && s.mlp_dim % 4 == 0 && s.depth >= 1,
+                ACMIL_E_INVALID, "vit: bad dims (dim %d, heads %d, mlp %d, depth %d)", s.dim, s.heads, s.mlp_dim, s.depth);
+  const int g = s.img / s.patch;
+  ACMIL_REQUIRE(g * g + 1 <= 1024, ACMIL_E_INVALID, "vit: %d tokens exceed the 1024-token softmax kernel", g * g + 1);
+  ACMIL_REQUIRE((long long)s.batch * s.heads <= 65535, ACMIL_E_INVALID, "vit: batch * heads too large (%d x %d)", s.batch, s.heads);
+  return ACMIL_OK;
+}
+
+}  // namespace
+
+extern "C" int acmil_vit_workspace_bytes(const acmil_vit_shape* shape, size_t* bytes) {
+  ACMIL_REQUIRE(shape && bytes, ACMIL_E_INVALID, "vit: null argument");
+  TM_RUN(vit_check(*shape));
+  *bytes = vit_layout(*shape).total * sizeof(float);
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weights* w, const float* d_images, float* d_features,
+                             float* d_logits, void* d_workspace, size_t workspace_bytes, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(shape && w && d_images && d_features && d_workspace && w->blocks, ACMIL_E_INVALID, "vit: null argument");
+  const acmil_vit_shape& s = *shape;
+  TM_RUN(vit_check(s));
+  ACMIL_REQUIRE(w->d_cls_token && w->d_pos_embed && w->d_patch_w && w->d_patch_b && w->d_norm_w && w->d_norm_b, ACMIL_E_INVALID,
+                "vit: null weight");
+  ACMIL_REQUIRE(s.n_class == 0 || !d_logits || (w->d_head_w && w->d_head_b), ACMIL_E_INVALID, "vit: logits requested without a head");
+  ACMIL_REQUIRE(((uintptr_t)d_workspace & 255) == 0 && ((uintptr_t)d_images & 15) == 0, ACMIL_E_INVALID, "vit: unaligned buffers");
+  const VitLayout L = vit_layout(s);
+  ACMIL_REQUIRE(workspace_bytes >= L.total * sizeof(float), ACMIL_E_WORKSPACE, "vit: workspace %zu < %zu bytes", workspace_bytes,
+                L.total * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(d_workspace);
+  const int B = s.batch, D = s.dim, Hh = s.heads, dh = D / Hh, T = L.T, Tp = L.Tp, P = s.precise;
+  const int64_t rows = (int64_t)B * Tp;
+  float *x = ws + L.x, *xn = ws + L.xn, *qk = ws + L.qk, *vt = ws + L.vt, *S = ws + L.s, *merged = ws + L.merged, *hid = ws + L.hid;
+  ACMIL_CHECK_CUDA(cudaMemsetAsync(x, 0, (size_t)rows * D * sizeof(float), st));            // pad tokens stay finite
+  ACMIL_CHECK_CUDA(cudaMemsetAsync(merged, 0, (size_t)rows * D * sizeof(float), st));
+
+  // patch embedding: Conv2d(in_ch, dim, patch, stride = patch) as im2col + GEMM, + position embedding
+  const int kk = s.in_ch * s.patch * s.patch;
+  {
+    const size_t total4 = (size_t)B * L.np * kk / 4;
+    tm_im2col_kernel<<<(unsigned)std::min<size_t>((total4 + 255) / 256, 148 * 16), 256, 0, st>>>(d_images, hid, B, s.in_ch, s.img, s.patch);
+    tm_cls_kernel<<<B, 128, 0, st>>>(x, w->d_cls_token, w->d_pos_embed, D, (long long)Tp * D);
+    g_acmil_launches += 2;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    acmil_gemm_desc g = gemm0(P);
+    g.a = hid; g.lda = kk; g.a_batch_stride = (int64_t)L.np * kk; g.m = L.np; g.k = kk; g.batch = B;
+    g.b = w->d_patch_w; g.ldb = kk; g.n = D;
+    g.bias = w->d_patch_b;
+    g.addend = w->d_pos_embed + D; g.ld_addend = D; g.beta = 1.f;
+    g.c = x + D; g.ldc = D; g.c_batch_stride = (int64_t)Tp * D;
+    TM_RUN(tm_gemm(g, st));
+  }
+  const int64_t head_sz = rows * dh;      // one head of q (or k): [B * Tp][dh]
+  for (int i = 0; i < s.depth; ++i) {
+    const acmil_vit_block_weights& bw = w->blocks[i];
+    ACMIL_REQUIRE(bw.d_ln1_w && bw.d_ln1_b && bw.d_qkv_w && bw.d_qkv_b && bw.d_proj_w && bw.d_proj_b && bw.d_ln2_w && bw.d_ln2_b &&
+                      bw.d_fc1_w && bw.d_fc1_b && bw.d_fc2_w && bw.d_fc2_b,
+                  ACMIL_E_INVALID, "vit: null weight in block %d", i);
+    // x = x + proj(softmax(q k^T / sqrt(dh)) v),  q, k, v = qkv(LN(x))
+    TM_RUN(acmil_layernorm_rows(x, D, rows, D, bw.d_ln1_w, bw.d_ln1_b, s.ln_eps, xn, D, stream));
+    {
+      acmil_gemm_desc g = gemm0(P);      // q, k head-major: [which * heads + head][B * Tp][dh]
+      g.a = xn; g.lda = D; g.m = (int)rows; g.k = D; g.batch = 1;
+      g.b = bw.d_qkv_w; g.ldb = D; g.n = 2 * D; g.bias = bw.d_qkv_b;
+      g.c = qk; g.ldc = dh; g.col_block_width = dh; g.col_block_stride = head_sz;
+      TM_RUN(tm_gemm(g, st));
+      acmil_gemm_desc gv = gemm0(P);     // v transposed: [dim][B * Tp]
+      gv.a = bw.d_qkv_w + (size_t)2 * D * D; gv.lda = D; gv.m = D; gv.k = D; gv.batch = 1;
+      gv.b = xn; gv.ldb = D; gv.n = (int)rows;
+      gv.bias = bw.d_qkv_b + 2 * D; gv.bias_per_row = 1;
+      gv.c = vt; gv.ldc = rows;
+      TM_RUN(tm_gemm(gv, st));
+    }
+    {
+      acmil_gemm_desc g = gemm0(P);      // scores, batch z = head * B + image
+      g.batch = Hh * B; g.batch_inner = B;
+      g.a = qk; g.lda = dh; g.a_batch_stride = (int64_t)Tp * dh; g.a_batch_stride2 = head_sz; g.m = T; g.k = dh;
+      g.b = qk + (size_t)Hh * head_sz; g.ldb = dh; g.b_batch_stride = (int64_t)Tp * dh; g.b_batch_stride2 = head_sz; g.n = T;
+      g.c = S; g.ldc = Tp; g.c_batch_stride = (int64_t)T * Tp; g.c_batch_stride2 = (int64_t)B * T * Tp;
+      g.alpha = 1.f / sqrtf((float)dh);
+      TM_RUN(tm_gemm(g, st));
+      TM_RUN(acmil_softmax_rows_inplace(S, Tp, (int64_t)Hh * B * T, T, stream));
+      acmil_gemm_desc g2 = gemm0(P);     // attn @ v -> heads merged as [B * Tp][dim]
+      g2.batch = Hh * B; g2.batch_inner = B;
+      g2.a = S; g2.lda = Tp; g2.a_batch_stride = (int64_t)T * Tp; g2.a_batch_stride2 = (int64_t)B * T * Tp; g2.m = T; g2.k = T;
+      g2.b = vt; g2.ldb = rows; g2.b_batch_stride = Tp; g2.b_batch_stride2 = (int64_t)dh * rows; g2.n = dh;
+      g2.c = merged; g2.ldc = D; g2.c_batch_stride = (int64_t)Tp * D; g2.c_batch_stride2 = dh;
+      TM_RUN(tm_gemm(g2, st));
+      acmil_gemm_desc g3 = gemm0(P);     // proj + residual, in place
+      g3.a = merged; g3.lda = D; g3.m = (int)rows; g3.k = D; g3.batch = 1;
+      g3.b = bw.d_proj_w; g3.ldb = D; g3.n = D; g3.bias = bw.d_proj_b;
+      g3.addend = x; g3.ld_addend = D; g3.beta = 1.f;
+      g3.c = x; g3.ldc = D;
+      TM_RUN(tm_gemm(g3, st));
+    }
+    // x = x + fc2(gelu(fc1(LN(x))))
+    TM_RUN(acmil_layernorm_rows(x, D, rows, D, bw.d_ln2_w, bw.d_ln2_b, s.ln_eps, xn, D, stream));
+    {
+      acmil_gemm_desc g = gemm0(P);
+      g.a = xn; g.lda = D; g.m = (int)rows; g.k = D; g.batch = 1;
+      g.b = bw.d_fc1_w; g.ldb = D; g.n = s.mlp_dim; g.bias = bw.d_fc1_b; g.act = 2;
+      g.c = hid; g.ldc = s.mlp_dim;
+      TM_RUN(tm_gemm(g, st));
+      acmil_gemm_desc g2 = gemm0(P);
+      g2.a = hid; g2.lda = s.mlp_dim; g2.m = (int)rows; g2.k = s.mlp_dim; g2.batch = 1;
+      g2.b = bw.d_fc2_w; g2.ldb = s.mlp_dim; g2.n = D; g2.bias = bw.d_fc2_b;
+      g2.addend = x; g2.ld_addend = D; g2.beta = 1.f;
+      g2.c = x; g2.ldc = D;
+      TM_RUN(tm_gemm(g2, st));
+    }
+  }
+  // final norm, class token (global_pool = 'token'), optional CustomModel.head
+  TM_RUN(acmil_layernorm_rows(x, (int64_t)Tp * D, B, D, w->d_norm_w, w->d_norm_b, s.ln_eps, d_features, D, stream));
+  if (d_logits && s.n_class > 0) {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = d_features; g.lda = D; g.m = B; g.k = D; g.batch = 1;
+    g.b = w->d_head_w; g.ldb = D; g.n = s.n_class; g.bias = w->d_head_b;
+    g.c = d_logits; g.ldc = s.n_class;
     TM_RUN(tm_gemm(g, st));
   }
   return ACMIL_OK;

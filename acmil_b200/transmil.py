@@ -40,8 +40,8 @@ def _no_grad_path(what, *tensors):
         raise NotImplementedError(f"{what}: the B200 TransMIL kernels are forward-only; call under torch.no_grad()")
 
 
-def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu=False, precise=True, out=None,
-            out_t=None, k_split=1):
+def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu=False, gelu=False, precise=True,
+            out=None, out_t=None, k_split=1):
     """out[..., m, n] = alpha * a[..., m, k] @ b[..., n, k]^T (+ diag I) (+ bias) (+ beta * addend) (relu).
 
     ``a`` / ``b`` are fp32 CUDA tensors, 2-D or 3-D (leading batch; a 2-D operand is shared by the batch).
@@ -75,7 +75,8 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
     if addend is not None:
         ad = (addend if addend.dim() == 3 else addend.unsqueeze(0)).contiguous()
         g.addend, g.ld_addend, g.addend_batch_stride = _ptr(ad), ad.stride(1), ad.stride(0) if ad.shape[0] > 1 else 0
-    g.alpha, g.beta, g.diag, g.relu, g.precise = float(alpha), float(beta), float(diag), int(relu), int(precise)
+    g.alpha, g.beta, g.diag, g.precise = float(alpha), float(beta), float(diag), int(precise)
+    g.act = 2 if gelu else int(relu)
     ws = None
     if k_split > 1:
         ws = torch.empty(k_split * batch * m * n, device=a.device, dtype=torch.float32)

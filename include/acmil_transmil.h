@@ -13,6 +13,9 @@
  *                               optionally fused with the pre-LayerNorm and the residual add of
  *                               TransLayer.forward (transMIL.py:25-28)
  *   acmil_ppeg_fwd           <- PPEG.forward (transMIL.py:38-45)
+ *   acmil_vit_workspace_bytes, acmil_vit_fwd
+ *                            <- the ViT-S/16 patch encoder of Step2_feature_extract.py (models.py:138-149,
+ *                               166-179; timm 0.9.2 VisionTransformer.forward)
  */
 #ifndef ACMIL_TRANSMIL_H
 #define ACMIL_TRANSMIL_H
@@ -32,7 +35,10 @@ extern "C" {
  * A batch stride of 0 shares the operand between batch entries.  All strides in floats; operand
  * pointers 16-byte aligned, lda / ldb multiples of 4.  precise = 1: 3xTF32 split (fp32-faithful,
  * ~2^-21), precise = 0: plain TF32 (~2^-10).  k_split > 1 partitions K over that many CTAs per tile
- * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction). */
+ * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction).
+ * Two-level batches: with batch_inner > 0, entry z uses offsets (z % batch_inner) * X_batch_stride +
+ * (z / batch_inner) * X_batch_stride2 for every operand X (e.g. z = head * images + image).
+ * act: 0 none, 1 relu, 2 exact (erf) GELU -- applied last. */
 typedef struct acmil_gemm_desc {
   const float* a;
   const float* b;
@@ -48,9 +54,12 @@ typedef struct acmil_gemm_desc {
   int32_t k_split;
   int64_t col_block_stride;
   float alpha, beta, diag;
-  int32_t relu;
+  int32_t act;
   int32_t precise;
-  int32_t reserved[3];
+  int32_t batch_inner;
+  int32_t bias_per_row;           /* 1: bias is indexed by the output row instead of the column */
+  int32_t reserved;
+  int64_t a_batch_stride2, b_batch_stride2, c_batch_stride2, ct_batch_stride2, addend_batch_stride2;
 } acmil_gemm_desc;
 
 ACMIL_API int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream);
@@ -98,6 +107,40 @@ ACMIL_API int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const acm
 ACMIL_API int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32_t gw, int32_t c, const float* d_w7,
                              const float* d_b7, const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3,
                              float* d_out, void* stream);
+
+/* in-place softmax over `rows` rows of length len <= 1024 stored with leading dimension ld. */
+ACMIL_API int acmil_softmax_rows_inplace(float* d_a, int64_t ld, int64_t rows, int32_t len, void* stream);
+
+/* ---- ViT patch encoder (models.py:138-149 vit_small -> timm 0.9.2 VisionTransformer(img_size=224,
+ * patch_size=16, embed_dim=384, num_heads=6, num_classes=0): conv patch embedding, class token + learned
+ * position embedding, depth x [LN, MHSA with qkv bias, LN, MLP with exact GELU], final LN, class-token
+ * feature; CustomModel.head (models.py:166-179) optionally applied to the feature). */
+typedef struct acmil_vit_shape {
+  int32_t batch, img, patch, in_ch;   /* images: [batch, in_ch, img, img] fp32 */
+  int32_t dim, depth, heads, mlp_dim;
+  int32_t n_class;                    /* 0: no head */
+  int32_t precise;
+  float ln_eps;                       /* 1e-6 in timm's ViT */
+  int32_t reserved[5];
+} acmil_vit_shape;
+
+typedef struct acmil_vit_block_weights {
+  const float *d_ln1_w, *d_ln1_b, *d_qkv_w, *d_qkv_b, *d_proj_w, *d_proj_b;
+  const float *d_ln2_w, *d_ln2_b, *d_fc1_w, *d_fc1_b, *d_fc2_w, *d_fc2_b;
+} acmil_vit_block_weights;
+
+typedef struct acmil_vit_weights {
+  const float *d_cls_token, *d_pos_embed;     /* [1,1,dim], [1, 1 + (img/patch)^2, dim] */
+  const float *d_patch_w, *d_patch_b;         /* patch_embed.proj: [dim, in_ch, patch, patch], [dim] */
+  const float *d_norm_w, *d_norm_b;           /* final norm */
+  const float *d_head_w, *d_head_b;           /* [n_class, dim], [n_class] or NULL */
+  const acmil_vit_block_weights* blocks;      /* HOST array of `depth` entries */
+} acmil_vit_weights;
+
+ACMIL_API int acmil_vit_workspace_bytes(const acmil_vit_shape* shape, size_t* bytes);
+/* d_features: [batch, dim]; d_logits: [batch, n_class] or NULL. */
+ACMIL_API int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weights* w, const float* d_images, float* d_features,
+                            float* d_logits, void* d_workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
