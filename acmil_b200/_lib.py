@@ -129,6 +129,10 @@ SYMBOLS = {
     "acmil_vit_workspace_bytes": (C.c_int, [C.POINTER(VitShape), _SIZE_P]),
     "acmil_vit_fwd": (C.c_int, [C.POINTER(VitShape), C.POINTER(VitWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
+    "acmil_preprocess_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _SIZE_P]),
+    "acmil_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_f32_to_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "acmil_ppeg_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

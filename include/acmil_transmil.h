@@ -142,6 +142,17 @@ ACMIL_API int acmil_vit_workspace_bytes(const acmil_vit_shape* shape, size_t* by
 ACMIL_API int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weights* w, const float* d_images, float* d_features,
                             float* d_logits, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- feature-extraction loop (Step2_feature_extract.py:35-71, 164-167; datasets/dataset_h5.py:20-37) ----
+ * d_img: uint8 RGB patches [batch, in_h, in_w, 3] (PIL layout) -> d_out fp32 [batch, 3, out, out] =
+ * Normalize(mean, std)(ToTensor(Resize(out)(patch))); the resize is Pillow's antialiased 8-bit BILINEAR resample,
+ * byte-exact.  mean3 / std3 are HOST arrays of 3 floats. */
+ACMIL_API int acmil_preprocess_workspace_bytes(int32_t in_h, int32_t in_w, int32_t out_size, size_t* bytes);
+ACMIL_API int acmil_preprocess_u8(const uint8_t* d_img, int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size,
+                                  const float* mean3, const float* std3, float* d_out, void* d_workspace,
+                                  size_t workspace_bytes, void* stream);
+/* d_y[i] = (fp16) d_x[i], round to nearest even: the `.astype(np.float16)` of the feature store. */
+ACMIL_API int acmil_f32_to_f16(const float* d_x, void* d_y, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
