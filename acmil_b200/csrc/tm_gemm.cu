@@ -5,17 +5,21 @@
 // Both operands are fp32, K contiguous (nn.Linear weights, q/k/v rows, attention rows).  The reference computes every one
 // of these products in IEEE fp32 (torch.matmul / einsum / nn.Linear: nystrom_attention.py:83,119-121,135,147 and
 // transMIL.py:61,89), so the tensor-core path is an error-compensated TF32 split
-//      a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo ,   a_hi = a & 0xFFFFE000 (a valid TF32), a_lo = a - a_hi (exact)
+//      a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo ,   a_hi = a & 0xFFFFE000 (what the MMA reads of a), a_lo = a - a_hi (exact)
 // i.e. 3 kind::tf32 MMAs per product with fp32 accumulation in TMEM (~2^-21 relative).  PRECISE = false runs one
 // MMA on the raw operands (plain TF32, ~2^-10).
 //
-// One CTA per 128 x BN output tile, 192 threads:
-//   warp 0     TMA producer: 128 x 32 fp32 boxes of A and B (SWIZZLE_128B, 3-D maps: K, rows, batch), 3-stage ring
-//   warp 1     MMA issuer (one elected thread), accumulator in TMEM, tcgen05.commit frees the ring stage
-//   warps 2-5  split each landed stage in place into hi (masked) and lo tiles, then run the epilogue:
-//              thread = row (tcgen05.ld 32x32b), scale / diagonal / bias / addend / relu, optional second store of the
-//              transposed tile (the Moore-Penrose iteration needs every product in both orientations).
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles; 320 threads:
+//   warp 0     TMA producer: 128 x 32 fp32 boxes of A and B (SWIZZLE_128B, 4-D maps: K, rows, batch_lo, batch_hi),
+//              3-stage ring that keeps running across tile boundaries
+//   warp 1     MMA issuer (one elected thread), two accumulators in TMEM, tcgen05.commit frees the ring stage
+//   warps 2-5  produce the lo tile of each landed stage (the raw tile is the hi operand: the MMA ignores the low bits)
+//   warps 6-9  epilogue of the previous tile while the next one accumulates: thread = row (tcgen05.ld 32x32b),
+//              scale / diagonal / bias / addend / activation, optional second store of the transposed tile (the
+//              Moore-Penrose iteration needs every product in both orientations).
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "acmil_transmil.h"
 #include "gp_common.cuh"
@@ -24,7 +28,7 @@
 namespace {
 using namespace sm100;
 
-constexpr int GT = 192;          // threads per CTA
+constexpr int GT = 320;          // threads per CTA: TMA, MMA, 4 splitter warps, 4 epilogue warps
 constexpr int BM = 128;          // tile rows
 constexpr int KC = 32;           // fp32 columns per stage = one 128-byte swizzle row
 constexpr int NST = 3;           // ring stages
@@ -52,13 +56,15 @@ struct GemmParams {
   int ksplit;                    // > 1: blockIdx.z = batch * ksplit + split; raw partial tiles go to split_ws
   int k_per_split;               // multiple of KC
   float* split_ws;               // [batch * ksplit][M][N]
+  int ntiles;
 };
 
 struct Bars {
   uint64_t full[NST];            // TMA bytes landed
   uint64_t split[NST];           // hi/lo tiles written (4 converter warps)
   uint64_t empty[NST];           // MMAs that read the stage have completed
-  uint64_t acc_full;
+  uint64_t acc_full[2];          // accumulator buffer complete (tcgen05.commit)
+  uint64_t acc_empty[2];         // accumulator buffer drained by the 4 epilogue warps
   uint32_t tmem;
 };
 
@@ -93,21 +99,35 @@ __host__ __device__ constexpr uint32_t stage_bytes(bool precise) {
   return (TILE_BYTES + (uint32_t)BN * KC * 4) * (precise ? 2u : 1u);
 }
 
+struct TileCoord {
+  int m0, n0, bz, split;
+};
+
+// tiles: n fastest (CTAs that run concurrently share the A rows in L2), then m, then batch * ksplit
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, int ntn, int ntm, int bn) {
+  TileCoord t;
+  t.n0 = (tile % ntn) * bn;
+  t.m0 = ((tile / ntn) % ntm) * BM;
+  const int z = tile / (ntn * ntm);
+  t.bz = p.ksplit > 1 ? z / p.ksplit : z;
+  t.split = p.ksplit > 1 ? z % p.ksplit : 0;
+  return t;
+}
+
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and the two TMEM
+// accumulators run across tile boundaries, so TMA prefetch, MMAs and the epilogue of consecutive tiles overlap.
 template <int BN, bool PRECISE>
 __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t B_BYTES = (uint32_t)BN * KC * 4;
   constexpr uint32_t STAGE = stage_bytes<BN>(PRECISE);
+  constexpr uint32_t TM_COLS = 2 * (BN < 32 ? 32 : BN);
   Bars* bars = reinterpret_cast<Bars*>(smem + NST * STAGE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int bz = p.ksplit > 1 ? blockIdx.z / p.ksplit : blockIdx.z;
-  const int kbeg = p.ksplit > 1 ? (blockIdx.z % p.ksplit) * p.k_per_split : 0;
-  const int kend = p.ksplit > 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
-  const int nchunk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
-  const int zlo = bz % p.zdiv, zhi = bz / p.zdiv;
+  const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM;
+  const int ntiles = p.ntiles;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
@@ -115,13 +135,16 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
       mbar_init(&bars->split[s], 4);
       mbar_init(&bars->empty[s], 1);
     }
-    mbar_init(&bars->acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 4);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&p.ta);
     tma_prefetch_desc(&p.tb);
   }
   if (warp == 1) {
-    tmem_alloc<1>(&bars->tmem, BN < 32 ? 32 : BN);
+    tmem_alloc<1>(&bars->tmem, TM_COLS);
     tmem_relinquish<1>();
   }
   tc_fence_before();
@@ -129,146 +152,184 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
   tc_fence_after();
   const uint32_t tm = bars->tmem;
 
+  auto k_range = [&](const TileCoord& t, int& kbeg, int& nchunk) {
+    kbeg = p.ksplit > 1 ? t.split * p.k_per_split : 0;
+    const int kend = p.ksplit > 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
+    nchunk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int c = 0; c < nchunk; ++c) {
-        const int s = c % NST;
-        const uint32_t ph = (uint32_t)(c / NST) & 1u;
-        mbar_wait(&bars->empty[s], ph ^ 1u);
-        unsigned char* st = smem + s * STAGE;
-        mbar_expect_tx(&bars->full[s], TILE_BYTES + B_BYTES);
-        tma_load_4d(st, &p.ta, kbeg + c * KC, m0, p.a_batched ? zlo : 0, p.a_batched ? zhi : 0, &bars->full[s]);
-        tma_load_4d(st + TILE_BYTES, &p.tb, kbeg + c * KC, n0, p.b_batched ? zlo : 0, p.b_batched ? zhi : 0, &bars->full[s]);
+      uint32_t ctr = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+        int kbeg, nchunk;
+        k_range(t, kbeg, nchunk);
+        const int zlo = t.bz % p.zdiv, zhi = t.bz / p.zdiv;
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          mbar_wait(&bars->empty[s], ph ^ 1u);
+          unsigned char* st = smem + s * STAGE;
+          mbar_expect_tx(&bars->full[s], TILE_BYTES + B_BYTES);
+          tma_load_4d(st, &p.ta, kbeg + c * KC, t.m0, p.a_batched ? zlo : 0, p.a_batched ? zhi : 0, &bars->full[s]);
+          tma_load_4d(st + TILE_BYTES, &p.tb, kbeg + c * KC, t.n0, p.b_batched ? zlo : 0, p.b_batched ? zhi : 0, &bars->full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tf32_idesc(BM, BN);
-      for (int c = 0; c < nchunk; ++c) {
-        const int s = c % NST;
-        const uint32_t ph = (uint32_t)(c / NST) & 1u;
-        mbar_wait(PRECISE ? &bars->split[s] : &bars->full[s], ph);
+      uint32_t ctr = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+        int kbeg, nchunk;
+        k_range(t, kbeg, nchunk);
+        const uint32_t buf = it & 1u;
+        mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES;
-        const uint32_t a_lo = b_hi + B_BYTES, b_lo = a_lo + TILE_BYTES;
+        const uint32_t tacc = tm + buf * (TM_COLS / 2);
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          mbar_wait(PRECISE ? &bars->split[s] : &bars->full[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES;
+          const uint32_t a_lo = b_hi + B_BYTES, b_lo = a_lo + TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row
-          const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-          if constexpr (PRECISE) {
-            umma_tf32(tm, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
-            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
-            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
-          } else {
-            umma_tf32(tm, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+          for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            if constexpr (PRECISE) {
+              // the tensor core ignores the 13 low mantissa bits of a TF32 operand (measured: identical results with
+              // and without masking), so the raw fp32 tile IS the hi operand; only the lo tile is produced
+              umma_tf32(tacc, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
+              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
+            } else {
+              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+            }
           }
+          umma_commit(&bars->empty[s]);
         }
-        umma_commit(&bars->empty[s]);
+        if (nchunk > 0) umma_commit(&bars->acc_full[buf]);
+        else mbar_arrive(&bars->acc_full[buf]);      // empty K range (k-split tail): the epilogue writes zeros
       }
-      if (nchunk > 0) umma_commit(&bars->acc_full);
-      else mbar_arrive(&bars->acc_full);          // empty K range (k-split tail): the tile is all zeros
+    }
+  } else if (warp < 6) {
+    if constexpr (PRECISE) {
+      // lo = x - (x with the 13 low mantissa bits cleared), written at the same swizzled position of the lo tiles
+      const int ct = (warp - 2) * 32 + lane;             // 0..127
+      constexpr int NV = (TILE_BYTES + B_BYTES) / 16;    // float4 slots of {A, B}
+      uint32_t ctr = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+        int kbeg, nchunk;
+        k_range(t, kbeg, nchunk);
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          mbar_wait(&bars->full[s], ph);
+          const float4* hi = reinterpret_cast<const float4*>(smem + s * STAGE);
+          float4* lo = reinterpret_cast<float4*>(smem + s * STAGE + TILE_BYTES + B_BYTES);
+#pragma unroll 8
+          for (int i = ct; i < NV; i += 128) {
+            const float4 v = hi[i];
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            lo[i] = l;
+          }
+          fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->split[s]);
+        }
+      }
     }
   } else {
-    const int cw = warp - 2;                     // 0..3
-    if constexpr (PRECISE) {
-      // hi/lo split in place: same swizzled position in the lo tile, so no address arithmetic beyond the offset
-      const int ct = cw * 32 + lane;             // 0..127
-      constexpr int NV = (TILE_BYTES + B_BYTES) / 16;      // float4 slots of {A, B}
-      for (int c = 0; c < nchunk; ++c) {
-        const int s = c % NST;
-        const uint32_t ph = (uint32_t)(c / NST) & 1u;
-        mbar_wait(&bars->full[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE);
-        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE + TILE_BYTES + B_BYTES);
-#pragma unroll 4
-        for (int i = ct; i < NV; i += 128) {
-          const float4 v = hi[i];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          hi[i] = h;
-          lo[i] = l;
-        }
-        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->split[s]);
-      }
-    }
-    // ---------------- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 ----------------
+    // ---------------- epilogue warps 6..9: warp w may touch TMEM lanes 32 (w % 4) .. +31 ----------------
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(&bars->acc_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < p.M;
-    float* crow = p.c ? p.c + (size_t)zlo * p.c_batch_stride + (size_t)zhi * p.c_bs2 + (size_t)row * p.ldc : nullptr;
-    const float* arow =
-        p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
-    float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+      int kbeg, nchunk;
+      k_range(t, kbeg, nchunk);
+      const int zlo = t.bz % p.zdiv, zhi = t.bz / p.zdiv;
+      const uint32_t buf = it & 1u;
+      const int row = t.m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&bars->acc_full[buf], (it >> 1) & 1u);
+      tc_fence_after();
+      float* crow = p.c ? p.c + (size_t)zlo * p.c_batch_stride + (size_t)zhi * p.c_bs2 + (size_t)row * p.ldc : nullptr;
+      const float* arow =
+          p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
+      float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
+      const int zsplit = p.ksplit > 1 ? t.bz * p.ksplit + t.split : 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_wait_ld();
-      if (n0 + c0 >= p.N) continue;
-      if (p.ksplit > 1) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (t.n0 + c0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tm + buf * (TM_COLS / 2) + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_wait_ld();
+        if (p.ksplit > 1) {
+          if (row_ok) {
+            float* dst = p.split_ws + ((size_t)zsplit * p.M + row) * p.N + t.n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (t.n0 + c0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
+          }
+          continue;
+        }
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = t.n0 + c0 + j;
+          float x = p.alpha * __uint_as_float(v[j]);
+          if (p.diag != 0.f && col == row) x += p.diag;
+          if (p.bias && col < p.N) x += p.bias_row ? (row_ok ? p.bias[row] : 0.f) : p.bias[col];
+          r[j] = x;
+        }
         if (row_ok) {
-          float* dst = p.split_ws + ((size_t)blockIdx.z * p.M + row) * p.N + n0 + c0;
+          if (arow) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
-        }
-        continue;
-      }
-      float r[32];
+            for (int j = 0; j < 32; ++j)
+              if (t.n0 + c0 + j < p.N) r[j] = fmaf(p.beta, arow[t.n0 + c0 + j], r[j]);
+          }
+          if (p.act) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        float t = p.alpha * __uint_as_float(v[j]);
-        if (p.diag != 0.f && col == row) t += p.diag;
-        if (p.bias && col < p.N) t += p.bias_row ? (row_ok ? p.bias[row] : 0.f) : p.bias[col];
-        r[j] = t;
-      }
-      if (row_ok) {
-        if (arow) {
+            for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
+          }
+          if (crow) {
+            if (p.vec_ok && t.n0 + c0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) r[j] = fmaf(p.beta, arow[n0 + c0 + j], r[j]);
-        }
-        if (p.act) {
+              for (int j = 0; j < 32; j += 4) {
+                const int col = t.n0 + c0 + j;
+                float* dst = crow + (size_t)(col / p.cbw) * p.cbs + col % p.cbw;
+                *reinterpret_cast<float4*>(dst) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+              }
+            } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
-        }
-        if (crow) {
-          if (p.vec_ok && n0 + c0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int col = n0 + c0 + j;
-              float* dst = crow + (size_t)(col / p.cbw) * p.cbs + col % p.cbw;
-              *reinterpret_cast<float4*>(dst) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+              for (int j = 0; j < 32; ++j) {
+                const int col = t.n0 + c0 + j;
+                if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
+              }
             }
-          } else {
+          }
+          if (ctb) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int col = n0 + c0 + j;
-              if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
+              const int col = t.n0 + c0 + j;
+              if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
             }
           }
         }
-        if (ctb) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n0 + c0 + j;
-            if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
-          }
-        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);      // this warp's TMEM reads of the buffer are complete
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<1>(tm, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_dealloc<1>(tm, TM_COLS);
 }
 
 // k-split: sum the partial tiles in a fixed order, then the same epilogue terms
@@ -334,8 +395,17 @@ int launch(const GemmParams& gp, int batch, cudaStream_t st) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_gemm_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((gp.N + BN - 1) / BN, (gp.M + BM - 1) / BM, batch * (gp.ksplit > 1 ? gp.ksplit : 1));
-  tm_gemm_kernel<BN, PRECISE><<<grid, GT, smem, st>>>(gp);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    ACMIL_CHECK_CUDA(cudaGetDevice(&dev));
+    ACMIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmParams gq = gp;
+  const long long tiles = (long long)((gp.N + BN - 1) / BN) * ((gp.M + BM - 1) / BM) * batch * (gp.ksplit > 1 ? gp.ksplit : 1);
+  ACMIL_REQUIRE(tiles < (1ll << 31), ACMIL_E_INVALID, "gemm: too many tiles");
+  gq.ntiles = (int)tiles;
+  tm_gemm_kernel<BN, PRECISE><<<(unsigned)std::min<long long>(tiles, n_sm), GT, smem, st>>>(gq);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   if (gp.ksplit > 1) {
@@ -355,7 +425,6 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
                 d.n, d.k, d.batch);
   ACMIL_REQUIRE(d.a && d.b && (d.c || d.ct), ACMIL_E_INVALID, "gemm: null operand");
   const int ksplit = d.k_split > 1 ? d.k_split : 1;
-  ACMIL_REQUIRE((long long)d.batch * ksplit <= 65535 && (d.m + BM - 1) / BM <= 65535, ACMIL_E_INVALID, "gemm: grid too large");
   ACMIL_REQUIRE(ksplit == 1 || d.split_ws != nullptr, ACMIL_E_INVALID, "gemm: k_split needs split_ws");
   GemmParams gp{};
   const int bn = d.n <= 64 ? 64 : 128;
@@ -384,6 +453,7 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.ksplit = ksplit;
   gp.k_per_split = ((((d.k + KC - 1) / KC) + ksplit - 1) / ksplit) * KC;
   gp.split_ws = d.split_ws;
+
   gp.vec_ok = d.c != nullptr && ((uintptr_t)d.c & 15) == 0 && d.ldc % 4 == 0 && gp.cbw % 4 == 0 && gp.cbs % 4 == 0 &&
               d.c_batch_stride % 4 == 0;
   if (d.precise) return bn == 64 ? launch<64, true>(gp, d.batch, st) : launch<128, true>(gp, d.batch, st);

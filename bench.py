@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil"],
+    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit"],
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
     ap.add_argument("--dim", type=int, default=512, help="transmil: D_inner")
     ap.add_argument("--d-feat", type=int, default=512, help="transmil: D_feat")
@@ -326,14 +326,14 @@ def run_ours(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.workload == "transmil":
-        import bench_transmil
+    if args.workload in ("transmil", "vit"):
+        mod = __import__("bench_" + args.workload)
         if args.impl == "reference":
-            bench_transmil.run_reference(args)
+            mod.run_reference(args)
         elif not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (acmil_b200 has no CPU path); use --impl reference for the CPU arm")
         else:
-            bench_transmil.run_ours(args, ClockSampler)
+            mod.run_ours(args, ClockSampler)
     elif args.impl == "reference":
         run_reference(args)
     else:
