@@ -229,7 +229,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA) =====================================
-    if (cta == 0 && lane == 0 && T > 0) {
+    // The whole warp runs the scheduler on identical values; only the tcgen05 instructions sit under elect_one().
+    if (cta == 0 && T > 0) {
       PROF_DECL();
       const long long t_start = clock64();
       { PROF_T0(); mbar_wait_cluster(&bars->w_ready, 0); PROF_ADD(0); }  // both CTAs' weight images have landed
@@ -245,15 +246,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         tc_fence_after();
         const uint32_t xa_hi = tm + TM_X + q * 32, xa_lo = xa_hi + 16;
         const uint32_t boff = (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 64u;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
-          umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
-          umma_ts<2>(tm + TM_D1, xa_lo + ks * 8, bhi, idesc, 1u);
-          umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, blo, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
+            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
+            umma_ts<2>(tm + TM_D1, xa_lo + ks * 8, bhi, idesc, 1u);
+            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, blo, idesc, 1u);
+          }
+          umma_commit_2sm(&bars->xop_empty[q], 3);
+          if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
         }
-        umma_commit_2sm(&bars->xop_empty[q], 3);
-        if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
+        __syncwarp();
         ++xc;
         return true;
       };
@@ -266,15 +270,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         const uint32_t n_use = 2u * (uint32_t)t + (uint32_t)(qr >> 1);      // how often buffer b was used before
         if (n_use > 0 && !mbar_test_wait(&bars->d2_empty[b], (n_use - 1u) & 1u)) return false;
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t boff = (uint32_t)(qr * 2 + (ks >> 2)) * 4096u + (uint32_t)(ks & 3) * 32u;
-          const uint64_t bhi = umma_desc_k_sw128(wg_hi + boff), blo = umma_desc_k_sw128(wg_lo + boff);
-          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, bhi, idesc64, ks ? 1u : 0u);
-          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HLO + ks * 8, bhi, idesc64, 1u);
-          umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, blo, idesc64, 1u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t boff = (uint32_t)(qr * 2 + (ks >> 2)) * 4096u + (uint32_t)(ks & 3) * 32u;
+            const uint64_t bhi = umma_desc_k_sw128(wg_hi + boff), blo = umma_desc_k_sw128(wg_lo + boff);
+            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, bhi, idesc64, ks ? 1u : 0u);
+            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HLO + ks * 8, bhi, idesc64, 1u);
+            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, blo, idesc64, 1u);
+          }
+          umma_commit_2sm(&bars->d2_full[b], 3);
         }
-        umma_commit_2sm(&bars->d2_full[b], 3);
+        __syncwarp();
         return true;
       };
       // issue order: the gate quarters of tile t have priority (the epilogue is waiting for them); chunks of the
@@ -284,14 +291,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         int qr = 0, c = 0;
         const int nc = (t + 1 < T) ? NCH : 0;
         while (qr < 4 || c < nc) {
+#if GP_UMMA_PROF
+          const long long t_it = clock64();
+#endif
           if (qr < 4 && g2_try(t, qr)) { ++qr; continue; }
           if (c < nc && g1_try(t + 1, c)) { ++c; continue; }
+#if GP_UMMA_PROF
+          {   // nothing could be issued: attribute the idle poll to what blocks each GEMM
+            const long long dt = clock64() - t_it;
+            if (c < nc) {
+              if (c == 0 && !mbar_test_wait(&bars->d1_empty, (uint32_t)t & 1u)) prof[1] += dt; else prof[2] += dt;
+            } else prof[5] += dt;
+            if (qr < 4) {
+              if (qr == 0 && !mbar_test_wait(&bars->hop_full, (uint32_t)t & 1u)) prof[3] += dt; else prof[4] += dt;
+            } else prof[6] += dt;
+          }
+#endif
         }
       }
 #if GP_UMMA_PROF
       prof[7] = clock64() - t_start;
+      if (lane == 0) PROF_FLUSH(8);
 #endif
-      PROF_FLUSH(8);
     }
     __syncwarp();
   } else if (warp == 3) {
@@ -354,22 +375,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     const int lane_base = q * 32 + hs * 16;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const int rg = lane >> 2, cp = lane & 3;
-    float* tbuf = reinterpret_cast<float*>(smem + sm.tbuf + e_idx * 1024);   // [16 rows][16 feats]
     float* psw = reinterpret_cast<float*>(smem + sm.ps + e_idx * 512);       // [16 rows][8]
     const float* cstp = reinterpret_cast<const float*>(smem + sm.cst);
     constexpr int CREC = cst_rec(KB);
     const int L = 128;
     const int cap = seg.n_masked_cap;
-    const int jf = lane & 15, rs = lane >> 4;     // pool: feature inside the 16-feature chunk, row subset
-    const float* tE0 = tbuf + rs * (128 + 16) + jf;          // even i, swizzle phase 0
-    const float* tE1 = tbuf + rs * (128 + 16) + (jf ^ 8);    // even i, phase 1
-    const float* tO0 = tbuf + rs * (128 - 16) + jf;          // odd i
-    const float* tO1 = tbuf + rs * (128 - 16) + (jf ^ 8);
-    const float* pE = psw + rs * (64 + 8);
-    const float* pO = psw + rs * (64 - 8);
     const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
 
-    float l_run[KB], acc[8][KB];     // l_run: per-lane partial of sum exp(score)
+    // Softmax-pool state of this warp's stream.  Numerators are p' = exp(s - m_ref[k]) * 2^PSH against a per-warp
+    // reference m_ref[k] that only grows, and only when a taken row exceeds it by more than REF_SLACK nats (then l and
+    // acc are rescaled: rare), so p' <= 2^15 always fits the fp16 hi/lo operands of the pool's tensor-core step.
+    // acc is the set of mma.sync D fragments: acc[j][0..1] = feature 16j + rg, branches 2cp, 2cp + 1;
+    // acc[j][2..3] = feature 16j + rg + 8.
+    constexpr float PSH = 4.f, REF_SLACK = 7.6f;       // (7.6 log2e + 4 < 15)
+    float l_run[KB], m_ref[KB], c_ref[KB], acc[8][4];     // l_run: per-lane partial of sum p'; c_ref = PSH - m_ref log2e
     CandShared* cs = reinterpret_cast<CandShared*>(smem + sm.cand);
     const int rcap = seg.rec_cap;
     float* sc_all = reinterpret_cast<float*>(smem + sm.ps);     // [8 warps][16 rows][8]: scores, later softmax numerators
@@ -391,8 +410,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         l_run[k] = 0.f;
+        m_ref[k] = -INFINITY;
+        c_ref[k] = INFINITY;
+      }
 #pragma unroll
-        for (int g = 0; g < 8; ++g) acc[g][k] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    };
+    // exp(a - b) for references a <= b, with exp(-inf - anything) = 0
+    auto ref_scale = [](float a, float b) { return a == -INFINITY ? 0.f : ex2_approx((a - b) * LOG2E); };
+    // move branch k's reference up to v (warp-uniform; k is a compile-time constant at every call site)
+    auto raise_ref = [&](int k, float v) {
+      const float f = ref_scale(m_ref[k], v);
+      l_run[k] *= f;
+      m_ref[k] = v;
+      c_ref[k] = PSH - v * LOG2E;
+      if (cp == (k >> 1)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j][k & 1] *= f;
+          acc[j][2 + (k & 1)] *= f;
+        }
       }
     };
     // end of a bag (all 8 epilogue warps call this together)
@@ -431,11 +468,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             const int app = cs->app[k];
             for (int rec = e_idx; rec < app; rec += 8) {
               if ((cs->active[k][rec >> 5] >> (rec & 31)) & 1u) continue;
-              const float wgt = ex2_approx(rsc[(size_t)k * rcap + rec] * LOG2E);
+              const float sc = rsc[(size_t)k * rcap + rec];
+              if (sc > m_ref[k] + REF_SLACK) raise_ref(k, sc);
+              const float wgt = ex2_approx(fmaf(sc, LOG2E, c_ref[k]));
               if (lane == 0) l_run[k] += wgt;
-              if (rs == 0) {
+              if (cp == (k >> 1)) {
+                const float* hrow = rh + ((size_t)k * rcap + rec) * L + rg;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) acc[g][k] = fmaf(wgt, rh[((size_t)k * rcap + rec) * L + g * 16 + jf], acc[g][k]);
+                for (int j = 0; j < 8; ++j) {
+                  acc[j][k & 1] = fmaf(wgt, hrow[16 * j], acc[j][k & 1]);
+                  acc[j][2 + (k & 1)] = fmaf(wgt, hrow[16 * j + 8], acc[j][2 + (k & 1)]);
+                }
               }
             }
           }
@@ -444,19 +487,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       } else if (cap > 0 && e_idx == 0 && lane < K) {
         reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt)[(size_t)cb * K + lane] = 0;
       }
-      // fold the two row subsets / the lanes of each warp, then tree-merge the 8 warps' partials through shared
-      // memory (the transpose + numerator buffers are idle here): one record per CTA and bag
+      // fold the lanes' l partials, then tree-merge the 8 warps' {m_ref, l, acc} through shared memory (the buffers of
+      // the tile loop are idle here) with the usual log-sum-exp rule: one record per CTA and bag
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        l_run[k] = warp_sum(l_run[k]);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) acc[g][k] += __shfl_xor_sync(0xffffffffu, acc[g][k], 16);
-      }
+      for (int k = 0; k < KB; ++k) l_run[k] = warp_sum(l_run[k]);
       {
         float* xbuf = reinterpret_cast<float*>(smem + sm.tbuf);          // 12 KB: tbuf (8 KB) + ps (4 KB)
-        constexpr int PF = KB * 129;                                     // floats of one warp partial: {l, acc[128]} per branch
+        constexpr int PF = KB * 130;                                     // floats of one warp partial: {m, l, acc[128]} per branch
         constexpr int MAXSLOT = (12288 / 4) / PF >= 4 ? 4 : ((12288 / 4) / PF >= 2 ? 2 : 1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");                   // everybody is done with tbuf / ps
+        asm volatile("bar.sync 1, 256;" ::: "memory");                   // everybody is done with ps
 #pragma unroll 1
         for (int stride = 4; stride >= 1; stride >>= 1) {
 #pragma unroll 1
@@ -466,10 +505,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
               float* slot = xbuf + (e_idx - w_lo) * PF;
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
-                if (lane == 0) slot[k * 129] = l_run[k];
-                if (rs == 0) {
+                if (lane == 0) {
+                  slot[k * 130] = m_ref[k];
+                  slot[k * 130 + 1] = l_run[k];
+                }
+                if (cp == (k >> 1)) {
 #pragma unroll
-                  for (int g = 0; g < 8; ++g) slot[k * 129 + 1 + g * 16 + jf] = acc[g][k];
+                  for (int j = 0; j < 8; ++j) {
+                    slot[k * 130 + 2 + 16 * j + rg] = acc[j][k & 1];
+                    slot[k * 130 + 2 + 16 * j + rg + 8] = acc[j][2 + (k & 1)];
+                  }
                 }
               }
             }
@@ -478,9 +523,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
               const float* slot = xbuf + (e_idx - base) * PF;
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
-                l_run[k] += slot[k * 129];
+                const float mo = slot[k * 130], mn = fmaxf(m_ref[k], mo);
+                const float f_me = ref_scale(m_ref[k], mn), f_o = ref_scale(mo, mn);
+                l_run[k] = l_run[k] * f_me + slot[k * 130 + 1] * f_o;
+                m_ref[k] = mn;
+                if (cp == (k >> 1)) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) acc[g][k] += slot[k * 129 + 1 + g * 16 + jf];
+                  for (int j = 0; j < 8; ++j) {
+                    acc[j][k & 1] = acc[j][k & 1] * f_me + slot[k * 130 + 2 + 16 * j + rg] * f_o;
+                    acc[j][2 + (k & 1)] = acc[j][2 + (k & 1)] * f_me + slot[k * 130 + 2 + 16 * j + rg + 8] * f_o;
+                  }
+                }
               }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -493,12 +546,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         for (int k = 0; k < KB; ++k) {
           if (k < K) {
             if (lane == 0) {
-              part[(size_t)k * (L + 2) + 0] = 0.f;     // softmax reference point of this kernel
+              part[(size_t)k * (L + 2) + 0] = m_ref[k] - PSH * 0.6931471805599453f;   // l, acc are sums of exp(s - this)
               part[(size_t)k * (L + 2) + 1] = l_run[k];
             }
-            if (rs == 0) {
+            if (cp == (k >> 1)) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) part[(size_t)k * (L + 2) + 2 + g * 16 + jf] = acc[g][k];
+              for (int j = 0; j < 8; ++j) {
+                part[(size_t)k * (L + 2) + 2 + 16 * j + rg] = acc[j][k & 1];
+                part[(size_t)k * (L + 2) + 2 + 16 * j + rg + 8] = acc[j][2 + (k & 1)];
+              }
             }
           }
         }
@@ -712,17 +768,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
       }
-      // softmax numerators against the FIXED reference 0: scores are bounded by B_k = sum_u |ww[k][u]| + |bw[k]|
-      // (|tanh * sigmoid| < 1) and acmil_gp_pack only enables this kernel when B_k <= 77, so exp(s) can neither
-      // overflow nor flush to zero and no running max / rescale / cross-lane traffic is needed per tile.
+      // running reference: a taken row more than REF_SLACK above m_ref moves it (first tile of a stream: from -inf)
+      {
+        float tmax[KB];
+        bool grow = false;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          const bool take_a = valid_a && !((ex_a >> k) & 1u), take_b = valid_b && !((ex_b >> k) & 1u);
+          tmax[k] = fmaxf(take_a ? sa[k] : -INFINITY, take_b ? sb[k] : -INFINITY);
+          grow |= tmax[k] > m_ref[k] + REF_SLACK;
+        }
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            float v = tmax[k];
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            if (v > m_ref[k] + REF_SLACK) raise_ref(k, v);
+          }
+        }
+      }
+      // softmax numerators p' = 2^(s log2e + c_ref)  (<= 2^15 by construction; parked / out-of-range rows: 0)
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         const bool take_a = valid_a && !((ex_a >> k) & 1u), take_b = valid_b && !((ex_b >> k) & 1u);
-        pa[k] = take_a ? ex2_approx(sa[k] * LOG2E) : 0.f;
-        pb[k] = take_b ? ex2_approx(sb[k] * LOG2E) : 0.f;
+        pa[k] = take_a ? ex2_approx(fmaf(sa[k], LOG2E, c_ref[k])) : 0.f;
+        pb[k] = take_b ? ex2_approx(fmaf(sb[k], LOG2E, c_ref[k])) : 0.f;
         if (cp == 0) l_run[k] += pa[k] + pb[k];       // each row once; lanes are summed at flush
       }
-      if (cp < 2) {   // p of row a (cp 0) / row b (cp 1) -> smem for the pool
+      if (cp < 2) {   // p' of row a (cp 0) / row b (cp 1) -> smem, from where the pool builds its B fragments
         float4 p0, p1;
         p0.x = cp ? pb[0] : pa[0];
         p0.y = KB > 1 ? (cp ? pb[KB > 1 ? 1 : 0] : pa[KB > 1 ? 1 : 0]) : 0.f;
@@ -740,7 +815,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       prof[4] += clock64() - t_e3;
       const long long t_e4 = clock64();
 #endif
-      // ---------------- pool: acc[k][:] += sum_rows p[row][k] h[row][:]  (h = hi + lo of the TMEM operand) ----------------
+      // ---------------- pool: acc[feature][branch] += sum_rows h[row][feature] p'[row][branch] ----------------
+      // A contraction over the warp's 16 rows = the K dimension of mma.sync m16n8k16 with A = h^T (16 features x 16 rows)
+      // and B = p' (16 rows x 8 branches).  tcgen05.ld 16x128b hands out the packed fp16 h operand in exactly the
+      // fragment layout movmatrix expects (thread (rg, cp): rows rg / rg + 8, feature pair 8i + 2cp), so a transpose is
+      // one MOVM per 8x8 block and there is no shared-memory round trip.  fp32-faithful through the same hi/lo split as
+      // the big GEMMs: h_hi p_hi + h_lo p_hi + h_hi p_lo.
       float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
       float* t0 = nullptr;
       float* t1 = nullptr;
@@ -759,76 +839,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
       }
-      // 16-feature chunks, TMEM loads of chunk g + 1 in flight while chunk g is transposed and accumulated
-      auto pool_chunk = [&](const uint32_t (&hh)[4], const uint32_t (&hl)[4], auto gc) {
-        constexpr int g = decltype(gc)::value;
-        // this thread holds features 8 ii + 2 cp + {0,1} of the chunk for rows rg (a) and rg + 8 (b)
+      __syncwarp();
+      uint32_t bh[2], bl[2];      // B fragments: {p'[2cp][rg], p'[2cp+1][rg]}, {p'[2cp+8][rg], p'[2cp+9][rg]} as fp16 hi / lo
+      {
+        const float q0 = psw[(2 * cp) * 8 + rg], q1 = psw[(2 * cp + 1) * 8 + rg];
+        const float q2 = psw[(2 * cp + 8) * 8 + rg], q3 = psw[(2 * cp + 9) * 8 + rg];
+        split2(q0, q1, bh[0], bl[0]);
+        split2(q2, q3, bh[1], bl[1]);
+      }
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const float2 ah = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * ii]));
-          const float2 al = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * ii]));
-          const float2 bh = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * ii + 1]));
-          const float2 bl = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * ii + 1]));
-          const float2 fa = make_float2(ah.x + al.x, ah.y + al.y), fb = make_float2(bh.x + bl.x, bh.y + bl.y);
-          const int fcol = ii * 8 + cp * 2;
-          const int fsw = fcol ^ (((rg >> 1) & 1) << 3);     // rows of equal parity land in different bank groups
-          *reinterpret_cast<float2*>(tbuf + rg * 16 + fsw) = fa;
-          *reinterpret_cast<float2*>(tbuf + (rg + 8) * 16 + fsw) = fb;
-          // park rows that entered a list this tile: two precomputed targets cover practically every case
-          if (t0 != nullptr) *reinterpret_cast<float2*>(t0 + g * 16 + fcol) = t0b ? fb : fa;
-          if (t1 != nullptr) *reinterpret_cast<float2*>(t1 + g * 16 + fcol) = t1b ? fb : fa;
-          if (rest_a | rest_b) {   // a row group parked in more than two (row, branch) pairs: generic path
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hh[16], hl[16];     // regs {2i, 2i+1}: rows rg / rg + 8, features 64 hf + 8i + 2cp + {0,1}
+        tmem_ld_16x128b_x8(tm + lane_addr + TM_HHI + hf * 32, hh);
+        tmem_ld_16x128b_x8(tm + lane_addr + TM_HLO + hf * 32, hl);
+        tmem_wait_ld();
+        if (ex_a | ex_b) {   // park the rows that entered a list this tile (fp32 h = hi + lo)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 ah = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * i]));
+            const float2 al = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * i]));
+            const float2 bhf = __half22float2(*reinterpret_cast<const __half2*>(&hh[2 * i + 1]));
+            const float2 blf = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * i + 1]));
+            const float2 fa = make_float2(ah.x + al.x, ah.y + al.y), fb = make_float2(bhf.x + blf.x, bhf.y + blf.y);
+            const int fcol = hf * 64 + i * 8 + cp * 2;
+            if (t0 != nullptr) *reinterpret_cast<float2*>(t0 + fcol) = t0b ? fb : fa;
+            if (t1 != nullptr) *reinterpret_cast<float2*>(t1 + fcol) = t1b ? fb : fa;
+            if (rest_a | rest_b) {   // a row group parked in more than two (row, branch) pairs: generic path
 #pragma unroll 1
-            for (int k = 0; k < K; ++k) {
-              if ((rest_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_a, k)) * L + g * 16 + fcol) = fa;
-              if ((rest_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_b, k)) * L + g * 16 + fcol) = fb;
+              for (int k = 0; k < K; ++k) {
+                if ((rest_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_a, k)) * L + fcol) = fa;
+                if ((rest_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_b, k)) * L + fcol) = fb;
+              }
             }
           }
         }
-        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // row rs * 8 + (i ^ rs): the two row subsets read rows of opposite parity; all address math is in the
-          // four lane-constant bases (even/odd i x swizzle phase) plus an immediate
-          const float* tb = (i & 1) ? (((i >> 1) & 1) ? tO1 : tO0) : (((i >> 1) & 1) ? tE1 : tE0);
-          const float* pp = (i & 1) ? pO : pE;
-          const float hv = tb[i * 16];
-          const float4 p0 = *reinterpret_cast<const float4*>(pp + i * 8);
-          acc[g][0] = fmaf(p0.x, hv, acc[g][0]);
-          if (KB > 1) acc[g][KB > 1 ? 1 : 0] = fmaf(p0.y, hv, acc[g][KB > 1 ? 1 : 0]);
-          if (KB > 2) acc[g][KB > 2 ? 2 : 0] = fmaf(p0.z, hv, acc[g][KB > 2 ? 2 : 0]);
-          if (KB > 3) acc[g][KB > 3 ? 3 : 0] = fmaf(p0.w, hv, acc[g][KB > 3 ? 3 : 0]);
-          if (KB > 4) {
-            const float4 p1 = *reinterpret_cast<const float4*>(pp + i * 8 + 4);
-            acc[g][KB > 4 ? 4 : 0] = fmaf(p1.x, hv, acc[g][KB > 4 ? 4 : 0]);
-            if (KB > 5) acc[g][KB > 5 ? 5 : 0] = fmaf(p1.y, hv, acc[g][KB > 5 ? 5 : 0]);
-            if (KB > 6) acc[g][KB > 6 ? 6 : 0] = fmaf(p1.z, hv, acc[g][KB > 6 ? 6 : 0]);
-            if (KB > 7) acc[g][KB > 7 ? 7 : 0] = fmaf(p1.w, hv, acc[g][KB > 7 ? 7 : 0]);
-          }
+        for (int jj = 0; jj < 4; ++jj) {
+          // blocks 2jj, 2jj + 1 of this half -> A fragment {blk0 rows 0-7, blk1 rows 0-7, blk0 rows 8-15, blk1 rows 8-15}
+          uint32_t ahi[4], alo[4];
+          ahi[0] = movmatrix_t(hh[4 * jj]);
+          ahi[1] = movmatrix_t(hh[4 * jj + 2]);
+          ahi[2] = movmatrix_t(hh[4 * jj + 1]);
+          ahi[3] = movmatrix_t(hh[4 * jj + 3]);
+          alo[0] = movmatrix_t(hl[4 * jj]);
+          alo[1] = movmatrix_t(hl[4 * jj + 2]);
+          alo[2] = movmatrix_t(hl[4 * jj + 1]);
+          alo[3] = movmatrix_t(hl[4 * jj + 3]);
+          mma_16816_f16(acc[hf * 4 + jj], ahi, bh);
+          mma_16816_f16(acc[hf * 4 + jj], alo, bh);
+          mma_16816_f16(acc[hf * 4 + jj], ahi, bl);
         }
-        __syncwarp();
-      };
-      {
-        uint32_t hhA[4], hlA[4], hhB[4], hlB[4];
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI, hhA);
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO, hlA);
-#define POOL_PAIR(G)                                                            \
-        tmem_wait_ld();                                                         \
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + ((G) + 1) * 8, hhB);       \
-        tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + ((G) + 1) * 8, hlB);       \
-        pool_chunk(hhA, hlA, std::integral_constant<int, (G)>{});               \
-        tmem_wait_ld();                                                         \
-        if ((G) + 2 < 8) {                                                      \
-          tmem_ld_16x128b_x2(tm + lane_addr + TM_HHI + ((G) + 2) * 8, hhA);     \
-          tmem_ld_16x128b_x2(tm + lane_addr + TM_HLO + ((G) + 2) * 8, hlA);     \
-        }                                                                       \
-        pool_chunk(hhB, hlB, std::integral_constant<int, (G) + 1>{});
-        POOL_PAIR(0)
-        POOL_PAIR(2)
-        POOL_PAIR(4)
-        POOL_PAIR(6)
-#undef POOL_PAIR
       }
+      __syncwarp();      // psw is rewritten by the next tile
 #if GP_UMMA_PROF
       prof[5] += clock64() - t_e4;
 #endif

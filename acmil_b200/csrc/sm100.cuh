@@ -75,6 +75,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // barriers guard lives in L1 (TMEM operands / accumulators, ordered by tcgen05.fence).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
+// One lane of a converged warp.  Issue tcgen05.mma / commit / TMA under `if (elect_one())` from warp-uniform code:
+// ptxas then knows a single thread is active and emits the uniform-datapath instruction directly, whereas under
+// `if (lane == 0)` it wraps every such instruction in an ELECT / BRA.U.ANY loop (~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -326,6 +335,20 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// ---- warp-level tensor-core path (legacy mma.sync; used for small transposing contractions) ----
+// 8x8 b16 transpose across the warp: thread (g = lane/4, c = lane%4) gives {M[g][2c], M[g][2c+1]}, gets {M[2c][g], M[2c+1][g]}
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// D[16x8] += A[16x16] B[16x8], fp16 operands, fp32 accumulate (fragment layouts of the PTX ISA)
+__device__ __forceinline__ void mma_16816_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
