@@ -68,19 +68,46 @@ struct UmmaParams {
   uint32_t w1_part_bytes;      // bytes of one (hi or lo) W1 half image
 };
 
-// Top-n tracking per CTA and bag (training-mode masking).  Epilogue warp k is the "manager" of branch k: per tile
-// every warp publishes its rows' scores in shared memory, the managers compare all 128 rows of the tile with the
-// CTA's current n-th best (list kept in the manager's registers: lane i = entry i) and flag the rows that enter.
-// A flagged row is "parked": kept out of the sums, its score / index / h row appended to scratch.  At the end of
-// the bag the parked rows that did not stay in the CTA's top n are added back by the CTA; the n survivors go to
-// the reduce kernel.  Nothing is ever subtracted, no locks, and the record order is deterministic.
-constexpr int REC_CAP = 128;   // parked rows per (CTA, bag, branch); expected ~ n (1 + ln(tiles)) + 25
+// Top-n tracking per CTA and bag (training-mode masking).  Rows that may belong to the bag's top n of a branch must stay
+// out of the softmax sums (the reference masks them before the softmax), so they are "parked": score / row index /
+// h row go to scratch records and rejoin the sums later unless they end up masked.  Nothing is ever subtracted.
+//  * Epilogue warps only APPEND: a row whose score beats tau = max(CTA's n-th best, bag-wide n-th best) takes the
+//    next record slot of its branch with one shared-memory atomicAdd and is parked.  No locks, no waiting; in the
+//    common case no row beats tau and the check costs a few instructions per branch.
+//  * Warp 2 is the list manager: it follows the appended records and keeps the CTA's top-n list of every branch
+//    (entry i <-> lane i), publishes the CTA's n-th best (tau) and mirrors the list to the workspace (cand_score).
+//  * Warp 3 keeps merging the mirrored lists of ALL CTAs that work on the current bag into gtau[k] = the bag-wide
+//    n-th best score seen so far by anybody (a lower bound of the final one).
+//  * The CTA's first tile of a bag has no threshold yet: there warp k selects the tile's top n of branch k directly
+//    (two CTA barriers, once per bag and CTA).
+//  * End of the bag: the manager catches up, records that are not in the final list are added back by the CTA, the
+//    n survivors go to the reduce kernel.
+// Which rows get parked depends on timing, so the summation order of the result does; the top-n set and the mask do not.
+constexpr int REC_CAP = 128;   // parked rows per (CTA, bag, branch)
+constexpr int CAND_KMAX = 6;   // masking on this kernel: K <= 6
+constexpr unsigned REC_EMPTY = 0xFFFFFFFFu;     // record score not written yet (a NaN pattern no score can have)
 struct CandShared {
-  unsigned char flag[128][8];        // per tile row and branch: 0 = takes part in the sums, r + 1 = parked in record r
-  unsigned active[KMAX][REC_CAP / 32];   // bag end: records that are still in the manager's list
-  int cnt[KMAX];                     // bag end: live list entries
-  int app[KMAX];                     // bag end: records appended
+  float ls[CAND_KMAX][32];               // list scores, +inf beyond cnt
+  int lrec[CAND_KMAX][32];               // ... and their record indices
+  unsigned active[CAND_KMAX][REC_CAP / 32];   // bag end: records that are still in the list
+  int cnt[8];                            // live list entries
+  int app[8];                            // records appended (may run past rec_cap: overflow)
+  int seen[8];                           // records the manager has looked at
+  float tau[8];                          // n-th best once the list is full, else -inf
+  unsigned long long gtau[8];            // bag << 32 | bits of the bag-wide n-th best so far (warp 3, one 8-byte store)
+  int cur_bag;                           // bag the epilogue is working on (-1: none yet, -2: kernel is finishing)
+  int epoch;                             // bumped when a bag's lists have been booted: the manager may work on them
+  int flush_req, flush_ack;              // epoch whose lists the epilogue wants final / the manager has finalised
 };
+
+// order-preserving float <-> uint (0 is below every float, +inf is below every NaN)
+__device__ __forceinline__ unsigned ord_enc(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_dec(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
 
 // gate constants in smem, one record of 2 CREC floats per pair of adjacent units (2c, 2c+1), laid out as fp32 pairs
 // for the packed FFMA2 path: {ww[k][2c], ww[k][2c+1]} for k < KB, then the bv' pair and the bu' pair, where
@@ -98,7 +125,7 @@ __host__ __device__ inline SmemMap smem_map(int din, int kb) {
   m.wg = (uint32_t)(din / 64) * 8192u * 2u;
   m.stage = m.wg + 65536u;
   m.tbuf = m.stage + NSTAGE * STAGE_BYTES;
-  m.ps = m.tbuf + 8 * 1024;
+  m.ps = m.tbuf + 7 * 1024;        // tbuf + ps = 11 KB scratch of the bag-end merge
   m.cst = m.ps + 8 * 512;
   m.cand = m.cst + 128 * (uint32_t)cst_rec(kb) * 4;
   m.bars = m.cand + (kb > 6 ? 128u : (uint32_t)sizeof(CandShared));   // K > 6: no masking on this kernel
@@ -186,6 +213,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       rec[2 * KB] = p.c.bv[u] * (-2.f * LOG2E);
       rec[2 * KB + 2] = p.c.bu[u] * (-LOG2E);
     }
+  }
+  if (KB <= 6) {
+    CandShared* cs0 = reinterpret_cast<CandShared*>(smem + sm.cand);
+    if (tid < CAND_KMAX * 32) cs0->ls[tid >> 5][tid & 31] = INFINITY;
+    if (tid < 8) { cs0->cnt[tid] = 0; cs0->app[tid] = 0; cs0->seen[tid] = 0; cs0->tau[tid] = -INFINITY; cs0->gtau[tid] = ~0ull; }
+    if (tid == 0) { cs0->cur_bag = -1; cs0->epoch = 0; cs0->flush_req = 0; cs0->flush_ack = 0; }
   }
   if (warp == 2) {
     tmem_alloc<2>(&bars->tmem_base, 512);
@@ -315,6 +348,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #endif
     }
     __syncwarp();
+  } else if (warp == 2) {
+    if (KB <= CAND_KMAX && seg.n_masked_cap > 0 && T > 0) {
+      // ===================================== top-n list manager =====================================
+      CandShared* cs = reinterpret_cast<CandShared*>(smem + sm.cand);
+      const unsigned* recs = reinterpret_cast<const unsigned*>(smem + sm.tbuf + 1024);      // [K][rec_cap] score bits
+      float* g_score_all = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score);
+      const int cap = seg.n_masked_cap, rcap = seg.rec_cap;
+      int dead_epoch = 0;       // lists of this epoch are final (or not booted yet): hands off
+      while (true) {
+        const int s = *reinterpret_cast<volatile int*>(&cs->cur_bag);
+        if (s == -2) break;
+        const int ep = *reinterpret_cast<volatile int*>(&cs->epoch);
+        const int fr = *reinterpret_cast<volatile int*>(&cs->flush_req);      // read BEFORE the scan: if it already
+        if (ep != dead_epoch && s >= 0) {                                      // asks for ep, the scan below sees all
+          const int nmk = seg.nm[s];
+          const int holder = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 2 + (int)cta;
+          for (int k = 0; k < K; ++k) {
+            int seen = cs->seen[k];
+            const int app = min(*reinterpret_cast<volatile int*>(&cs->app[k]), rcap);
+            if (seen >= app) continue;
+            float mg_s = cs->ls[k][lane];
+            int mg_rec = cs->lrec[k][lane], mg_cnt = cs->cnt[k];
+            float mg_tau = -INFINITY;
+            int mg_tau_lane = 0;
+            auto find_min = [&]() {
+              const unsigned key = __reduce_min_sync(0xffffffffu, ord_enc(mg_s));
+              mg_tau = ord_dec(key);
+              mg_tau_lane = __ffs(__ballot_sync(0xffffffffu, ord_enc(mg_s) == key)) - 1;
+            };
+            if (mg_cnt == nmk) find_min();
+            bool changed = false;
+            for (; seen < app; ++seen) {
+              const unsigned bits = *reinterpret_cast<const volatile unsigned*>(&recs[k * rcap + seen]);
+              if (bits == REC_EMPTY) break;       // slot taken, score not stored yet: next round
+              const float s_new = __uint_as_float(bits);
+              if (mg_cnt == nmk && !(s_new > mg_tau)) continue;
+              const int dst = mg_cnt < nmk ? mg_cnt++ : mg_tau_lane;
+              if (lane == dst) { mg_s = s_new; mg_rec = seen; }
+              if (mg_cnt == nmk) find_min();
+              changed = true;
+            }
+            if (changed) {
+              cs->ls[k][lane] = mg_s;
+              cs->lrec[k][lane] = mg_rec;
+              if (lane < cap) g_score_all[((size_t)holder * K + k) * cap + lane] = lane < mg_cnt ? mg_s : -INFINITY;
+              if (lane == 0) {
+                cs->cnt[k] = mg_cnt;
+                if (mg_cnt == nmk) *reinterpret_cast<volatile float*>(&cs->tau[k]) = mg_tau;
+              }
+            }
+            if (lane == 0) cs->seen[k] = seen;
+            __syncwarp();
+          }
+          if (fr == ep) {       // every append of this bag happened before the request: the lists are final
+            __threadfence_block();
+            if (lane == 0) *reinterpret_cast<volatile int*>(&cs->flush_ack) = ep;
+            dead_epoch = ep;
+          }
+        }
+        __nanosleep(100);
+      }
+    }
   } else if (warp == 3) {
     // this CTA's resident weights are in place -> tell the leader's MMA thread
     if (lane == 0) {
@@ -322,6 +417,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       mbar_arrive_cluster(&bars->w_ready, 0);
     }
     __syncwarp();
+    if (KB <= CAND_KMAX && seg.n_masked_cap > 0 && T > 0) {
+      // ===================================== bag-wide threshold service =====================================
+      // merge the mirrored top-n lists of every CTA working on the current bag: the n-th best of their union is the
+      // n-th best of all rows anybody has scored so far (any such row is in its own CTA's list), a lower bound of
+      // the final one.  Entries not written in this launch are NaN (memset by the host) and ignored.
+      CandShared* cs = reinterpret_cast<CandShared*>(smem + sm.cand);
+      const float* g_score = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.cand_score);
+      const int cap = seg.n_masked_cap;
+      while (true) {
+        const int s = *reinterpret_cast<volatile int*>(&cs->cur_bag);
+        if (s == -2) break;
+        const int nmk = s >= 0 ? seg.nm[s] : 0;
+        if (nmk > 0) {
+          const int seg0 = seg.seg_begin[s], E = (seg.seg_begin[s + 1] - seg0) * cap;
+          for (int k = 0; k < K; ++k) {
+            float ls = INFINITY, tau = -INFINITY;     // lane i = entry i of the merged top-n
+            int cnt = 0, tau_lane = 0;
+            for (int e0 = 0; e0 < E; e0 += 256) {
+              float v[8];       // 8 independent L2 reads in flight per lane
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int e = e0 + 32 * u + lane;
+                v[u] = -INFINITY;
+                if (e < E) {
+                  const int j = e / cap, i = e - j * cap;
+                  v[u] = __ldcg(g_score + ((size_t)(seg0 + j) * K + k) * cap + i);
+                  if (!(v[u] == v[u])) v[u] = -INFINITY;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                unsigned bal = __ballot_sync(0xffffffffu, v[u] > tau);
+                while (bal) {
+                  const int src = __ffs(bal) - 1;
+                  bal &= bal - 1;
+                  const float s_new = __shfl_sync(0xffffffffu, v[u], src);
+                  if (cnt == nmk && !(s_new > tau)) continue;
+                  const int dst = cnt < nmk ? cnt++ : tau_lane;
+                  if (lane == dst) ls = s_new;
+                  if (cnt == nmk) {
+                    const unsigned key = __reduce_min_sync(0xffffffffu, ord_enc(ls));
+                    tau = ord_dec(key);
+                    tau_lane = __ffs(__ballot_sync(0xffffffffu, ord_enc(ls) == key)) - 1;
+                  }
+                }
+              }
+              if (*reinterpret_cast<volatile int*>(&cs->cur_bag) != s) break;     // bag changed / kernel finishing
+            }
+            if (*reinterpret_cast<volatile int*>(&cs->cur_bag) != s) break;
+            if (cnt == nmk && lane == 0)
+              *reinterpret_cast<volatile unsigned long long*>(&cs->gtau[k]) = ((unsigned long long)(unsigned)s << 32) | __float_as_uint(tau);
+          }
+        }
+        __nanosleep(500);
+      }
+    }
   }
   } else if (warp < 8) {
     // ===================================== converters: fp32 staging -> fp16 hi/lo in TMEM =====================================
@@ -391,11 +542,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     float l_run[KB], m_ref[KB], c_ref[KB], acc[8][4];     // l_run: per-lane partial of sum p'; c_ref = PSH - m_ref log2e
     CandShared* cs = reinterpret_cast<CandShared*>(smem + sm.cand);
     const int rcap = seg.rec_cap;
-    float* sc_all = reinterpret_cast<float*>(smem + sm.ps);     // [8 warps][16 rows][8]: scores, later softmax numerators
-    // manager state of branch e_idx (meaningful for e_idx < K): unsorted top-n list, lane i = entry i
-    float mg_s = INFINITY, mg_tau = -INFINITY;
-    int mg_rec = 0, mg_cnt = 0, mg_app = 0, mg_tau_lane = 0;
     int s_cur = -1, s_hint = 0, nm = 0, seg_id = 0, cb = 0;
+    bool boot = false;     // the next tile is this CTA's first tile of the bag: the lists are empty
+    int epoch_cur = 0;     // bags booted so far (same value in all epilogue warps)
     int64_t n_rows = 0;
 
     auto reset_stream = [&](int s) {
@@ -404,9 +553,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       n_rows = seg.row_off[s + 1] - seg.row_off[s];
       seg_id = seg.seg_begin[s] + (cluster - seg.u_cfirst[s]) * 2 + (int)cta;   // one segment per CTA and bag
       cb = seg_id;                     // ... which is also its candidate holder
-      mg_s = INFINITY;
-      mg_tau = -INFINITY;
-      mg_rec = mg_cnt = mg_app = mg_tau_lane = 0;
+      boot = true;
+      if (KB <= CAND_KMAX && e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->cur_bag) = s;
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
         l_run[k] = 0.f;
@@ -439,14 +587,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         const float* rsc = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
         const int* rix = reinterpret_cast<const int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
         const float* rh = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
-        if (e_idx < K) {     // managers publish which records are still in their list and hand it to the reduce kernel
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // every warp is past the bag's last tile: no more appends
+        if (e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->flush_req) = epoch_cur;
+        while (*reinterpret_cast<volatile int*>(&cs->flush_ack) != epoch_cur) __nanosleep(50);     // manager caught up
+        if (e_idx < K) {     // warp k publishes which records are still in list k and hands the list to the reduce kernel
           const int k = e_idx;
+          const float mg_s = cs->ls[k][lane];
+          const int mg_rec = cs->lrec[k][lane], mg_cnt = cs->cnt[k], mg_app = min(cs->app[k], rcap);
 #pragma unroll
           for (int w = 0; w < REC_CAP / 32; ++w) {
             const unsigned m = __reduce_or_sync(0xffffffffu, (lane < mg_cnt && (mg_rec >> 5) == w) ? (1u << (mg_rec & 31)) : 0u);
             if (lane == 0) cs->active[k][w] = m;
           }
-          if (lane == 0) { cs->cnt[k] = mg_cnt; cs->app[k] = mg_app; }
+          (void)mg_app;
           int* g_cnt = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt) + (size_t)cb * K;
           float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)cb * K * cap;
           int* g_idx = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_idx) + (size_t)cb * K * cap;
@@ -460,12 +613,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
         __threadfence_block();
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // every warp is past the bag's last tile, lists are published
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // active[] is published
         // parked rows that did not stay in the CTA's top n rejoin the sums (every 8th record per warp)
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
           if (k < K) {
-            const int app = cs->app[k];
+            const int app = min(cs->app[k], rcap);
             for (int rec = e_idx; rec < app; rec += 8) {
               if ((cs->active[k][rec >> 5] >> (rec & 31)) & 1u) continue;
               const float sc = rsc[(size_t)k * rcap + rec];
@@ -483,7 +636,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // the shared words may be reused by the next bag
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // everybody has read app / active: reset the lists for the next bag
+        if (e_idx < K) {
+          cs->ls[e_idx][lane] = INFINITY;
+          if (lane == 0) { cs->cnt[e_idx] = 0; cs->app[e_idx] = 0; cs->seen[e_idx] = 0; cs->tau[e_idx] = -INFINITY; }
+        }
       } else if (cap > 0 && e_idx == 0 && lane < K) {
         reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt)[(size_t)cb * K + lane] = 0;
       }
@@ -569,7 +726,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     for (int t = 0; t < T; ++t) {
       const TilePos tp = tile_pos(g0 + t, s_hint);
       if (tp.s != s_cur) {
-        flush_stream();
+        { PROF_T0(); flush_stream(); PROF_ADD(6); }
         reset_stream(tp.s);
       }
       const int64_t row_a = tp.row_in_bag + lane_base + rg, row_b = row_a + 8;
@@ -699,8 +856,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       int slot_a[KB], slot_b[KB];
 #pragma unroll
       for (int k = 0; k < KB; ++k) slot_a[k] = slot_b[k] = 0;
-      if (nm > 0) {
-        // 1. publish this warp's scores ([16 rows][8]) and clear its rows' flags
+      if (KB <= CAND_KMAX && nm > 0 && boot) {
+        // First tile of the bag in this CTA: every row would be a candidate, so instead of 8 warps queueing at the
+        // locks, warp k picks the tile's top n of branch k in one go (descending order: exactly n insertions).
+        float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
+        int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+        float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)cb * K * cap;
+        float* sc_all = reinterpret_cast<float*>(smem + sm.ps);                 // [8 warps][16 rows][8]
+        unsigned char* bflag = smem + sm.tbuf;                                   // [128 rows][8]: 0 or record + 1
         if (cp < 2) {
           float4 s0, s1;
           s0.x = cp ? sb[0] : sa[0];
@@ -713,52 +876,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           const int prow = rg + 8 * cp;
           *reinterpret_cast<float4*>(psw + prow * 8) = s0;
           *reinterpret_cast<float4*>(psw + prow * 8 + 4) = s1;
-          *reinterpret_cast<uint2*>(&cs->flag[lane_base + prow][0]) = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(bflag + (lane_base + prow) * 8) = make_uint2(0u, 0u);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        // 2. manager of branch k = e_idx looks at all 128 rows of the tile, in row order
         if (e_idx < K) {
           const int k = e_idx;
-          float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
-          int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
-          auto find_min = [&]() {
-            mg_tau = mg_s;       // lanes >= cnt hold +inf
+          float sv[4];
+          unsigned todo = 0u;      // bit i: tile row lane + 32 i is still in the running
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mg_tau = fminf(mg_tau, __shfl_xor_sync(0xffffffffu, mg_tau, o));
-            mg_tau_lane = __ffs(__ballot_sync(0xffffffffu, mg_s == mg_tau)) - 1;
-          };
-#pragma unroll 1
-          for (int i = 0; i < 4; ++i) {      // tile rows 32 i + lane: owned by epilogue warps i (lanes 0-15) and i + 4
-            const int trow = 32 * i + lane;
-            const float sv = sc_all[(i + 4 * (lane >> 4)) * 128 + (lane & 15) * 8 + k];
-            const bool ok = tp.row_in_bag + trow < n_rows;
-            unsigned bal = __ballot_sync(0xffffffffu, ok && (mg_cnt < nm || sv > mg_tau));
-            while (bal) {
-              const int src = __ffs(bal) - 1;
-              bal &= bal - 1;
-              const float s_new = __shfl_sync(0xffffffffu, sv, src);
-              if (mg_cnt == nm && !(s_new > mg_tau)) continue;
-              if (mg_app >= rcap) {       // out of parking slots: poison the result (the reduce kernel writes NaN)
-                if (lane == 0) atomicExch(reinterpret_cast<int*>(p.mp.ws + p.mp.wl.flags), 1);
-                continue;
-              }
-              const int rec = mg_app++;
-              const int dst = mg_cnt < nm ? mg_cnt++ : mg_tau_lane;
-              if (lane == dst) { mg_s = s_new; mg_rec = rec; }
-              if (lane == 0) {
-                rsc[(size_t)k * rcap + rec] = s_new;
-                rix[(size_t)k * rcap + rec] = (int)tp.row_in_bag + 32 * i + src;
-                cs->flag[32 * i + src][k] = (unsigned char)(rec + 1);
-              }
-              if (mg_cnt == nm) find_min();
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            sv[i] = sc_all[(((r >> 4) & 1) * 4 + (r >> 5)) * 128 + (r & 15) * 8 + k];
+            if (tp.row_in_bag + r < n_rows) todo |= 1u << i;
+          }
+          float mg_s = INFINITY;
+          int mg_rec = 0, mg_cnt = 0;
+          for (int it = 0; it < nm; ++it) {
+            unsigned key = 0u;
+            int which = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const unsigned ki = ((todo >> i) & 1u) ? ord_enc(sv[i]) : 0u;
+              if (ki > key) { key = ki; which = i; }
             }
+            const unsigned best = __reduce_max_sync(0xffffffffu, key);
+            if (best == 0u) break;
+            const int src = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+            const int r = src + 32 * __shfl_sync(0xffffffffu, which, src);
+            if (lane == src) todo &= ~(1u << which);
+            if (lane == it) { mg_s = ord_dec(best); mg_rec = it; }
+            if (lane == 0) {
+              rsc[(size_t)k * rcap + it] = ord_dec(best);
+              rix[(size_t)k * rcap + it] = (int)tp.row_in_bag + r;
+              bflag[r * 8 + k] = (unsigned char)(it + 1);
+            }
+            ++mg_cnt;
+          }
+          cs->ls[k][lane] = mg_s;
+          cs->lrec[k][lane] = mg_rec;
+          if (lane < cap) g_score[k * cap + lane] = lane < mg_cnt ? mg_s : -INFINITY;
+          const float tau0 = ord_dec(__reduce_min_sync(0xffffffffu, ord_enc(mg_s)));
+          unsigned* recs = reinterpret_cast<unsigned*>(smem + sm.tbuf + 1024) + k * rcap;
+          for (int i = lane; i < rcap; i += 32) recs[i] = REC_EMPTY;       // (the manager starts behind the booted ones)
+          if (lane == 0) {
+            cs->cnt[k] = mg_cnt;
+            cs->app[k] = mg_cnt;
+            cs->seen[k] = mg_cnt;
+            cs->tau[k] = mg_cnt == nm ? tau0 : -INFINITY;
           }
         }
+        ++epoch_cur;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        // 3. every thread learns which of its two rows are parked, and where
+        if (e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->epoch) = epoch_cur;     // lists are live
         {
-          const uint2 fa = *reinterpret_cast<const uint2*>(&cs->flag[lane_base + rg][0]);
-          const uint2 fb = *reinterpret_cast<const uint2*>(&cs->flag[lane_base + rg + 8][0]);
+          const uint2 fa = *reinterpret_cast<const uint2*>(bflag + (lane_base + rg) * 8);
+          const uint2 fb = *reinterpret_cast<const uint2*>(bflag + (lane_base + rg + 8) * 8);
 #pragma unroll
           for (int k = 0; k < KB; ++k) {
             const unsigned va = ((k < 4 ? fa.x : fa.y) >> (8 * (k & 3))) & 0xffu;
@@ -767,7 +939,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             if (vb) { ex_b |= 1u << k; slot_b[k] = (int)vb - 1; }
           }
         }
+      } else if (nm > 0) {
+        float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
+        int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+        unsigned* recs = reinterpret_cast<unsigned*>(smem + sm.tbuf + 1024);
+        // lane (rg, cp = 0) speaks for row a, lane (rg, cp = 1) for row b of the row group
+        const bool mine = (cp == 0 && valid_a) || (cp == 1 && valid_b);
+#pragma unroll
+        for (int k = 0; k < (KB <= CAND_KMAX ? KB : 0); ++k) {
+          if (k < K) {
+            const unsigned long long gq = *reinterpret_cast<volatile unsigned long long*>(&cs->gtau[k]);
+            const float tau = fmaxf(*reinterpret_cast<volatile float*>(&cs->tau[k]),
+                                    (unsigned)(gq >> 32) == (unsigned)s_cur ? __uint_as_float((unsigned)gq) : -INFINITY);
+            const float sv = cp == 0 ? sa[k] : sb[k];
+            const bool hit = mine && sv > tau;
+            if (__any_sync(0xffffffffu, hit)) {
+              int rec = -1;
+              if (hit) {
+                rec = atomicAdd(&cs->app[k], 1);
+                if (rec < rcap) {
+                  rsc[(size_t)k * rcap + rec] = sv;
+                  rix[(size_t)k * rcap + rec] = (int)(cp == 0 ? row_a : row_b);
+                  *reinterpret_cast<volatile unsigned*>(&recs[k * rcap + rec]) = __float_as_uint(sv);
+                } else {        // out of parking slots: poison the result (the reduce kernel writes NaN)
+                  atomicExch(reinterpret_cast<int*>(p.mp.ws + p.mp.wl.flags), 1);
+                  rec = -1;
+                }
+              }
+              const int ra = __shfl_sync(0xffffffffu, rec, lane & ~3), rb = __shfl_sync(0xffffffffu, rec, (lane & ~3) | 1);
+              if (ra >= 0) { ex_a |= 1u << k; slot_a[k] = ra; }
+              if (rb >= 0) { ex_b |= 1u << k; slot_b[k] = rb; }
+            }
+          }
+        }
       }
+      boot = false;
       // running reference: a taken row more than REF_SLACK above m_ref moves it (first tile of a stream: from -inf)
       {
         float tmax[KB];
@@ -895,7 +1101,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       prof[5] += clock64() - t_e4;
 #endif
     }
-    flush_stream();
+    { PROF_T0(); flush_stream(); PROF_ADD(6); }
+    if (KB <= CAND_KMAX && e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->cur_bag) = -2;     // stops the service warp
 #if GP_UMMA_PROF
     prof[7] = clock64() - t_start;
     if (warp == 8 && lane == 0) PROF_FLUSH(24);
@@ -1145,6 +1352,8 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
   const size_t smem = smem_map(s.d_in, K == 1 ? 1 : (K <= 5 ? 5 : 8)).total + 1024;
   const int grid = p.seg.u_nclusters * 2;
   ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, 16, st));
+  if (p.seg.n_masked_cap > 0)     // mirrored top-n lists: NaN = "not written in this launch" for the threshold service
+    ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.cand_score, 0xFF, p.wl.cand_idx - p.wl.cand_score, st));
   if (K == 1) return launch_kb<1>(up, grid, smem, st);
   if (K <= 5) return launch_kb<5>(up, grid, smem, st);
   return launch_kb<8>(up, grid, smem, st);

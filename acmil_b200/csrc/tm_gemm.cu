@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop on identical values; the tcgen05 instructions sit under elect_one() so that
+        // ptxas emits them directly instead of inside an ELECT / BRA.U.ANY loop per MMA
       constexpr uint32_t idesc = tf32_idesc(BM, BN);
       uint32_t ctr = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES;
           const uint32_t a_lo = b_hi + B_BYTES, b_lo = a_lo + TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row
             const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
@@ -208,9 +210,14 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
             }
           }
           umma_commit(&bars->empty[s]);
+          }
+          __syncwarp();
         }
-        if (nchunk > 0) umma_commit(&bars->acc_full[buf]);
-        else mbar_arrive(&bars->acc_full[buf]);      // empty K range (k-split tail): the epilogue writes zeros
+        if (elect_one()) {
+          if (nchunk > 0) umma_commit(&bars->acc_full[buf]);
+          else mbar_arrive(&bars->acc_full[buf]);      // empty K range (k-split tail): the epilogue writes zeros
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 6) {

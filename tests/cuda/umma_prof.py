@@ -25,7 +25,7 @@ a = np.array(buf[:], dtype=np.int64).reshape(148, 32)
 names = {0: "TMA wait_empty_x", 8: "MMA wait_w_ready", 9: "MMA idle: G1 blk d1_empty", 10: "MMA idle: G1 blk xop_full", 11: "MMA idle: G2 blk hop_full",
          12: "MMA idle: G2 blk d2_empty", 13: "MMA idle: G1 done", 14: "MMA idle: G2 done", 15: "MMA total", 16: "CVT wait_full_x", 17: "CVT wait_xop_empty", 23: "CVT total",
          24: "EPI wait_d1_full", 25: "EPI wait_d2_full", 26: "EPI epi1", 27: "EPI epi2(incl wait)", 28: "EPI softmax/cand",
-         29: "EPI pool", 31: "EPI total"}
+         29: "EPI pool", 30: "EPI flush (bag ends)", 31: "EPI total"}
 for cta in (0, 1):
     sel = a[cta::2]
     print(f"--- cta rank {cta} (mean over {len(sel)} CTAs; tiles per CTA ~{S * 196 / 74:.1f})")
