@@ -1252,14 +1252,15 @@ int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned ch
       consts->inv_scale[i] = 1.f / sc;
     }
     consts->inv_scale[3] = 1.f;
-    // the tcgen05 kernel's softmax uses the fixed reference 0: needs |score| <= 77 for every possible input
+    // the tcgen05 kernel's softmax follows a running reference, so any finite score range is fine; non-finite score
+    // weights are left to the exact FFMA kernel (which propagates them like the reference does)
     float bound = 0.f;
     for (int k = 0; k < s.n_branch; ++k) {
       float bk = fabsf(consts->bw[k]);
       for (int u = 0; u < 128; ++u) bk += fabsf(consts->ww[k][u]);
       if (!(bk <= bound)) bound = bk;   // NaN-propagating max
     }
-    consts->valid = (bound <= 77.f) ? ACMIL_ABI_VERSION : 0;
+    consts->valid = isfinite(bound) ? ACMIL_ABI_VERSION : 0;
   }
   return ACMIL_OK;
 }

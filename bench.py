@@ -221,7 +221,9 @@ def run_ours(a):
 
         # the step is launch-bound next to its 0.27 ms row pass (9 small launches): capture it once per bag group
         graphs, graph_res, launch_mode = None, None, "eager"
-        if a.launch == "graph":
+        if a.launch == "graph" and world > 1:
+            launch_mode = "eager (the step holds NCCL collectives; graph replay is used at 1 GPU only)"
+        elif a.launch == "graph":
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
