@@ -46,7 +46,7 @@ def sources() -> list[str]:
 def _digest() -> str:
     h = hashlib.sha256()
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
-    files.append(os.path.join(ROOT, "include", "acmil_b200.h"))
+    files += sorted(os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h"))
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:

@@ -164,7 +164,12 @@ def build_model(cfg):
         encoder = vit_small(pretrained=True, progress=False, key="DINO_p16", patch_size=16)
     elif cfg.pretrain == 'tailored_sl':
         encoder = vit_small(pretrained=True, progress=False, key="DINO_p16", patch_size=16)
+    elif cfg.pretrain == 'natural_supervised' and cfg.backbone == 'Resnet18':      # models.py:201-204
+        from .resnet import resnet18
+        encoder = resnet18()
+        encoder.class_classifier = nn.Identity()
+        encoder.embed_dim = encoder.inplanes
     else:
         raise NotImplementedError(f"acmil_b200.build_model: backbone {cfg.backbone!r} / pretrain {cfg.pretrain!r} is not built "
-                                  "(only the ViT-S/16 encoders of SURVEY section 8a row a12)")
+                                  "(only the ViT-S/16 and ResNet18 encoders of SURVEY section 8a rows a12-a13)")
     return CustomModel(cfg, encoder)

@@ -221,7 +221,7 @@ def run_ours(a):
 
         # the step is launch-bound next to its 0.27 ms row pass (9 small launches): capture it once per bag group
         graphs, graph_res, launch_mode = None, None, "eager"
-        if a.launch == "graph" and world > 1:
+        if a.launch == "graph" and world > 1 and os.environ.get("ACMIL_BENCH_NCCL_GRAPH", "0") != "1":
             launch_mode = "eager (the step holds NCCL collectives; graph replay is used at 1 GPU only)"
         elif a.launch == "graph":
             try:
@@ -235,7 +235,7 @@ def run_ours(a):
                 graphs, graph_res = [], []
                 for gi in range(a.groups):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         r = step(gi)
                     graphs.append(g)
                     graph_res.append(r)
@@ -246,6 +246,7 @@ def run_ours(a):
             except Exception as exc:      # e.g. a collective that cannot be captured: eager launches
                 graphs, graph_res = None, None
                 launch_mode = f"eager (graph capture failed: {type(exc).__name__})"
+                print(f"[rank {rank}] graph capture failed: {exc!r}", file=sys.stderr)
                 torch.cuda.synchronize()
 
         sampler = ClockSampler(local)
