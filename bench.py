@@ -50,7 +50,7 @@ def parse():
                     help="graph: the step (mask draw + row pass + reduce + finish) is captured once per bag group in a CUDA "
                          "graph and replayed (falls back to eager launches if capture fails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit"],
+    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit", "resnet"],
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
     ap.add_argument("--dim", type=int, default=512, help="transmil: D_inner")
     ap.add_argument("--d-feat", type=int, default=512, help="transmil: D_feat")
@@ -371,8 +371,8 @@ def run_ours(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.workload in ("transmil", "vit"):
-        mod = __import__("bench_" + args.workload)
+    if args.workload in ("transmil", "vit", "resnet"):
+        mod = __import__("bench_" + ("vit" if args.workload == "resnet" else args.workload))
         if args.impl == "reference":
             mod.run_reference(args)
         elif not torch.cuda.is_available():

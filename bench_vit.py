@@ -14,9 +14,21 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PATCH_FLOPS = 2 * (196 * 768 * 384 + 12 * (197 * 384 * 1152 + 2 * 6 * 197 * 197 * 64 + 197 * 384 * 384 + 2 * 197 * 384 * 1536))
+# ResNet18 at 224x224 (models.py:13-77): conv1 + 4 stages of 2 BasicBlocks (+ 3 strided 1x1 downsample convolutions)
+RESNET_FLOPS = 2 * (112 * 112 * 147 * 64 + 4 * 56 * 56 * 576 * 64
+                    + 28 * 28 * (576 * 128 + 3 * 1152 * 128 + 64 * 128) + 14 * 14 * (1152 * 256 + 3 * 2304 * 256 + 128 * 256)
+                    + 7 * 7 * (2304 * 512 + 3 * 4608 * 512 + 256 * 512))
 
 
-def cpu_rate(batch, reps):
+def is_resnet(a):
+    return getattr(a, "workload", "vit") == "resnet"
+
+
+def names(a):
+    return ("ResNet18", RESNET_FLOPS, 512) if is_resnet(a) else ("ViT-S/16", PATCH_FLOPS, 384)
+
+
+def cpu_rate(batch, reps, resnet=False):
     from acmil_b200.vit import vit_small
     from oracle import preprocess as OP
     import numpy as np
@@ -39,6 +51,15 @@ def cpu_rate(batch, reps):
             t = t + F.linear(F.gelu(F.linear(y, p[b + "mlp.fc1.weight"], p[b + "mlp.fc1.bias"])), p[b + "mlp.fc2.weight"], p[b + "mlp.fc2.bias"])
         return F.layer_norm(t, (384,), p["norm.weight"], p["norm.bias"], 1e-6)[:, 0]
 
+    if resnet:      # the reference's own module graph (torchvision BasicBlocks) on the host cores
+        from acmil_b200.resnet import resnet18
+        rn = resnet18(pretrained=False).eval()
+
+        def fwd(x):      # models.py:54-73 with class_classifier = Identity (models.py:201-204)
+            x = rn.maxpool(rn.relu(rn.bn1(rn.conv1(x))))
+            x = rn.layer4(rn.layer3(rn.layer2(rn.layer1(x))))
+            return rn.avgpool(x).flatten(1)
+
     from PIL import Image
     from torchvision import transforms
     tr = transforms.Compose([transforms.Resize(224), transforms.ToTensor(),
@@ -57,7 +78,7 @@ def cpu_rate(batch, reps):
 
 
 def config(a, world, batch, cpu=False):
-    return {"workload": "ViT-S/16 patch-feature extraction: uint8 256x256 RGB patches -> Resize(224)+normalise -> encoder -> fp16 "
+    return {"workload": f"{names(a)[0]} patch-feature extraction: uint8 256x256 RGB patches -> Resize(224)+normalise -> encoder -> fp16 "
                         "features (BASELINE.json configs[3]; 100k patches = one slide), 3xTF32",
             "patches_per_step": batch * (1 if cpu else world), "parallelism": "cpu" if cpu else f"{world} data-parallel replica(s)",
             "l2_policy": "rotating resident patch batches (50 MB uint8 each, 154 MB fp32 after resize); activations of a batch exceed L2"}
@@ -67,9 +88,9 @@ def run_reference(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     batch = 64
-    rate = cpu_rate(batch, max(1, min(a.steps, 2)))
+    rate = cpu_rate(batch, max(1, min(a.steps, 2)), is_resnet(a))
     print(json.dumps({
-        "impl": "reference", "metric": "patches/sec (ViT-S/16 feature extraction)", "value": rate, "unit": "patches/s",
+        "impl": "reference", "metric": f"patches/sec ({names(a)[0]} feature extraction)", "value": rate, "unit": "patches/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": 1, "ms_per_step": batch / rate * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(a, 1, batch, cpu=True),
         "cpu_baseline": {"value": rate, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -91,7 +112,15 @@ def run_ours(a, ClockSampler):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = CustomModel(Struct(n_class=2), vit_small(False, False, None)).to(dev).eval()
+    if is_resnet(a):
+        from acmil_b200.resnet import resnet18
+        enc = resnet18(pretrained=False)
+        enc.class_classifier = torch.nn.Identity()
+        enc.embed_dim = enc.inplanes
+    else:
+        enc = vit_small(False, False, None)
+    model = CustomModel(Struct(n_class=2), enc).to(dev).eval()
+    enc_name, flops, feat_dim = names(a)
     batch = a.slides * 32
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     bags = [torch.randint(0, 256, (batch, 256, 256, 3), device=dev, dtype=torch.uint8, generator=gen) for _ in range(3)]
@@ -155,27 +184,27 @@ def run_ours(a, ClockSampler):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1345.7))
     sec = ms * 1e-3 / a.steps
-    achieved = PATCH_FLOPS * batch / sec / 1e12
+    achieved = flops * batch / sec / 1e12
     rate = world * batch * a.steps / (ms * 1e-3)
     line = {
-        "metric": "patches/sec (ViT-S/16 feature extraction)", "value": rate, "unit": "patches/s", "n_gpus": world,
+        "metric": f"patches/sec ({enc_name} feature extraction)", "value": rate, "unit": "patches/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 -> f32 (3xTF32 tensor-core products) -> f16", "data": "synthetic",
         "config": config(a, world, batch), "slides_per_sec_100k_patches": rate / 1e5,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "whole step (tm_gemm_kernel dominates)", "algorithmic_flops_per_patch": PATCH_FLOPS,
+                     "kernel": "whole step (tm_gemm_kernel dominates)", "algorithmic_flops_per_patch": flops,
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1345.7") +
                                     "; the fp32-faithful 3xTF32 split costs 6 bf16-equivalent MMAs per product"},
         "clocks": clocks,
         "e2e": {"value": world * n_e2e * 2 * batch / dt, "unit": "patches/s", "h2d_bytes_per_step": world * batch * 256 * 256 * 3,
-                "d2h_bytes_per_step": world * batch * 384 * 4,
+                "d2h_bytes_per_step": world * batch * feat_dim * 4,
                 "api": "extract_feature(uint8 patches in pinned host memory, model, batch_size): H2D, preprocess, encoder, features .cpu()"},
         "gpu_launches": int(launches * a.steps), "checksum": checksum,
     }
     if not a.no_cpu_baseline:
-        r = cpu_rate(64, 1)
+        r = cpu_rate(64, 1, is_resnet(a))
         line["cpu_baseline"] = {"value": r, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "1 batch of 64 patches after 1 warm-up: PIL/torchvision transform + torch CPU ViT-S/16 forward"}
+                                "sample": f"1 batch of 64 patches after 1 warm-up: PIL/torchvision transform + torch CPU {enc_name} forward"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
