@@ -316,8 +316,30 @@ def run_ours(a):
                 t = torch.tensor([dt], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
+            # the same call fed with fp16 features, the dtype the reference stores them in (Step2_feature_extract.py:165;
+            # Step3_WSI_classification_ACMIL.py:193 casts after the copy): half the PCIe bytes, cast on the device
+            fp16 = None
+            if world == 1:
+                host16 = [h.half().pin_memory() for h in host]
+                xdev16 = torch.empty(1, n_loc, D_FEAT, device=dev, dtype=torch.float16)
+
+                def user_call16(i):
+                    xdev16[0].copy_(host16[i % 2], non_blocking=True)
+                    _, slide, _ = model(xdev16)
+                    return slide.cpu()
+
+                for i in range(2):
+                    user_call16(i)
+                barrier()
+                t1 = time.perf_counter()
+                for i in range(n_e2e):
+                    user_call16(i)
+                barrier()
+                fp16 = {"value": n_e2e / (time.perf_counter() - t1), "unit": "slides/s",
+                        "h2d_bytes_per_step": a.slides * n_loc * D_FEAT * 2,
+                        "note": "fp16 features in pinned host memory (the H5 storage dtype), cast to fp32 on the device"}
             # at world > 1 one bag (sharded) per call; n_e2e bags in total
-            e2e = {"value": n_e2e / dt, "unit": "slides/s",
+            e2e = {"value": n_e2e / dt, "unit": "slides/s", "fp16_features": fp16,
                    "h2d_bytes_per_step": a.slides * n_loc * D_FEAT * 4 * world,
                    "d2h_bytes_per_step": a.slides * N_CLASS * 4 * world,
                    "api": "ACMIL_GA.forward(x[1,N,D]) per bag: pinned host -> device copy, fused kernels, logits .cpu()",
