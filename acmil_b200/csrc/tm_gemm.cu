@@ -28,7 +28,7 @@
 namespace {
 using namespace sm100;
 
-constexpr int GT = 320;          // threads per CTA: TMA, MMA, 4 splitter warps, 4 epilogue warps
+constexpr int GT = 448;          // threads per CTA: TMA, MMA, 4 splitter warps, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int BM = 128;          // tile rows
 constexpr int KC = 32;           // fp32 columns per stage = one 128-byte swizzle row
 constexpr int NST = 3;           // ring stages
@@ -53,6 +53,8 @@ struct GemmParams {
   int zdiv;                      // two-level batch: z_lo = z % zdiv, z_hi = z / zdiv
   long long c_bs2, ct_bs2, add_bs2;
   int vec_ok;                    // float4 stores are legal for c
+  int add_vec_ok;                // float4 loads are legal for addend
+  int bias_vec_ok;               // float4 loads are legal for a column bias
   int ksplit;                    // > 1: blockIdx.z = batch * ksplit + split; raw partial tiles go to split_ws
   int k_per_split;               // multiple of KC
   float* split_ws;               // [batch * ksplit][M][N]
@@ -64,7 +66,7 @@ struct Bars {
   uint64_t split[NST];           // hi/lo tiles written (4 converter warps)
   uint64_t empty[NST];           // MMAs that read the stage have completed
   uint64_t acc_full[2];          // accumulator buffer complete (tcgen05.commit)
-  uint64_t acc_empty[2];         // accumulator buffer drained by the 4 epilogue warps
+  uint64_t acc_empty[2];         // accumulator buffer drained by the 8 epilogue warps
   uint32_t tmem;
 };
 
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars->acc_full[b], 1);
-      mbar_init(&bars->acc_empty[b], 4);
+      mbar_init(&bars->acc_empty[b], 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.ta);
@@ -252,8 +254,10 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
       }
     }
   } else {
-    // ---------------- epilogue warps 6..9: warp w may touch TMEM lanes 32 (w % 4) .. +31 ----------------
-    const int q = warp & 3;
+    // ---------------- epilogue warps 6..13: warp w may touch TMEM lanes 32 (w % 4) .. +31; the two warps of a lane
+    // quarter take alternate 32-column chunks.  Thread = row: all per-element work is on registers, global traffic is
+    // float4 wherever the layout allows, and the column-block split is resolved once per chunk. ----------------
+    const int q = warp & 3, half = (warp - 6) >> 2;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
@@ -270,52 +274,83 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
           p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
       float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
       const int zsplit = p.ksplit > 1 ? t.bz * p.ksplit + t.split : 0;
+      const float rbias = (p.bias && p.bias_row && row_ok) ? p.bias[row] : 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (t.n0 + c0 >= p.N) break;
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        const int col0 = t.n0 + c0;
+        if (col0 >= p.N) break;
         uint32_t v[32];
         tmem_ld32(tm + buf * (TM_COLS / 2) + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_wait_ld();
+        const bool full = col0 + 32 <= p.N;      // warp-uniform
         if (p.ksplit > 1) {
           if (row_ok) {
-            float* dst = p.split_ws + ((size_t)zsplit * p.M + row) * p.N + t.n0 + c0;
+            float* dst = p.split_ws + ((size_t)zsplit * p.M + row) * p.N + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (t.n0 + c0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
+              if (col0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
           }
           continue;
         }
         float r[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = t.n0 + c0 + j;
-          float x = p.alpha * __uint_as_float(v[j]);
-          if (p.diag != 0.f && col == row) x += p.diag;
-          if (p.bias && col < p.N) x += p.bias_row ? (row_ok ? p.bias[row] : 0.f) : p.bias[col];
-          r[j] = x;
+        for (int j = 0; j < 32; ++j) r[j] = p.alpha * __uint_as_float(v[j]);
+        if (p.diag != 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j == row) r[j] += p.diag;
+        }
+        if (p.bias) {
+          if (p.bias_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += rbias;
+          } else if (full && p.bias_vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);      // same address in every lane: broadcast
+              r[j] += b4.x; r[j + 1] += b4.y; r[j + 2] += b4.z; r[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) r[j] += p.bias[col0 + j];
+          }
         }
         if (row_ok) {
           if (arow) {
+            if (full && p.add_vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (t.n0 + c0 + j < p.N) r[j] = fmaf(p.beta, arow[t.n0 + c0 + j], r[j]);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(arow + col0 + j);
+                r[j] = fmaf(p.beta, a4.x, r[j]); r[j + 1] = fmaf(p.beta, a4.y, r[j + 1]);
+                r[j + 2] = fmaf(p.beta, a4.z, r[j + 2]); r[j + 3] = fmaf(p.beta, a4.w, r[j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) r[j] = fmaf(p.beta, arow[col0 + j], r[j]);
+            }
           }
           if (p.act) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
           }
           if (crow) {
-            if (p.vec_ok && t.n0 + c0 + 32 <= p.N) {
+            // column blocks: the chunk sits inside one block whenever its first and last column do
+            const int blk0 = col0 / p.cbw, off0 = col0 - blk0 * p.cbw;
+            const bool one_blk = off0 + 32 <= p.cbw;
+            float* dst = crow + (size_t)blk0 * p.cbs + off0;
+            if (full && one_blk && p.vec_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const int col = t.n0 + c0 + j;
-                float* dst = crow + (size_t)(col / p.cbw) * p.cbs + col % p.cbw;
-                *reinterpret_cast<float4*>(dst) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-              }
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            } else if (one_blk) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = r[j];
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int col = t.n0 + c0 + j;
+                const int col = col0 + j;
                 if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
               }
             }
@@ -323,7 +358,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
           if (ctb) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int col = t.n0 + c0 + j;
+              const int col = col0 + j;
               if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
             }
           }
@@ -452,7 +487,7 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.M = d.m; gp.N = d.n; gp.K = d.k;
   gp.a_batched = a_b; gp.b_batched = b_b;
   gp.c_batch_stride = d.c_batch_stride; gp.ldc = d.ldc;
-  gp.cbw = d.col_block_width > 0 ? d.col_block_width : d.n;
+  gp.cbw = d.col_block_width > 0 ? d.col_block_width : (1 << 30);      // no column blocks: one block holds every column
   gp.cbs = d.col_block_width > 0 ? d.col_block_stride : 0;
   gp.ct_batch_stride = d.ct_batch_stride; gp.ldct = d.ldct;
   gp.add_batch_stride = d.addend_batch_stride; gp.ld_add = d.ld_addend;
@@ -462,7 +497,10 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.split_ws = d.split_ws;
 
   gp.vec_ok = d.c != nullptr && ((uintptr_t)d.c & 15) == 0 && d.ldc % 4 == 0 && gp.cbw % 4 == 0 && gp.cbs % 4 == 0 &&
-              d.c_batch_stride % 4 == 0;
+              d.c_batch_stride % 4 == 0 && d.c_batch_stride2 % 4 == 0;
+  gp.add_vec_ok = d.addend != nullptr && ((uintptr_t)d.addend & 15) == 0 && d.ld_addend % 4 == 0 &&
+                  d.addend_batch_stride % 4 == 0 && d.addend_batch_stride2 % 4 == 0;
+  gp.bias_vec_ok = d.bias != nullptr && !d.bias_per_row && ((uintptr_t)d.bias & 15) == 0;
   if (d.precise) return bn == 64 ? launch<64, true>(gp, d.batch, st) : launch<128, true>(gp, d.batch, st);
   return bn == 64 ? launch<64, false>(gp, d.batch, st) : launch<128, false>(gp, d.batch, st);
 }
