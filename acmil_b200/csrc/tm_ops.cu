@@ -63,16 +63,17 @@ __global__ void __launch_bounds__(256) tm_landmark_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// in-place softmax over rows of length len <= 1024: one warp per row, the row lives in registers
-__global__ void __launch_bounds__(256) tm_softmax_small_kernel(float* __restrict__ a, long long rows, int len, long long ld) {
+// in-place softmax over rows of length len <= 32 * NI <= 1024: one warp per row, the row lives in registers
+template <int NI>
+__global__ void __launch_bounds__(256) tm_softmax_small_kernel_t(float* __restrict__ a, long long rows, int len, long long ld) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* r = a + row * ld;
-  float v[32];
+  float v[NI];
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int j = lane + 32 * i;
     v[i] = j < len ? r[j] : -INFINITY;
     mx = fmaxf(mx, v[i]);
@@ -80,14 +81,23 @@ __global__ void __launch_bounds__(256) tm_softmax_small_kernel(float* __restrict
   mx = warp_max(mx);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = lane + 32 * i < len ? expf(v[i] - mx) : 0.f;
+  for (int i = 0; i < NI; ++i) {
+    v[i] = expf(v[i] - mx);      // exp(-inf) = 0 for the slots past the row
     s += v[i];
   }
   s = warp_sum(s);
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
+  for (int i = 0; i < NI; ++i)
     if (lane + 32 * i < len) r[lane + 32 * i] = v[i] / s;
+}
+// launch with the smallest register tile that holds the row
+static inline void tm_softmax_small_launch(float* a, long long rows, int len, long long ld, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (len <= 64) tm_softmax_small_kernel_t<2><<<grid, 256, 0, st>>>(a, rows, len, ld);
+  else if (len <= 128) tm_softmax_small_kernel_t<4><<<grid, 256, 0, st>>>(a, rows, len, ld);
+  else if (len <= 256) tm_softmax_small_kernel_t<8><<<grid, 256, 0, st>>>(a, rows, len, ld);
+  else if (len <= 512) tm_softmax_small_kernel_t<16><<<grid, 256, 0, st>>>(a, rows, len, ld);
+  else tm_softmax_small_kernel_t<32><<<grid, 256, 0, st>>>(a, rows, len, ld);
 }
 
 // in-place softmax over long rows: one CTA per row, three passes (the row stays in L2)
@@ -422,7 +432,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
     g.c = a2; g.ldc = m; g.c_batch_stride = mm;
     TM_RUN(tm_gemm(g, st));
-    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * m + 7) / 8), 256, 0, st>>>(a2, (long long)H * m, m, m);
+    tm_softmax_small_launch(a2, (long long)H * m, m, m, st);
     ++g_acmil_launches;
   }
   float *z = ws + L.za, *zt = ws + L.zta, *z2 = ws + L.zb, *zt2 = ws + L.ztb;
@@ -491,7 +501,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
     g.c = sbuf; g.ldc = m; g.c_batch_stride = (int64_t)nr * m;
     TM_RUN(tm_gemm(g, st));
-    tm_softmax_small_kernel<<<(unsigned)(((size_t)H * nr + 7) / 8), 256, 0, st>>>(sbuf, (long long)H * nr, m, m);
+    tm_softmax_small_launch(sbuf, (long long)H * nr, m, m, st);
     ++g_acmil_launches;
     ACMIL_CHECK_CUDA(cudaGetLastError());
     for (int b = 0; b < s.batch; ++b) {
@@ -531,7 +541,7 @@ extern "C" int acmil_softmax_rows_inplace(float* d_a, int64_t ld, int64_t rows, 
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
   ACMIL_REQUIRE(d_a && rows >= 0 && len >= 1 && len <= 1024 && ld >= len, ACMIL_E_INVALID, "softmax_rows_inplace: bad arguments");
   if (rows == 0) return ACMIL_OK;
-  tm_softmax_small_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_a, rows, len, ld);
+  tm_softmax_small_launch(d_a, rows, len, ld, (cudaStream_t)stream);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
