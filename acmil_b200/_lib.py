@@ -115,6 +115,9 @@ SYMBOLS = {
     "acmil_gp_finish": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_void_p, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(GpHeads),
                                   C.POINTER(GpOutputs), C.c_void_p]),
+    "acmil_gp_finish_rand": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_void_p, C.c_size_t, C.c_int,
+                                       C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.c_int32, C.POINTER(GpHeads),
+                                       C.POINTER(GpOutputs), C.c_void_p]),
     "acmil_gp_attn_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "acmil_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -252,9 +252,10 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
   return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), st);
 }
 
-int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
-                    size_t partial_bytes, int n_ranks, const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
-                    const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream) {
+static int gp_finish_common(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
+                            size_t partial_bytes, int n_ranks, const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
+                            const float* d_rand, int32_t rand_ld, const acmil_gp_heads* heads, const acmil_gp_outputs* out,
+                            void* stream) {
   if (int rc = check_shape(shape)) return rc;
   if (int rc = check_batch(batch)) return rc;
   ACMIL_REQUIRE(d_partials && heads && out, ACMIL_E_INVALID, "NULL argument");
@@ -277,12 +278,14 @@ int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch, co
     p.keep[s] = (keep && batch->n_masked > 0) ? keep[s] : 0;
     ACMIL_REQUIRE(p.keep[s] >= 0 && p.keep[s] <= batch->n_masked && p.keep[s] <= p.keep_ld, ACMIL_E_INVALID,
                   "keep[%d]=%d out of range", s, p.keep[s]);
-    ACMIL_REQUIRE(p.keep[s] == 0 || d_rsel != nullptr, ACMIL_E_INVALID, "masking needs d_rsel");
+    ACMIL_REQUIRE(p.keep[s] == 0 || d_rsel != nullptr || d_rand != nullptr, ACMIL_E_INVALID, "masking needs d_rsel or d_rand");
     p.row_off[s] = batch->row_offsets[s];
     p.shard_begin[s] = batch->shard_row_begin ? batch->shard_row_begin[s] : 0;
   }
   p.row_off[batch->n_slides] = batch->row_offsets[batch->n_slides];
   p.rsel = d_rsel;
+  p.rand = d_rand;
+  p.rand_ld = rand_ld;
   p.a_out = batch->d_a_out;
   p.a_ld = batch->a_ld;
   p.heads = *heads;
@@ -291,6 +294,19 @@ int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch, co
   ACMIL_REQUIRE(!(heads->slide_head || heads->shared_head) || (heads->d_ws && heads->d_bs), ACMIL_E_INVALID,
                 "slide/shared head needs d_ws/d_bs");
   return gp_launch_finish(p, (cudaStream_t)stream);
+}
+
+int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
+                    size_t partial_bytes, int n_ranks, const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
+                    const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream) {
+  return gp_finish_common(shape, batch, d_partials, partial_bytes, n_ranks, keep, d_rsel, keep_ld, nullptr, 0, heads, out, stream);
+}
+
+int acmil_gp_finish_rand(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
+                         size_t partial_bytes, int n_ranks, const int32_t* keep, const float* d_rand, int32_t rand_ld,
+                         int32_t keep_ld, const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream) {
+  ACMIL_REQUIRE(d_rand != nullptr && rand_ld >= 1, ACMIL_E_INVALID, "finish_rand needs the draws");
+  return gp_finish_common(shape, batch, d_partials, partial_bytes, n_ranks, keep, nullptr, keep_ld, d_rand, rand_ld, heads, out, stream);
 }
 
 int acmil_gp_attn_stats(const float* d_a, int64_t a_ld, int32_t n_branch, const int64_t* row_offsets, int32_t n_slides,

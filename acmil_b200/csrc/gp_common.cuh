@@ -220,6 +220,8 @@ struct GpFinishParams {
   int32_t keep[SMAX];
   const int64_t* rsel;    // [S][K][keep_ld]
   int keep_ld;
+  const float* rand;      // alternative to rsel: the uniform draws [S][K][rand_ld]; the kernel takes argsort(rand)[:keep]
+  int rand_ld;
   float* a_out;
   int64_t a_ld;
   int64_t row_off[SMAX + 1];

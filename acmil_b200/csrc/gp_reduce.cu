@@ -286,8 +286,7 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
       for (int i = ntop + lane; i < p.n_masked; i += 32) p.out.d_topk_idx[((size_t)s * K + k) * p.n_masked + i] = -1;
     if (lane == 0) s_ntop[k] = ntop;
     __syncwarp();
-    for (int i = lane; i < keep; i += 32) {
-      const int64_t sel = p.rsel[((size_t)s * K + k) * p.keep_ld + i];
+    auto mask_one = [&](int i, int64_t sel) {      // the i-th masked entry is the top row of rank `sel`
       if (sel >= 0 && sel < ntop) {
         const int pos = top_pos[k * NMAX + (int)sel];
         e_flag[k * ne + pos] = 3;
@@ -297,6 +296,19 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
         if (p.a_out && loc >= 0 && loc < p.row_off[s + 1] - p.row_off[s])
           p.a_out[(size_t)k * p.a_ld + p.row_off[s] + loc] = MASK_FILL;
       }
+    };
+    if (p.rand) {
+      // rsel = argsort(rand[k, :ntop])[:keep] (transformer.py:316) inside the warp: lane j holds draw j, its rank is the
+      // number of smaller draws (ties: lower index first); the lane of rank i provides the i-th masked entry
+      const float rv = lane < ntop ? p.rand[((size_t)s * K + k) * p.rand_ld + lane] : INFINITY;
+      int rank = 0;
+      for (int l = 0; l < ntop; ++l) {
+        const float o = __shfl_sync(0xffffffffu, rv, l);
+        rank += (o < rv || (o == rv && l < lane)) ? 1 : 0;
+      }
+      if (lane < ntop && rank < keep) mask_one(rank, lane);
+    } else {
+      for (int i = lane; i < keep; i += 32) mask_one(i, p.rsel[((size_t)s * K + k) * p.keep_ld + i]);
     }
     // ---- 2. same warp: m*, l*, afeat of branch k (no block-level synchronisation per branch) ----
     __syncwarp();

@@ -141,8 +141,11 @@ class GatedPool:
 
     def finish(self, ctx: dict, records: torch.Tensor, n_ranks: int = 1, *, keep: Optional[Sequence[int]] = None,
                rsel: Optional[torch.Tensor] = None, branch_w=None, branch_b=None, head_w=None, head_b=None,
-               slide_head: bool = False, shared_head: bool = False) -> GatedPoolResult:
-        """Merges ``n_ranks`` partial records (back to back in ``records``) and produces the outputs."""
+               slide_head: bool = False, shared_head: bool = False, rand: Optional[torch.Tensor] = None) -> GatedPoolResult:
+        """Merges ``n_ranks`` partial records (back to back in ``records``) and produces the outputs.
+
+        The mask draw comes either sorted (``rsel`` = ``argsort(rand)[..., :keep]``, int64) or raw (``rand`` =
+        ``torch.rand(..., n)`` itself, [S, K, n] fp32: the kernel sorts, no extra launches)."""
         lib = L.load()
         sp = self.spec
         K, Lw = sp.n_branch, sp.d_inner
@@ -151,14 +154,22 @@ class GatedPool:
         keep = [int(v) for v in keep] if keep is not None else [0] * S
         keep_ld = max([1] + keep)
         keep_arr = (C.c_int32 * max(S, 1))(*keep)
+        rand_ld = 0
         if n_masked > 0 and any(keep):
-            if rsel is None:
-                raise ValueError("masking needs rsel")
-            rsel = rsel.to(device=dev, dtype=torch.int64).contiguous()
-            if rsel.numel() < S * K * keep_ld:
-                raise ValueError("rsel must hold [S, K, max(keep)] indices")
+            if rand is not None:
+                rand = rand.to(device=dev, dtype=torch.float32).contiguous()
+                rand_ld = int(rand.shape[-1])
+                if rand.numel() != S * K * rand_ld:
+                    raise ValueError("rand must be [S, K, n] uniform draws")
+                rsel = None
+            elif rsel is None:
+                raise ValueError("masking needs rsel or rand")
+            else:
+                rsel = rsel.to(device=dev, dtype=torch.int64).contiguous()
+                if rsel.numel() < S * K * keep_ld:
+                    raise ValueError("rsel must hold [S, K, max(keep)] indices")
         else:
-            rsel = None
+            rsel = rand = None
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
         out_sub = f(S, K, C_) if (branch_w is not None or shared_head) else None
         out_slide = f(S, C_) if slide_head else None
@@ -175,8 +186,13 @@ class GatedPool:
                            _ptr(topk), _ptr(masked))
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            L.check(lib.acmil_gp_finish(C.byref(self._shape), C.byref(ctx["batch"]), _ptr(records), records.numel() * 4,
-                                        int(n_ranks), keep_arr, _ptr(rsel), keep_ld, C.byref(heads), C.byref(outs), st))
+            if rand is not None:
+                L.check(lib.acmil_gp_finish_rand(C.byref(self._shape), C.byref(ctx["batch"]), _ptr(records), records.numel() * 4,
+                                                 int(n_ranks), keep_arr, _ptr(rand), rand_ld, keep_ld, C.byref(heads),
+                                                 C.byref(outs), st))
+            else:
+                L.check(lib.acmil_gp_finish(C.byref(self._shape), C.byref(ctx["batch"]), _ptr(records), records.numel() * 4,
+                                            int(n_ranks), keep_arr, _ptr(rsel), keep_ld, C.byref(heads), C.byref(outs), st))
         scores = ctx["scores"]
         return GatedPoolResult(out_sub, out_slide, afeat, bag, lse_m, lse_l,
                                None if scores is None else scores[:, :R], topk, masked, ctx["row_offsets"])
@@ -186,7 +202,8 @@ class GatedPool:
             branch_w: Optional[torch.Tensor] = None, branch_b: Optional[torch.Tensor] = None,
             head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
             slide_head: bool = False, shared_head: bool = False, want_scores: bool = True,
-            shard_begin: Optional[Sequence[int]] = None, group=None, impl: Optional[int] = None) -> GatedPoolResult:
+            shard_begin: Optional[Sequence[int]] = None, group=None, impl: Optional[int] = None,
+            rand: Optional[torch.Tensor] = None) -> GatedPoolResult:
         """x: [R, d_in] fp32 CUDA, rows of S bags concatenated; row_offsets: S+1 host ints.
 
         With ``group`` (a torch.distributed process group) every rank passes its row shard of each bag and
@@ -200,7 +217,7 @@ class GatedPool:
             shard_begin is not None and torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
         gathered = gather_records(part, group) if world > 1 else part
         return self.finish(ctx, gathered, world, keep=keep, rsel=rsel, branch_w=branch_w, branch_b=branch_b,
-                           head_w=head_w, head_b=head_b, slide_head=slide_head, shared_head=shared_head)
+                           head_w=head_w, head_b=head_b, slide_head=slide_head, shared_head=shared_head, rand=rand)
 
     # ------------------------------------------------------------------ small ops
     @staticmethod

@@ -142,7 +142,7 @@ class _GatedPoolModule(nn.Module):
         raise NotImplementedError
 
     def _pool(self, x2d: torch.Tensor, *, n_masked=0, keep=0, rsel=None, branch=None, head=None,
-              slide_head=False, shared_head=False):
+              slide_head=False, shared_head=False, rand=None):
         """x2d [N, d_in] -> GatedPoolResult for one bag, differentiable w.r.t. params (and x)."""
         if not x2d.is_cuda:
             raise RuntimeError("acmil_b200 modules run on CUDA only: move the module and its input to a GPU "
@@ -156,7 +156,7 @@ class _GatedPoolModule(nn.Module):
             packed = op.pack(w.get("w1"), w.get("b1"), w["wv"], w.get("bv"), w.get("wu"), w.get("bu"), w["ww"], w.get("bw"))
             bw_, bb_ = (None, None) if branch is None else branch
             hw_, hb_ = (None, None) if head is None else head
-            return op.run(packed, xin.detach(), [0, n], n_masked=n_masked, keep=[keep], rsel=rsel, branch_w=bw_,
+            return op.run(packed, xin.detach(), [0, n], n_masked=n_masked, keep=[keep], rsel=rsel, rand=rand, branch_w=bw_,
                           branch_b=bb_, head_w=hw_, head_b=hb_, slide_head=slide_head, shared_head=shared_head)
 
         runner.spec = op.spec
@@ -300,22 +300,25 @@ class ACMIL_GA(_GatedPoolModule):
         nm = min(self.n_masked_patch, n)
         keep = int(nm * self.mask_drop)
         # same call, shape, device and order as transformer.py:316 -> same generator stream
-        rsel = torch.argsort(torch.rand(k, nm, device=device), dim=-1)[:, :keep]
+        # (the reference's argsort(...)[:, :keep] of the draw is taken inside acmil_gp_finish_rand: it consumes no
+        # random numbers, so only the rand call has to stay here)
+        rand = torch.rand(k, nm, device=device)
         if keep == 0:       # int(nm * mask_drop) == 0: the reference masks nothing (the draw above still happened)
             return 0, 0, None
-        return self.n_masked_patch, keep, rsel
+        return self.n_masked_patch, keep, rand
 
     def _run(self, x, use_mask, with_heads):
         x0 = x[0]
         if self.n_masked_patch > L.MAX_MASKED and use_mask:
             raise ValueError(f"n_masked_patch > {L.MAX_MASKED} is not supported by the kernels")
-        n_masked, keep, rsel = self._mask_args(x0.shape[0], x0.device, use_mask)
+        n_masked, keep, rand = self._mask_args(x0.shape[0], x0.device, use_mask)
         plain = with_heads and (self._droprate == 0.0 or not self.training)
         branch = head = None
         if plain:
             branch = (torch.stack([c.fc.weight for c in self.classifier]), torch.stack([c.fc.bias for c in self.classifier]))
             head = (self.Slide_classifier.fc.weight, self.Slide_classifier.fc.bias)
-        return self._pool(x0, n_masked=n_masked, keep=keep, rsel=rsel, branch=branch, head=head, slide_head=plain), plain
+        return self._pool(x0, n_masked=n_masked, keep=keep, rand=None if rand is None else rand[None], branch=branch, head=head,
+                          slide_head=plain), plain
 
     def forward(self, x):
         (res, diff), plain = self._run(x, self.training, True)

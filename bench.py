@@ -194,14 +194,13 @@ def run_ours(a):
     keep = int(nm * MASK_DROP)
 
     def step(i):
-        rsel = None
+        r = None
         if masking:
-            r = torch.rand(S, K_BRANCH, nm, device=dev)          # per bag: transformer.py:316
-            rsel = torch.argsort(r, dim=-1)[..., :keep].contiguous()
-            if world > 1:
-                dist.broadcast(rsel, src=0)
+            r = torch.rand(S, K_BRANCH, nm, device=dev)          # per bag: the draw of transformer.py:316; its argsort is
+            if world > 1:                                        # taken inside acmil_gp_finish_rand
+                dist.broadcast(r, src=0)
         return op.run(packed, groups[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
-                      keep=[keep if masking else 0] * S, rsel=rsel, branch_w=branch_w, branch_b=branch_b,
+                      keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
                       head_w=head_w, head_b=head_b, slide_head=True, shard_begin=shard_begin if world > 1 else None,
                       group=dist.group.WORLD if world > 1 else None)
 

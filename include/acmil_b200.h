@@ -192,6 +192,15 @@ ACMIL_API int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch*
                     const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
                     const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream);
 
+/* Same, but the mask draw is handed over raw: d_rand[S, K, rand_ld] = the uniform numbers of
+ * torch.rand(K, n) (transformer.py:316) and the kernel itself takes rsel = argsort(rand[:, :n])[:, :keep]
+ * (n = min(n_masked, rows of the bag); ties: lower index first), saving the caller's sort launches.
+ * d_masked_idx rows keep the stride keep_ld. */
+ACMIL_API int acmil_gp_finish_rand(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
+                                   size_t partial_bytes, int n_ranks, const int32_t* keep, const float* d_rand,
+                                   int32_t rand_ld, int32_t keep_ld, const acmil_gp_heads* heads,
+                                   const acmil_gp_outputs* out, void* stream);
+
 /* ---- small ops on the [K, N] score matrix --------------------------------------------- */
 /* Per bag: gram[K,K] = sum_n P_i P_j, ent[K] = sum_n P log P with P = softmax(A_out) given the
  * (m, l) of acmil_gp_finish; div = mean pairwise cosine; all fp32. */

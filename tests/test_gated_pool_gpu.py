@@ -376,3 +376,23 @@ def test_cabi_error_behaviour():
     with torch.no_grad():
         m(torch.zeros(1, 4, 384, device="cuda"))
     assert L.launch_count() >= before + 3
+
+
+@pytest.mark.parametrize("n", [50000, 7])
+def test_in_kernel_argsort_of_the_mask_draw_matches_torch(n):
+    """acmil_gp_finish_rand (raw uniform draws, argsort inside the kernel) == acmil_gp_finish fed torch.argsort(draws)."""
+    m = _random_acmil(3).cuda()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 384, generator=g).cuda()
+    nm = min(10, n)
+    keep = int(nm * 0.6)
+    rand = torch.rand(5, nm, generator=g)
+    rsel = torch.argsort(rand, dim=-1)[:, :keep].cuda()
+    branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+    head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+    with torch.no_grad():
+        a, _ = m._pool(x, n_masked=10, keep=keep, rsel=rsel, branch=branch, head=head, slide_head=True)
+        b, _ = m._pool(x, n_masked=10, keep=keep, rand=rand[None].cuda(), branch=branch, head=head, slide_head=True)
+    assert torch.equal(a.masked_idx, b.masked_idx)          # same rows in the same order
+    assert torch.equal(a.topk_idx, b.topk_idx)
+    np.testing.assert_allclose(b.slide.cpu().numpy(), a.slide.cpu().numpy(), rtol=1e-5, atol=1e-6)
