@@ -69,7 +69,9 @@ __device__ float block_sum(float v, float* red) {
 // One CTA of 1024 threads per (bag, branch).  Latency is what matters here (a few hundred KB at most):
 // warp 0 selects the rank's top-n candidates while warps 1..31 merge the segment partials, then all 32 warps
 // add the unselected candidates back; each warp covers the 128 features with one float4 per lane.
-constexpr int RR = 1024;
+// RR = threads per CTA: 1024 for the long segment / candidate lists of a whole 50k-row bag on one GPU, 256 when a bag
+// has few segments (row-sharded bags, small bags), where 8 CTAs per SM finish the whole batch in one wave.
+template <int RR>
 __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float red[RR / 32];
@@ -523,14 +525,19 @@ int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_recor
     const int c = (mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]) / mp.seg.cand_div * mp.seg.nm[s];
     if (c > max_cand) max_cand = c;
   }
-  const size_t smem = (((size_t)max_cand * 16 + 15) / 16) * 16 + (size_t)(RR / 32) * mp.sh.d_inner * 4 + 32;
+  int max_seg = 0;
+  for (int s = 0; s < S; ++s) max_seg = std::max(max_seg, mp.seg.seg_begin[s + 1] - mp.seg.seg_begin[s]);
+  const bool small = max_seg <= 8 && max_cand <= 128;
+  const int rr = small ? 256 : 1024;
+  const size_t smem = (((size_t)max_cand * 16 + 15) / 16) * 16 + (size_t)(rr / 32) * mp.sh.d_inner * 4 + 32;
   ACMIL_REQUIRE(smem <= 220 * 1024, ACMIL_E_INVALID, "reduce: too many candidates per bag (%d)", max_cand);
   static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!small && smem > configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gp_reduce_kernel<<<S * K, RR, smem, st>>>(p);
+  if (small) gp_reduce_kernel<256><<<S * K, 256, smem, st>>>(p);
+  else gp_reduce_kernel<1024><<<S * K, 1024, smem, st>>>(p);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;

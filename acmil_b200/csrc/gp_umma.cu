@@ -945,15 +945,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         unsigned* recs = reinterpret_cast<unsigned*>(smem + sm.tbuf + 1024);
         // lane (rg, cp = 0) speaks for row a, lane (rg, cp = 1) for row b of the row group
         const bool mine = (cp == 0 && valid_a) || (cp == 1 && valid_b);
+        // all thresholds first (independent shared-memory reads), one vote for the common "nothing to park" outcome
+        unsigned hits = 0u;
 #pragma unroll
         for (int k = 0; k < (KB <= CAND_KMAX ? KB : 0); ++k) {
           if (k < K) {
             const unsigned long long gq = *reinterpret_cast<volatile unsigned long long*>(&cs->gtau[k]);
             const float tau = fmaxf(*reinterpret_cast<volatile float*>(&cs->tau[k]),
                                     (unsigned)(gq >> 32) == (unsigned)s_cur ? __uint_as_float((unsigned)gq) : -INFINITY);
-            const float sv = cp == 0 ? sa[k] : sb[k];
-            const bool hit = mine && sv > tau;
-            if (__any_sync(0xffffffffu, hit)) {
+            if (mine && (cp == 0 ? sa[k] : sb[k]) > tau) hits |= 1u << k;
+          }
+        }
+        if (__any_sync(0xffffffffu, hits != 0u)) {
+#pragma unroll
+          for (int k = 0; k < (KB <= CAND_KMAX ? KB : 0); ++k) {
+            const bool hit = (hits >> k) & 1u;
+            if (k < K && __any_sync(0xffffffffu, hit)) {
+              const float sv = cp == 0 ? sa[k] : sb[k];
               int rec = -1;
               if (hit) {
                 rec = atomicAdd(&cs->app[k], 1);

@@ -196,8 +196,11 @@ def run_ours(a):
     def step(i):
         r = None
         if masking:
-            r = torch.rand(S, K_BRANCH, nm, device=dev)          # per bag: the draw of transformer.py:316; its argsort is
-            if world > 1:                                        # taken inside acmil_gp_finish_rand
+            # per bag: the draw of transformer.py:316; its argsort is taken inside acmil_gp_finish_rand.  Every rank seeds
+            # its generator identically (torch.manual_seed(0) above) and makes the same calls, so all ranks draw the same
+            # numbers without an exchange; `rng_in_sync` below checks that once and falls back to a broadcast otherwise.
+            r = torch.rand(S, K_BRANCH, nm, device=dev)
+            if world > 1 and not rng_in_sync[0]:
                 dist.broadcast(r, src=0)
         return op.run(packed, groups[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
                       keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
@@ -208,6 +211,15 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    rng_in_sync = [world == 1]
+    if world > 1:      # do the ranks' default CUDA generators agree?  (compare one probe draw with rank 0's)
+        probe = torch.rand(64, device=dev)
+        ref0 = probe.clone()
+        dist.broadcast(ref0, src=0)
+        same = torch.tensor([1.0 if torch.equal(probe, ref0) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        rng_in_sync[0] = bool(same.item() > 0.5)
 
     with torch.no_grad():
         for i in range(max(a.warmup, 3)):
@@ -378,6 +390,8 @@ def run_ours(a):
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps), "launch": launch_mode,
+        "mask_draw": "identical generator state on every rank (checked), no exchange" if (world > 1 and rng_in_sync[0]) else
+                     ("broadcast from rank 0" if world > 1 else "local"),
         "kernel_impl": a.kernel, "checksum": checksum,
     }
     if not a.no_cpu_baseline:
