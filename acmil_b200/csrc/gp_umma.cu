@@ -15,10 +15,16 @@
 //  * TMEM (512 columns): D1 h-accumulator 128 | D2 gate accumulator 128 (two halves per tile) |
 //    h operand hi/lo 128 | x operand ring 4 x 32.
 //
-// Roles per CTA (512 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
-// allocator, warps 4-7 converters (thread = row), warps 8-15 epilogue (16 rows per warp through the
-// 16-lane TMEM shapes; each warp keeps a private online-softmax stream and candidate lists, so there is
-// no cross-warp traffic per tile).
+// Roles per CTA (512 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA; warp-uniform code with
+// elect.sync around the tcgen05 instructions), warp 2 TMEM allocator + top-n list manager, warp 3 bag-wide
+// threshold service, warps 4-7 converters (thread = row), warps 8-15 epilogue (16 rows per warp through the
+// 16-lane TMEM shapes; each warp keeps a private softmax stream {m_ref, l, acc} whose pool step runs on
+// mma.sync fed by movmatrix transposes of the TMEM h operand, so there is no cross-warp traffic per tile;
+// rows that may be in a branch's top n are appended to scratch records instead of being summed).
+//
+// Scratch in shared memory ("tbuf", 7 KB + "ps", 4 KB): per tile ps holds each warp's softmax numerators
+// [16 rows][8]; tbuf holds the first-tile selection flags [128][8] (bytes 0-1023) and the appended record
+// scores [K][rec_cap] (from byte 1024); at a bag's end both are reused as the 11 KB buffer of the 8-warp merge.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -649,9 +655,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
       for (int k = 0; k < KB; ++k) l_run[k] = warp_sum(l_run[k]);
       {
-        float* xbuf = reinterpret_cast<float*>(smem + sm.tbuf);          // 12 KB: tbuf (8 KB) + ps (4 KB)
+        float* xbuf = reinterpret_cast<float*>(smem + sm.tbuf);          // 11 KB: tbuf (7 KB) + ps (4 KB)
         constexpr int PF = KB * 130;                                     // floats of one warp partial: {m, l, acc[128]} per branch
-        constexpr int MAXSLOT = (12288 / 4) / PF >= 4 ? 4 : ((12288 / 4) / PF >= 2 ? 2 : 1);
+        constexpr int MAXSLOT = (11264 / 4) / PF >= 4 ? 4 : ((11264 / 4) / PF >= 2 ? 2 : 1);
         asm volatile("bar.sync 1, 256;" ::: "memory");                   // everybody is done with ps
 #pragma unroll 1
         for (int stride = 4; stride >= 1; stride >>= 1) {
