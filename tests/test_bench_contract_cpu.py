@@ -1,0 +1,40 @@
+"""CPU: the reference arm of bench.py (the one bench leg that runs without a GPU) prints one JSON line that carries the
+keys the bench contract names, and the GPU arm refuses to run without a device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, timeout=600):
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", OMP_NUM_THREADS="4")
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
+                          cwd=ROOT, env=env)
+
+
+def test_reference_arm_prints_contract_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--rows", "2000")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "slides/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1
+    for key in ("metric", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_gpu_arm_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run("--steps", "1", "--warmup", "0", timeout=300)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout)
