@@ -243,6 +243,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// same for 64-byte swizzle: rows are 64 B apart, 8-row groups 512 B apart, SWIZZLE_64B(4) << 61
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
 // kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulate (c_format 1), both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

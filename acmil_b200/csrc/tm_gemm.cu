@@ -30,9 +30,18 @@ using namespace sm100;
 
 constexpr int GT = 448;          // threads per CTA: TMA, MMA, 4 splitter warps, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int BM = 128;          // tile rows
-constexpr int KC = 32;           // fp32 columns per stage = one 128-byte swizzle row
-constexpr int NST = 3;           // ring stages
-constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 16 KB
+#ifndef TM_GEMM_KC
+#define TM_GEMM_KC 32
+#endif
+// fp32 columns per stage: 32 = one 128-byte swizzle row, 3 stages of 64 KB.  -DTM_GEMM_KC=16 builds the 64-byte-swizzle
+// variant with 6 stages of 32 KB: measured 20 % SLOWER on the ViT GEMMs (fc1 478 vs 396 us), i.e. the engine is bound by
+// per-stage costs (barrier round trips, proxy fence, issue), not by the number of stages in flight.
+constexpr int KC = TM_GEMM_KC;
+constexpr int NST = KC == 16 ? 6 : 3;          // ring stages
+constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 8 KB (16 KB for KC = 32)
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+  return KC == 16 ? umma_desc_k_sw64(smem_addr) : umma_desc_k_sw128(smem_addr);
+}
 
 struct GemmParams {
   CUtensorMap ta, tb;            // (K, rows, batch_lo, batch_hi) fp32
@@ -204,11 +213,11 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
             if constexpr (PRECISE) {
               // the tensor core ignores the 13 low mantissa bits of a TF32 operand (measured: identical results with
               // and without masking), so the raw fp32 tile IS the hi operand; only the lo tile is produced
-              umma_tf32(tacc, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
-              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
-              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
+              umma_tf32(tacc, umma_desc_k(a_lo + k * 32), umma_desc_k(b_hi + k * 32), idesc, acc);
+              umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_lo + k * 32), idesc, 1u);
+              umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_hi + k * 32), idesc, 1u);
             } else {
-              umma_tf32(tacc, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+              umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_hi + k * 32), idesc, acc);
             }
           }
           umma_commit(&bars->empty[s]);
@@ -423,7 +432,7 @@ int make_map(CUtensorMap* m, const float* base, int rows, int K, long long ld, i
   cuuint32_t box[4] = {KC, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed for %s (%d)", what, (int)r);
   return ACMIL_OK;
