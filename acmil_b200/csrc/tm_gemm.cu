@@ -38,7 +38,8 @@ constexpr int BM = 128;          // tile rows
 // per-stage costs (barrier round trips, proxy fence, issue), not by the number of stages in flight.
 constexpr int KC = TM_GEMM_KC;
 constexpr int NST = KC == 16 ? 6 : 3;          // ring stages
-constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 8 KB (16 KB for KC = 32)
+constexpr uint32_t TILE_BYTES = BM * KC * 4;   // 16 KB (8 KB for KC = 16)
+constexpr int NST_MAX = 6;
 __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
   return KC == 16 ? umma_desc_k_sw64(smem_addr) : umma_desc_k_sw128(smem_addr);
 }
@@ -71,9 +72,9 @@ struct GemmParams {
 };
 
 struct Bars {
-  uint64_t full[NST];            // TMA bytes landed
-  uint64_t split[NST];           // hi/lo tiles written (4 converter warps)
-  uint64_t empty[NST];           // MMAs that read the stage have completed
+  uint64_t full[NST_MAX];        // TMA bytes landed
+  uint64_t split[NST_MAX];       // lo tile / TMEM operands written (4 converter warps)
+  uint64_t empty[NST_MAX];       // MMAs that read the stage have completed
   uint64_t acc_full[2];          // accumulator buffer complete (tcgen05.commit)
   uint64_t acc_empty[2];         // accumulator buffer drained by the 8 epilogue warps
   uint32_t tmem;
@@ -91,6 +92,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem: lane = row, one tf32 per column] * B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -104,11 +114,19 @@ __device__ __forceinline__ float act_apply_tm(float t, int act) {
   return t;
 }
 
-// smem: per stage {A hi, B hi, A lo, B lo}; B tiles hold BN rows
+// smem per stage: {A (raw fp32 = the hi operand), B hi, [B lo]}; B tiles hold BN rows.  In the precise mode the A operands
+// of the MMAs live in TMEM (TS mode): the converter warps read the landed A tile once and write A (raw) and A_lo there,
+// so shared memory carries the TMA fill, ONE read of A, the B split and only B's operand reads -- 128 KB per K chunk
+// instead of 192 KB (SS mode with A_lo in shared memory), which is what bounds this engine (profiles/ncu_r1_gemm_summary.md).
 template <int BN>
 __host__ __device__ constexpr uint32_t stage_bytes(bool precise) {
-  return (TILE_BYTES + (uint32_t)BN * KC * 4) * (precise ? 2u : 1u);
+  return TILE_BYTES + (uint32_t)BN * KC * 4 * (precise ? 2u : 1u);
 }
+template <int BN>
+__host__ __device__ constexpr int ring_stages(bool precise) {      // as many as fit next to the barriers in 227 KB
+  return (precise && KC == 32) ? (BN <= 64 ? 6 : 4) : NST;
+}
+constexpr uint32_t A_SLOT_COLS = 2 * KC;      // TMEM columns of one A operand slot: KC raw + KC lo
 
 struct TileCoord {
   int m0, n0, bz, split;
@@ -133,15 +151,20 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t B_BYTES = (uint32_t)BN * KC * 4;
   constexpr uint32_t STAGE = stage_bytes<BN>(PRECISE);
-  constexpr uint32_t TM_COLS = 2 * (BN < 32 ? 32 : BN);
-  Bars* bars = reinterpret_cast<Bars*>(smem + NST * STAGE);
+  constexpr int NS = ring_stages<BN>(PRECISE);
+  constexpr uint32_t ACC_COLS = 2 * (BN < 32 ? 32 : BN);            // two accumulators
+  constexpr uint32_t TM_A = ACC_COLS;                               // A operand slots behind them (precise mode)
+  constexpr uint32_t TM_NEED = ACC_COLS + (PRECISE ? NS * A_SLOT_COLS : 0);
+  constexpr uint32_t TM_COLS = TM_NEED <= 64 ? 64 : (TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512));
+  static_assert(TM_NEED <= 512, "TMEM budget");
+  Bars* bars = reinterpret_cast<Bars*>(smem + NS * STAGE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM;
   const int ntiles = p.ntiles;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->split[s], 4);
       mbar_init(&bars->empty[s], 1);
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         k_range(t, kbeg, nchunk);
         const int zlo = t.bz % p.zdiv, zhi = t.bz / p.zdiv;
         for (int c = 0; c < nchunk; ++c, ++ctr) {
-          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
           mbar_wait(&bars->empty[s], ph ^ 1u);
           unsigned char* st = smem + s * STAGE;
           mbar_expect_tx(&bars->full[s], TILE_BYTES + B_BYTES);
@@ -199,23 +222,23 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         const uint32_t buf = it & 1u;
         mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tm + buf * (TM_COLS / 2);
+        const uint32_t tacc = tm + buf * (ACC_COLS / 2);
         for (int c = 0; c < nchunk; ++c, ++ctr) {
-          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
           mbar_wait(PRECISE ? &bars->split[s] : &bars->full[s], ph);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES;
-          const uint32_t a_lo = b_hi + B_BYTES, b_lo = a_lo + TILE_BYTES;
+          const uint32_t a_hi = smem_u32(smem + s * STAGE), b_hi = a_hi + TILE_BYTES, b_lo = b_hi + B_BYTES;
+          const uint32_t ta_hi = tm + TM_A + s * A_SLOT_COLS, ta_lo = ta_hi + KC;
           if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row
+          for (int k = 0; k < KC / 8; ++k) {      // one MMA covers K = 8 tf32 = 32 bytes of the swizzle row / 8 TMEM columns
             const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
             if constexpr (PRECISE) {
               // the tensor core ignores the 13 low mantissa bits of a TF32 operand (measured: identical results with
-              // and without masking), so the raw fp32 tile IS the hi operand; only the lo tile is produced
-              umma_tf32(tacc, umma_desc_k(a_lo + k * 32), umma_desc_k(b_hi + k * 32), idesc, acc);
-              umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_lo + k * 32), idesc, 1u);
-              umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_hi + k * 32), idesc, 1u);
+              // and without masking), so the raw fp32 value IS the hi operand; only the lo parts are produced
+              umma_tf32_ts(tacc, ta_lo + k * 8, umma_desc_k(b_hi + k * 32), idesc, acc);
+              umma_tf32_ts(tacc, ta_hi + k * 8, umma_desc_k(b_lo + k * 32), idesc, 1u);
+              umma_tf32_ts(tacc, ta_hi + k * 8, umma_desc_k(b_hi + k * 32), idesc, 1u);
             } else {
               umma_tf32(tacc, umma_desc_k(a_hi + k * 32), umma_desc_k(b_hi + k * 32), idesc, acc);
             }
@@ -233,29 +256,56 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
     }
   } else if (warp < 6) {
     if constexpr (PRECISE) {
-      // lo = x - (x with the 13 low mantissa bits cleared), written at the same swizzled position of the lo tiles
-      const int ct = (warp - 2) * 32 + lane;             // 0..127
-      constexpr int NV = (TILE_BYTES + B_BYTES) / 16;    // float4 slots of {A, B}
+      // Converter warps 2..5 (TMEM lane quarters 2, 3, 0, 1): thread = row of the A tile.  A: the landed fp32 row is read
+      // once (de-swizzled LDS.128, conflict-free: the 8 lanes of a quarter-warp hit 8 different 16-byte chunks), the raw
+      // values and lo = x - (x with the 13 low mantissa bits cleared) go to the stage's TMEM operand slot.  B: lo written
+      // at the same swizzled position of the B_lo tile (linear float4 slots, layout-agnostic).
+      static_assert(KC == 32, "the TMEM converter assumes 128-byte rows");
+      const int qd = warp & 3;
+      const int r = qd * 32 + lane;                      // A tile row == TMEM lane
+      const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+      const int ct = (warp - 2) * 32 + lane;             // 0..127: linear slot owner for B
+      constexpr int NVB = B_BYTES / 16;                  // float4 slots of B
       uint32_t ctr = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
         int kbeg, nchunk;
         k_range(t, kbeg, nchunk);
         for (int c = 0; c < nchunk; ++c, ++ctr) {
-          const uint32_t s = ctr % NST, ph = (ctr / NST) & 1u;
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
           mbar_wait(&bars->full[s], ph);
-          const float4* hi = reinterpret_cast<const float4*>(smem + s * STAGE);
-          float4* lo = reinterpret_cast<float4*>(smem + s * STAGE + TILE_BYTES + B_BYTES);
+          const unsigned char* rowp = smem + s * STAGE + (r >> 3) * 1024 + (r & 7) * 128;
+          const uint32_t ta = tm + lane_addr + TM_A + s * A_SLOT_COLS;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                  // 16 columns at a time keeps the register footprint small
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = *reinterpret_cast<const float4*>(rowp + (((4 * h + i) ^ (r & 7)) << 4));
+              hi[4 * i] = __float_as_uint(v.x); hi[4 * i + 1] = __float_as_uint(v.y);
+              hi[4 * i + 2] = __float_as_uint(v.z); hi[4 * i + 3] = __float_as_uint(v.w);
+              lo[4 * i] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+              lo[4 * i + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+              lo[4 * i + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+              lo[4 * i + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+            }
+            tmem_st16(ta + 16 * h, hi);
+            tmem_st16(ta + KC + 16 * h, lo);
+          }
+          const float4* bhi = reinterpret_cast<const float4*>(smem + s * STAGE + TILE_BYTES);
+          float4* blo = reinterpret_cast<float4*>(smem + s * STAGE + TILE_BYTES + B_BYTES);
 #pragma unroll 8
-          for (int i = ct; i < NV; i += 128) {
-            const float4 v = hi[i];
+          for (int i = ct; i < NVB; i += 128) {
+            const float4 v = bhi[i];
             float4 l;
             l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            lo[i] = l;
+            blo[i] = l;
           }
+          tmem_wait_st();
+          tc_fence_before();
           fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->split[s]);
@@ -289,7 +339,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         const int col0 = t.n0 + c0;
         if (col0 >= p.N) break;
         uint32_t v[32];
-        tmem_ld32(tm + buf * (TM_COLS / 2) + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld32(tm + buf * (ACC_COLS / 2) + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_wait_ld();
         const bool full = col0 + 32 <= p.N;      // warp-uniform
         if (p.ksplit > 1) {
@@ -441,7 +491,7 @@ int make_map(CUtensorMap* m, const float* base, int rows, int K, long long ld, i
 template <int BN, bool PRECISE>
 int launch(const GemmParams& gp, int batch, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = (size_t)NST * stage_bytes<BN>(PRECISE) + sizeof(Bars) + 1024;
+  const size_t smem = (size_t)ring_stages<BN>(PRECISE) * stage_bytes<BN>(PRECISE) + sizeof(Bars) + 1024;
   if (!configured) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_gemm_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
