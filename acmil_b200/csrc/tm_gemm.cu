@@ -108,6 +108,28 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
       : "memory");
 }
 
+// nn.GELU() (exact, erf based) on two values at once with packed fp32 arithmetic:  gelu(x) = x/2 (1 + erf(x / sqrt 2)),
+// erf(|z|) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p |z|)  (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, i.e.
+// one fp32 ulp of the 1 + erf factor).  ~10 issue slots per element instead of ~30 for erff: the GELU epilogue of the MLP's
+// first GEMM competes with the converter warps for issue slots.
+__device__ __forceinline__ uint64_t gelu2(uint64_t x2) {
+  const float x0 = lo2(x2), x1 = hi2(x2);
+  const uint64_t az = pack2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);      // |z|
+  const uint64_t den = fma2(pack2(0.3275911f, 0.3275911f), az, pack2(1.f, 1.f));
+  const uint64_t t = pack2(rcp_approx(lo2(den)), rcp_approx(hi2(den)));
+  uint64_t pl = fma2(pack2(1.061405429f, 1.061405429f), t, pack2(-1.453152027f, -1.453152027f));
+  pl = fma2(pl, t, pack2(1.421413741f, 1.421413741f));
+  pl = fma2(pl, t, pack2(-0.284496736f, -0.284496736f));
+  pl = fma2(pl, t, pack2(0.254829592f, 0.254829592f));
+  pl = mul2(pl, t);
+  const uint64_t ex = mul2(mul2(az, az), pack2(-1.4426950408889634f, -1.4426950408889634f));                  // -z^2 log2(e)
+  const uint64_t e = pack2(ex2_approx(lo2(ex)), ex2_approx(hi2(ex)));
+  const uint64_t erfa = fma2(mul2(pl, pack2(-1.f, -1.f)), e, pack2(1.f, 1.f));                                 // erf(|z|)
+  const uint64_t erfs = pack2(copysignf(lo2(erfa), x0), copysignf(hi2(erfa), x1));
+  const uint64_t hx = mul2(x2, pack2(0.5f, 0.5f));
+  return fma2(erfs, hx, hx);
+}
+
 __device__ __forceinline__ float act_apply_tm(float t, int act) {
   if (act == 1) return fmaxf(t, 0.f);
   if (act == 2) return 0.5f * t * (1.f + erff(t * 0.70710678118654752440f));      // nn.GELU() (exact)
@@ -390,7 +412,14 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
                 if (col0 + j < p.N) r[j] = fmaf(p.beta, arow[col0 + j], r[j]);
             }
           }
-          if (p.act) {
+          if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint64_t g = gelu2(pack2(r[j], r[j + 1]));
+              r[j] = lo2(g);
+              r[j + 1] = hi2(g);
+            }
+          } else if (p.act) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
           }
