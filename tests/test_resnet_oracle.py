@@ -49,3 +49,25 @@ def test_cpu_input_raises():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             m(torch.zeros(1, 3, 64, 64))
+
+
+def test_fold_matches_conv_then_batchnorm():
+    """acmil_b200.resnet._fold (eval BatchNorm folded into im2col-ordered weights + bias) against conv -> BN in torch."""
+    import torch.nn.functional as F
+    from acmil_b200.resnet import _fold
+    torch.manual_seed(0)
+    for cin, cout, k, stride, pad in [(3, 8, 7, 2, 3), (8, 16, 3, 1, 1), (8, 16, 1, 2, 0)]:
+        conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
+        bn = randomize_bn(torch.nn.BatchNorm2d(cout), 5).eval()
+        x = torch.randn(2, cin, 13, 11)
+        with torch.no_grad():
+            ref = bn(conv(x))
+            w, b = _fold(conv, bn)
+            # the column order of acmil_im2col: (ky, kx, c); unfold gives (c, ky, kx)
+            cols = F.unfold(x, k, padding=pad, stride=stride)                       # [B, c*k*k, L]
+            B, _, L = cols.shape
+            cols = cols.view(B, cin, k, k, L).permute(0, 4, 2, 3, 1).reshape(B * L, k * k * cin)
+            cols = F.pad(cols, (0, w.shape[1] - cols.shape[1]))
+            out = (cols @ w.T + b).view(B, L, cout).permute(0, 2, 1).reshape(ref.shape)
+        assert w.shape[1] % 4 == 0
+        np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
