@@ -38,7 +38,7 @@ extern "C" {
  * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction).
  * Two-level batches: with batch_inner > 0, entry z uses offsets (z % batch_inner) * X_batch_stride +
  * (z / batch_inner) * X_batch_stride2 for every operand X (e.g. z = head * images + image).
- * act: 0 none, 1 relu, 2 exact (erf) GELU -- applied last. */
+ * act: 0 none, 1 relu, 2 erf-based GELU (nn.GELU() default; erf by Abramowitz-Stegun 7.1.26, |error| <= 2e-7) -- applied last. */
 typedef struct acmil_gemm_desc {
   const float* a;
   const float* b;
