@@ -38,3 +38,16 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = _run("--steps", "1", "--warmup", "0", timeout=300)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm with torchrun too; rank 0 alone runs and prints, the others exit 0."""
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29578", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0", "--rows", "2000"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
