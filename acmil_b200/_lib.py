@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libacmil_b200.so")
+LIB_PATH = os.path.join(os.environ.get("ACMIL_B200_LIB_DIR") or os.path.join(_HERE, "lib"), "libacmil_b200.so")
 
 MAX_BRANCH, MAX_MASKED, MAX_SLIDES, MAX_CLASS = 8, 32, 64, 16
 ACT_TANH, ACT_RELU, ACT_GELU = 0, 1, 2
@@ -112,6 +112,8 @@ SYMBOLS = {
     "acmil_gp_sizes": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, _SIZE_P, _SIZE_P]),
     "acmil_gp_partial": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpConsts), C.POINTER(GpBatch), C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "acmil_gp_overflow_flags": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, C.c_void_p,
+                                          C.POINTER(C.c_int32), C.c_void_p]),
     "acmil_gp_finish": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_void_p, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_int32), C.c_void_p, C.c_int32, C.POINTER(GpHeads),
                                   C.POINTER(GpOutputs), C.c_void_p]),
@@ -154,11 +156,21 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        # (ACMIL_B200_NO_REBUILD=1: load what is there -- variant builds made with other ACMIL_NVCC_EXTRA flags)
+        stale = (os.path.exists(LIB_PATH) and os.environ.get("ACMIL_B200_NO_REBUILD") != "1"
+                 and not _build.up_to_date())
+        if not os.path.exists(LIB_PATH) or stale:
+            # missing, or built from other sources / flags than the ones in the tree (the stamp holds their digest)
             if not build_if_missing:
-                raise ImportError(f"{LIB_PATH} is missing; run `python -m acmil_b200.build`")
-            from . import build as _build
-            _build.build()
+                raise ImportError(f"{LIB_PATH} is {'stale' if stale else 'missing'}; run `python -m acmil_b200.build`")
+            try:
+                _build.build()
+            except RuntimeError:
+                if not stale:
+                    raise
+                import warnings
+                warnings.warn(f"{LIB_PATH} does not match the sources and could not be rebuilt; loading it as it is")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+from concurrent.futures import ThreadPoolExecutor
 import shutil
 import subprocess
 import sys
@@ -14,7 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB_DIR = os.path.join(HERE, "lib")
+# ACMIL_B200_LIB_DIR: build / load a variant library from another in-tree directory (kernel experiments: a second
+# build with other -D flags next to the default one); the default is acmil_b200/lib
+LIB_DIR = os.environ.get("ACMIL_B200_LIB_DIR") or os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libacmil_b200.so")
 STAMP = os.path.join(LIB_DIR, "libacmil_b200.stamp")
 
@@ -55,26 +58,55 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def up_to_date() -> bool:
+    """True when the in-tree library was built from the current sources and flags."""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == _digest()
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+    if not force and up_to_date():
         return LIB
-    objs = []
+    # one builder at a time (torchrun ranks all call load() at start-up); the others wait and then find the stamp
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    dig = _digest()
     log = []
-    for src in sources():
+
+    def compile_one(src: str) -> str:
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
         cmd = [_nvcc(), *_flags(), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        out = "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + log[-1])
-        objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+            raise RuntimeError("nvcc failed:\n" + out)
+        log.append(out)
+        return obj
+
+    # one nvcc per translation unit, all at once (the files are independent)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    # link under a temporary name and rename: a concurrent load() (torchrun ranks) never sees a half-written library
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + log[-1])
+    os.replace(tmp, LIB)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(STAMP, "w") as fh:

@@ -73,11 +73,13 @@ int pick_impl(const acmil_gp_shape& s, int impl) {
   return gp_umma_supported(s) ? ACMIL_IMPL_UMMA : ACMIL_IMPL_FFMA;
 }
 
+size_t rescue_offset(size_t umma_ws_bytes) { return (umma_ws_bytes + 1023) / 1024 * 1024; }
+
 int plan(const acmil_gp_shape& s, const acmil_gp_batch& b, int impl, GpSegTable* seg, GpWorkspace* wl) {
   if (impl == ACMIL_IMPL_UMMA)
     ACMIL_REQUIRE(gp_umma_build_plan(b, sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
   else
-    ACMIL_REQUIRE(gp_build_segments(b, 64, 4 * sm_count(), seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
+    ACMIL_REQUIRE(gp_build_segments(b, 64, 4 * sm_count(), s.n_branch, seg) == 0, ACMIL_E_INVALID, "bad row_offsets");
   *wl = gp_workspace_layout(s, *seg);
   return ACMIL_OK;
 }
@@ -190,10 +192,11 @@ int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int
   GpWorkspace wl;
   if (int rc = plan(*shape, *batch, pick_impl(*shape, impl), &seg, &wl)) return rc;
   size_t ws = wl.total_bytes;
-  if (impl == ACMIL_IMPL_AUTO && pick_impl(*shape, impl) == ACMIL_IMPL_UMMA) {
-    // AUTO may still run the FFMA kernel (no host constants): size for whichever needs more
+  if (pick_impl(*shape, impl) == ACMIL_IMPL_UMMA) {
+    // the tcgen05 kernel's workspace is followed by the FFMA kernel's: the rescue pass of bags that ran out of parking
+    // slots works there (and AUTO may run the FFMA kernel alone when no host constants were supplied)
     if (int rc = plan(*shape, *batch, ACMIL_IMPL_FFMA, &seg, &wl)) return rc;
-    if (wl.total_bytes > ws) ws = wl.total_bytes;
+    ws = rescue_offset(ws) + wl.total_bytes;
   }
   if (workspace_bytes) *workspace_bytes = ws;
   if (partial_bytes) *partial_bytes = gp_record(*shape, batch->n_masked).stride() * 4 * (size_t)batch->n_slides;
@@ -249,7 +252,42 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
                : gp_launch_main_ffma(p, st);
   if (rc) return rc;
   if (e1) ACMIL_CHECK_CUDA(cudaEventRecord(e1, st));
-  return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), st);
+  if (use != ACMIL_IMPL_UMMA || batch->n_masked == 0)
+    return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), nullptr, GP_REDUCE_ALL, st);
+  // Training-mode masking on the tcgen05 kernel: a bag whose score order defeats the bounded parking scratch (e.g. rows
+  // sorted by ascending score) is flagged per bag; the exact FFMA kernel redoes exactly those bags (its CTAs return at
+  // once otherwise) and each reduce launch takes the bags of its side.  No host round trip, graph-capturable.
+  const int* d_flags = reinterpret_cast<const int*>(p.ws + p.wl.flags);
+  static thread_local GpMainParams q;      // large: keep off the stack
+  q = p;
+  if ((rc = plan(*shape, *batch, ACMIL_IMPL_FFMA, &q.seg, &q.wl))) return rc;
+  q.ws = p.ws + rescue_offset(p.wl.total_bytes);
+  ACMIL_REQUIRE(workspace_bytes >= rescue_offset(p.wl.total_bytes) + q.wl.total_bytes, ACMIL_E_WORKSPACE,
+                "workspace too small for the rescue pass: %zu < %zu", workspace_bytes,
+                rescue_offset(p.wl.total_bytes) + q.wl.total_bytes);
+  q.rescue_flags = d_flags;
+  if ((rc = gp_launch_main_ffma(q, st))) return rc;
+  if ((rc = gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_UNFLAGGED, st))) return rc;
+  return gp_launch_reduce(q, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_FLAGGED, st);
+}
+
+int acmil_gp_overflow_flags(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int impl, const void* d_workspace,
+                            int32_t* host_flags, void* stream) {
+  if (int rc = check_shape(shape)) return rc;
+  if (int rc = check_batch(batch)) return rc;
+  ACMIL_REQUIRE(d_workspace && host_flags, ACMIL_E_INVALID, "NULL argument");
+  for (int s = 0; s < batch->n_slides; ++s) host_flags[s] = 0;
+  if (pick_impl(*shape, impl) != ACMIL_IMPL_UMMA || batch->n_masked == 0) return ACMIL_OK;
+  GpSegTable seg;
+  GpWorkspace wl;
+  if (int rc = plan(*shape, *batch, ACMIL_IMPL_UMMA, &seg, &wl)) return rc;
+  int32_t tmp[SMAX];
+  cudaStream_t st = (cudaStream_t)stream;
+  ACMIL_CHECK_CUDA(cudaMemcpyAsync(tmp, reinterpret_cast<const unsigned char*>(d_workspace) + wl.flags,
+                                   sizeof(int32_t) * batch->n_slides, cudaMemcpyDeviceToHost, st));
+  ACMIL_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < batch->n_slides; ++s) host_flags[s] = tmp[s] == 1 ? 1 : 0;
+  return ACMIL_OK;
 }
 
 static int gp_finish_common(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,

@@ -91,17 +91,21 @@ struct GpSegTable {
   // produces 2 segments (one per CTA; its 8 epilogue warps merge their partials in shared memory):
   // seg_begin[s] + (c - u_cfirst[s]) * 2 + cta
   // candidate bookkeeping: lists live per "candidate holder" = group of cand_div consecutive segments
-  // (FFMA: every segment; tcgen05: one per CTA and bag = 8 segments); each holder owns cand lists of
-  // n_masked_cap entries per branch and rec_cap parked h rows per branch
+  // (FFMA: every segment; tcgen05: one per CTA and bag); each holder owns cand lists of n_masked_cap
+  // entries per branch, rec_cap (score, row, h-slot) records per branch and row_cap parked h rows:
+  // a record's h row sits in slot  k * h_branch_stride + cand_slot  of the holder
+  // (FFMA: n_masked_cap private slots per branch; tcgen05: one slot per parked ROW, shared by the branches)
   int32_t cand_div;
   int32_t rec_cap;
+  int32_t row_cap;
+  int32_t h_branch_stride;
   int32_t u_nclusters;
   int32_t u_total_pt;
   int32_t u_pt_begin[SMAX + 1];
   int32_t u_cfirst[SMAX];
 };
 
-static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int target_seg, GpSegTable* t) {
+static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int target_seg, int s_branch, GpSegTable* t) {
   memset(t, 0, sizeof(*t));
   t->n_slides = b.n_slides;
   t->tile_rows = tile_rows;
@@ -135,6 +139,8 @@ static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int 
   t->n_masked_cap = cap;
   t->cand_div = 1;
   t->rec_cap = cap;
+  t->row_cap = cap * s_branch;
+  t->h_branch_stride = cap;
   return 0;
 }
 
@@ -142,10 +148,12 @@ static inline int gp_build_segments(const acmil_gp_batch& b, int tile_rows, int 
 // per segment and branch:  part[seg][k][L+2] = {m, l, acc[L]}
 // per candidate holder cb = seg / cand_div and branch:
 //   cand_cnt[cb][k]; cand_score/idx/slot[cb][k][cap] (the holder's top-n list; slot = index of the parked row)
-//   rec_score/rec_idx[cb][k][rec_cap] (every row ever parked; tcgen05 kernel only); cand_h[cb][k][rec_cap][L]
-//   flags[0] != 0: a holder ran out of parking slots (results are poisoned with NaN by the reduce kernel)
+//   rec_score/rec_idx/rec_slot[cb][k][rec_cap] (every row ever parked; tcgen05 kernel only); cand_h[cb][row_cap][L]
+//   flags[s] == 1: a holder of bag s ran out of parking slots in the tcgen05 kernel -> the bag is redone by the exact
+//   FFMA kernel ("rescue" launch) and the reduce kernel takes that result.  flags sits right in front of cand_score so
+//   that ONE memset (0xFF: flag -1 = clean, list entries NaN = "not written in this launch") prepares both.
 struct GpWorkspace {
-  size_t part, cand_cnt, cand_score, cand_idx, cand_slot, rec_score, rec_idx, cand_h, flags;  // byte offsets
+  size_t part, cand_cnt, flags, cand_score, cand_idx, cand_slot, rec_score, rec_idx, rec_slot, cand_h;  // byte offsets
   size_t total_bytes;
 };
 
@@ -154,17 +162,18 @@ static inline GpWorkspace gp_workspace_layout(const acmil_gp_shape& s, const GpS
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
   const size_t K = s.n_branch, L = s.d_inner;
-  const size_t n_seg = t.n_seg, cap = t.n_masked_cap, rcap = t.rec_cap;
+  const size_t n_seg = t.n_seg, cap = t.n_masked_cap, rcap = t.rec_cap, rowcap = t.row_cap;
   const size_t ncb = (n_seg + t.cand_div - 1) / (t.cand_div > 0 ? t.cand_div : 1);
   w.part = take(n_seg * K * (L + 2) * 4);
   w.cand_cnt = take(ncb * K * 4);
+  w.flags = take(SMAX * 4);
   w.cand_score = take(ncb * K * cap * 4);
   w.cand_idx = take(ncb * K * cap * 4);
   w.cand_slot = take(ncb * K * cap * 4);
   w.rec_score = take(ncb * K * rcap * 4);
   w.rec_idx = take(ncb * K * rcap * 4);
-  w.cand_h = take(ncb * K * rcap * L * 4);
-  w.flags = take(256);
+  w.rec_slot = take(ncb * K * rcap * 4);
+  w.cand_h = take(ncb * rowcap * L * 4);
   w.total_bytes = o + 256;
   return w;
 }
@@ -205,10 +214,16 @@ struct GpMainParams {
   unsigned char* ws;      // workspace base
   GpWorkspace wl;
   GpSegTable seg;
+  // FFMA kernel as the rescue pass of the tcgen05 kernel: only the bags with rescue_flags[s] == 1 are processed
+  const int* rescue_flags;
 };
 
+// which bags a reduce launch handles, by the tcgen05 kernel's per-bag overflow flag
+enum { GP_REDUCE_ALL = 0, GP_REDUCE_UNFLAGGED = 1, GP_REDUCE_FLAGGED = 2 };
+
 int gp_launch_main_ffma(const GpMainParams& p, cudaStream_t st);
-int gp_launch_reduce(const GpMainParams& p, const GpRecord& rec, float* d_record, cudaStream_t st);
+int gp_launch_reduce(const GpMainParams& p, const GpRecord& rec, float* d_record, const int* d_flags, int flag_mode,
+                     cudaStream_t st);
 
 struct GpFinishParams {
   acmil_gp_shape sh;

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
   const int seg = blockIdx.x;
   int s = 0;
   while (seg >= p.seg.seg_begin[s + 1]) ++s;
+  if (p.rescue_flags != nullptr && p.rescue_flags[s] != 1) return;   // rescue pass: only the bags the tcgen05 kernel gave up on
   const int j = seg - p.seg.seg_begin[s];
   const int64_t row0_bag = p.seg.row_off[s];
   const int64_t n_rows = p.seg.row_off[s + 1] - row0_bag;
@@ -488,7 +489,7 @@ int gp_launch_main_ffma(const GpMainParams& p, cudaStream_t st) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_main_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, 16, st));
+  if (p.rescue_flags == nullptr) ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, SMAX * 4, st));
   gp_main_ffma_kernel<<<p.seg.n_seg, FT, smem, st>>>(p);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());

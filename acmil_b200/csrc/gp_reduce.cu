@@ -22,6 +22,8 @@ struct GpReduceParams {
   GpSegTable seg;
   GpRecord rec;
   float* record;  // [S][stride]
+  const int* flags;   // per-bag overflow flags of the tcgen05 kernel (or NULL)
+  int flag_mode;      // GP_REDUCE_*
 };
 
 // block-wide argmax of (score desc, idx asc); returns winner position (or -1) to every thread
@@ -80,8 +82,14 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
 
   const int L = p.sh.d_inner, K = p.sh.n_branch;
   const int k = blockIdx.x % K, s = blockIdx.x / K;
+  if (p.flag_mode != GP_REDUCE_ALL) {
+    const bool flagged = p.flags[s] == 1;      // the tcgen05 kernel ran out of parking slots on this bag
+    if (flagged != (p.flag_mode == GP_REDUCE_FLAGGED)) return;
+  }
   const int seg0 = p.seg.seg_begin[s], nseg = p.seg.seg_begin[s + 1] - seg0;
-  const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap, rcap = p.seg.rec_cap, cdiv = p.seg.cand_div;
+  const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap, cdiv = p.seg.cand_div;
+  const size_t rowcap = (size_t)p.seg.row_cap;
+  const int hoff = k * p.seg.h_branch_stride;      // first h slot of this branch inside a holder
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cb0 = seg0 / cdiv, ncb = nseg / cdiv;      // candidate holders of this bag
   const int ncand = ncb * nm;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
       const int sg = c / nm;
       const float w = expf(c_score[c] - mstar);
       if (lane == 0) ls += w;
-      const float* hr = g_h + (((size_t)(cb0 + sg) * K + k) * rcap + c_slot[c]) * L;
+      const float* hr = g_h + ((size_t)(cb0 + sg) * rowcap + hoff + c_slot[c]) * L;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int qd = lane + 32 * j;
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   for (int i = warp; i < nmc; i += RR / 32) {
     const bool on = i < nsel;
     const int c = on ? sel_pos[i] : 0;
-    const float* hr = on ? g_h + (((size_t)(cb0 + c / nm) * K + k) * rcap + c_slot[c]) * L : nullptr;
+    const float* hr = on ? g_h + ((size_t)(cb0 + c / nm) * rowcap + hoff + c_slot[c]) * L : nullptr;
     for (int jf = lane; jf < L; jf += 32) rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = on ? hr[jf] : 0.f;
     if (lane == 0) {
       rec[p.rec.score() + (size_t)k * nmc + i] = on ? c_score[c] : -INFINITY;
@@ -216,8 +224,9 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
     }
   }
   if (tid == 0) {
-    const int overflow = *reinterpret_cast<const int*>(p.ws + p.wl.flags);
-    rec[p.rec.m() + k] = overflow ? NAN : mstar;      // a holder ran out of parking slots: fail loudly
+    // an overflow flag that nobody rescues (GP_REDUCE_ALL with flags given) still fails loudly
+    const bool poisoned = p.flag_mode == GP_REDUCE_ALL && p.flags != nullptr && p.flags[s] == 1;
+    rec[p.rec.m() + k] = poisoned ? NAN : mstar;
     rec[p.rec.l() + k] = lstar;
     reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
   }
@@ -510,8 +519,11 @@ __global__ void __launch_bounds__(512) softmax_rows_kernel(const float* __restri
 
 }  // namespace
 
-int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_record, cudaStream_t st) {
+int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_record, const int* d_flags, int flag_mode,
+                     cudaStream_t st) {
   GpReduceParams p;
+  p.flags = d_flags;
+  p.flag_mode = d_flags ? flag_mode : GP_REDUCE_ALL;
   p.sh = mp.sh;
   p.ws = mp.ws;
   p.wl = mp.wl;

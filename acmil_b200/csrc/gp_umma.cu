@@ -47,8 +47,15 @@ constexpr float LOG2E = 1.4426950408889634f;
 #ifndef GP_UMMA_PROF
 #define GP_UMMA_PROF 0
 #endif
+// polling periods (ns) of the two service warps: they share their schedulers with epilogue warps
+#ifndef GP_MGR_SLEEP
+#define GP_MGR_SLEEP 400
+#endif
+#ifndef GP_SVC_SLEEP
+#define GP_SVC_SLEEP 2000
+#endif
 #if GP_UMMA_PROF
-__device__ long long g_umma_prof[148][32];
+__device__ long long g_umma_prof[148][88];      // 0-7 TMA, 8-15 MMA, 16-23 converter, 24 + 8 e: epilogue warp e
 #define PROF_T0() const long long _t0 = clock64()
 #define PROF_ADD(slot) prof[slot] += clock64() - _t0
 #define PROF_DECL() long long prof[16] = {0}
@@ -89,7 +96,7 @@ struct UmmaParams {
 //  * End of the bag: the manager catches up, records that are not in the final list are added back by the CTA, the
 //    n survivors go to the reduce kernel.
 // Which rows get parked depends on timing, so the summation order of the result does; the top-n set and the mask do not.
-constexpr int REC_CAP = 128;   // parked rows per (CTA, bag, branch)
+constexpr int REC_CAP = 256;   // records per (CTA, bag, branch) and parked h rows per (CTA, bag): one slot per ROW
 constexpr int CAND_KMAX = 6;   // masking on this kernel: K <= 6
 constexpr unsigned REC_EMPTY = 0xFFFFFFFFu;     // record score not written yet (a NaN pattern no score can have)
 struct CandShared {
@@ -97,6 +104,7 @@ struct CandShared {
   int lrec[CAND_KMAX][32];               // ... and their record indices
   unsigned active[CAND_KMAX][REC_CAP / 32];   // bag end: records that are still in the list
   int cnt[8];                            // live list entries
+  int rows;                              // h row slots handed out for this bag (may run past row_cap: overflow)
   int app[8];                            // records appended (may run past rec_cap: overflow)
   int seen[8];                           // records the manager has looked at
   float tau[8];                          // n-th best once the list is full, else -inf
@@ -164,15 +172,6 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = pack_half2(a - ah, b - bh);
 }
 
-// element k of a register array without dynamic indexing (k is warp-uniform)
-template <int KB>
-__device__ __forceinline__ int sel_k(const int (&a)[KB], int k) {
-  int r = a[0];
-#pragma unroll
-  for (int i = 1; i < KB; ++i) r = (k == i) ? a[i] : r;
-  return r;
-}
-
 template <int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -224,7 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     CandShared* cs0 = reinterpret_cast<CandShared*>(smem + sm.cand);
     if (tid < CAND_KMAX * 32) cs0->ls[tid >> 5][tid & 31] = INFINITY;
     if (tid < 8) { cs0->cnt[tid] = 0; cs0->app[tid] = 0; cs0->seen[tid] = 0; cs0->tau[tid] = -INFINITY; cs0->gtau[tid] = ~0ull; }
-    if (tid == 0) { cs0->cur_bag = -1; cs0->epoch = 0; cs0->flush_req = 0; cs0->flush_ack = 0; }
+    if (tid == 0) { cs0->cur_bag = -1; cs0->epoch = 0; cs0->flush_req = 0; cs0->flush_ack = 0; cs0->rows = 0; }
   }
   if (warp == 2) {
     tmem_alloc<2>(&bars->tmem_base, 512);
@@ -246,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
   // NOTE: each setmaxnreg sits at the top of a branch that never rejoins the others before the kernel's
   // tail, otherwise ptxas allocates the whole kernel for the smallest budget.
   if (warp < 4) {
-  setmaxnreg_dec<64>();
+  setmaxnreg_dec<80>();
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
@@ -363,6 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       const int cap = seg.n_masked_cap, rcap = seg.rec_cap;
       int dead_epoch = 0;       // lists of this epoch are final (or not booted yet): hands off
       while (true) {
+        bool busy = false;
         const int s = *reinterpret_cast<volatile int*>(&cs->cur_bag);
         if (s == -2) break;
         const int ep = *reinterpret_cast<volatile int*>(&cs->epoch);
@@ -374,6 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             int seen = cs->seen[k];
             const int app = min(*reinterpret_cast<volatile int*>(&cs->app[k]), rcap);
             if (seen >= app) continue;
+            busy = true;
             float mg_s = cs->ls[k][lane];
             int mg_rec = cs->lrec[k][lane], mg_cnt = cs->cnt[k];
             float mg_tau = -INFINITY;
@@ -413,7 +414,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             dead_epoch = ep;
           }
         }
-        __nanosleep(100);
+        // idle polls back off; a pending flush request or fresh records are served right away
+        if (!busy) __nanosleep(*reinterpret_cast<volatile int*>(&cs->flush_req) != dead_epoch ? 40 : GP_MGR_SLEEP);
       }
     }
   } else if (warp == 3) {
@@ -476,13 +478,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
               *reinterpret_cast<volatile unsigned long long*>(&cs->gtau[k]) = ((unsigned long long)(unsigned)s << 32) | __float_as_uint(tau);
           }
         }
-        __nanosleep(500);
+        __nanosleep(GP_SVC_SLEEP);
       }
     }
   }
   } else if (warp < 8) {
     // ===================================== converters: fp32 staging -> fp16 hi/lo in TMEM =====================================
-    setmaxnreg_dec<112>();
+    setmaxnreg_dec<96>();
     const int r = (warp - 4) * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
     uint32_t ctr = 0;
@@ -592,7 +594,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       if (nm > 0) {
         const float* rsc = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
         const int* rix = reinterpret_cast<const int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
-        const float* rh = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
+        const int* rsl = reinterpret_cast<const int*>(p.mp.ws + p.mp.wl.rec_slot) + (size_t)cb * K * rcap;
+        const float* rh = reinterpret_cast<const float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * seg.row_cap * L;
         asm volatile("bar.sync 1, 256;" ::: "memory");     // every warp is past the bag's last tile: no more appends
         if (e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->flush_req) = epoch_cur;
         while (*reinterpret_cast<volatile int*>(&cs->flush_ack) != epoch_cur) __nanosleep(50);     // manager caught up
@@ -615,28 +618,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             const bool live = lane < mg_cnt;
             g_score[k * cap + lane] = live ? mg_s : -INFINITY;
             g_idx[k * cap + lane] = live ? rix[(size_t)k * rcap + mg_rec] : 0x7fffffff;
-            g_slot[k * cap + lane] = live ? mg_rec : 0;
+            g_slot[k * cap + lane] = live ? rsl[(size_t)k * rcap + mg_rec] : 0;
           }
         }
         __threadfence_block();
         asm volatile("bar.sync 1, 256;" ::: "memory");     // active[] is published
-        // parked rows that did not stay in the CTA's top n rejoin the sums (every 8th record per warp)
+        // parked rows that did not stay in the CTA's top n rejoin the sums.  Warp w takes records w, w + 8, ...: lane i
+        // fetches score / h slot of record w + 8 i (one round trip for the whole list), the reference moves once, then
+        // the h rows are streamed two records at a time (32 independent loads in flight per thread)
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
           if (k < K) {
             const int app = min(cs->app[k], rcap);
-            for (int rec = e_idx; rec < app; rec += 8) {
-              if ((cs->active[k][rec >> 5] >> (rec & 31)) & 1u) continue;
-              const float sc = rsc[(size_t)k * rcap + rec];
-              if (sc > m_ref[k] + REF_SLACK) raise_ref(k, sc);
-              const float wgt = ex2_approx(fmaf(sc, LOG2E, c_ref[k]));
-              if (lane == 0) l_run[k] += wgt;
-              if (cp == (k >> 1)) {
-                const float* hrow = rh + ((size_t)k * rcap + rec) * L + rg;
+            const int rec = e_idx + 8 * lane;
+            const bool back = rec < app && !((cs->active[k][rec >> 5] >> (rec & 31)) & 1u);
+            const float sc = back ? rsc[(size_t)k * rcap + rec] : -INFINITY;
+            const int sl = back ? rsl[(size_t)k * rcap + rec] : 0;
+            unsigned todo = __ballot_sync(0xffffffffu, back);
+            if (todo) {
+              const float mx = warp_max(sc);
+              if (mx > m_ref[k] + REF_SLACK) raise_ref(k, mx);
+              const float wgt = back ? ex2_approx(fmaf(sc, LOG2E, c_ref[k])) : 0.f;
+              l_run[k] += wgt;       // per-lane partials; the lanes are folded below
+              while (todo) {
+                const int s0 = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int s1 = todo ? __ffs(todo) - 1 : s0;
+                const bool two = todo != 0u;
+                todo &= todo - 1;
+                const float w0 = __shfl_sync(0xffffffffu, wgt, s0), w1 = two ? __shfl_sync(0xffffffffu, wgt, s1) : 0.f;
+                const int q0 = __shfl_sync(0xffffffffu, sl, s0), q1 = __shfl_sync(0xffffffffu, sl, s1);
+                if (cp == (k >> 1)) {
+                  const float* h0 = rh + (size_t)q0 * L + rg;
+                  const float* h1 = rh + (size_t)q1 * L + rg;
+                  float v0[16], v1[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  acc[j][k & 1] = fmaf(wgt, hrow[16 * j], acc[j][k & 1]);
-                  acc[j][2 + (k & 1)] = fmaf(wgt, hrow[16 * j + 8], acc[j][2 + (k & 1)]);
+                  for (int j = 0; j < 16; ++j) { v0[j] = __ldcg(h0 + 8 * j); v1[j] = __ldcg(h1 + 8 * j); }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    acc[j][k & 1] = fmaf(w0, v0[2 * j], acc[j][k & 1]);
+                    acc[j][2 + (k & 1)] = fmaf(w0, v0[2 * j + 1], acc[j][2 + (k & 1)]);
+                    acc[j][k & 1] = fmaf(w1, v1[2 * j], acc[j][k & 1]);
+                    acc[j][2 + (k & 1)] = fmaf(w1, v1[2 * j + 1], acc[j][2 + (k & 1)]);
+                  }
                 }
               }
             }
@@ -646,6 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         if (e_idx < K) {
           cs->ls[e_idx][lane] = INFINITY;
           if (lane == 0) { cs->cnt[e_idx] = 0; cs->app[e_idx] = 0; cs->seen[e_idx] = 0; cs->tau[e_idx] = -INFINITY; }
+          if (e_idx == 0 && lane == 0) cs->rows = 0;
         }
       } else if (cap > 0 && e_idx == 0 && lane < K) {
         reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt)[(size_t)cb * K + lane] = 0;
@@ -859,14 +884,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       // ---------------- candidates: rows that beat the CTA's n-th best score are parked ----------------
       float pa[KB], pb[KB];
       unsigned ex_a = 0u, ex_b = 0u;       // bit k: row a / b of this row group is parked for branch k
-      int slot_a[KB], slot_b[KB];
-#pragma unroll
-      for (int k = 0; k < KB; ++k) slot_a[k] = slot_b[k] = 0;
+      int slot_a = 0, slot_b = 0;          // ... in this h row slot of the holder (one slot per parked row)
+      const int rowcap = seg.row_cap;
       if (KB <= CAND_KMAX && nm > 0 && boot) {
         // First tile of the bag in this CTA: every row would be a candidate, so instead of 8 warps queueing at the
         // locks, warp k picks the tile's top n of branch k in one go (descending order: exactly n insertions).
         float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
         int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+        int* rsl = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_slot) + (size_t)cb * K * rcap;
         float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)cb * K * cap;
         float* sc_all = reinterpret_cast<float*>(smem + sm.ps);                 // [8 warps][16 rows][8]
         unsigned char* bflag = smem + sm.tbuf;                                   // [128 rows][8]: 0 or record + 1
@@ -907,8 +932,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             }
             const unsigned best = __reduce_max_sync(0xffffffffu, key);
             if (best == 0u) break;
-            const int src = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
-            const int r = src + 32 * __shfl_sync(0xffffffffu, which, src);
+            // equal scores: the lower row wins, like torch.topk / the oracle (row = lane + 32 which)
+            const int r = (int)__reduce_min_sync(0xffffffffu, key == best ? (unsigned)(lane + 32 * which) : 0xffffu);
+            const int src = r & 31;
             if (lane == src) todo &= ~(1u << which);
             if (lane == it) { mg_s = ord_dec(best); mg_rec = it; }
             if (lane == 0) {
@@ -935,19 +961,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->epoch) = epoch_cur;     // lists are live
         {
-          const uint2 fa = *reinterpret_cast<const uint2*>(bflag + (lane_base + rg) * 8);
-          const uint2 fb = *reinterpret_cast<const uint2*>(bflag + (lane_base + rg + 8) * 8);
+          // lane (rg, cp = 0) speaks for row a, lane (rg, cp = 1) for row b: a selected row takes ONE h slot, which all
+          // its records (one per branch that selected it) point to; n rows per branch <= K n <= row_cap: cannot overflow
+          const uint2 f = *reinterpret_cast<const uint2*>(bflag + (lane_base + rg + 8 * (cp & 1)) * 8);
+          unsigned mine = 0u;
+          int myslot = 0;
+          if (cp < 2 && (f.x | f.y) != 0u) {
+            myslot = atomicAdd(&cs->rows, 1);
 #pragma unroll
-          for (int k = 0; k < KB; ++k) {
-            const unsigned va = ((k < 4 ? fa.x : fa.y) >> (8 * (k & 3))) & 0xffu;
-            const unsigned vb = ((k < 4 ? fb.x : fb.y) >> (8 * (k & 3))) & 0xffu;
-            if (va) { ex_a |= 1u << k; slot_a[k] = (int)va - 1; }
-            if (vb) { ex_b |= 1u << k; slot_b[k] = (int)vb - 1; }
+            for (int k = 0; k < KB; ++k) {
+              const unsigned v = ((k < 4 ? f.x : f.y) >> (8 * (k & 3))) & 0xffu;
+              if (v) { mine |= 1u << k; rsl[(size_t)k * rcap + (int)v - 1] = myslot; }
+            }
           }
+          ex_a = __shfl_sync(0xffffffffu, mine, lane & ~3);
+          ex_b = __shfl_sync(0xffffffffu, mine, (lane & ~3) | 1);
+          slot_a = __shfl_sync(0xffffffffu, myslot, lane & ~3);
+          slot_b = __shfl_sync(0xffffffffu, myslot, (lane & ~3) | 1);
         }
       } else if (nm > 0) {
         float* rsc = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.rec_score) + (size_t)cb * K * rcap;
         int* rix = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_idx) + (size_t)cb * K * rcap;
+        int* rsl = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.rec_slot) + (size_t)cb * K * rcap;
         unsigned* recs = reinterpret_cast<unsigned*>(smem + sm.tbuf + 1024);
         // lane (rg, cp = 0) speaks for row a, lane (rg, cp = 1) for row b of the row group
         const bool mine = (cp == 0 && valid_a) || (cp == 1 && valid_b);
@@ -963,28 +998,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           }
         }
         if (__any_sync(0xffffffffu, hits != 0u)) {
+          int myslot = 0;
+          if (hits != 0u) {
+            // one h slot per parked row, one record per (row, branch).  Out of slots / records: the bag is flagged and
+            // redone by the exact FFMA kernel (rescue launch); what this kernel computes for it no longer matters
+            myslot = atomicAdd(&cs->rows, 1);
+            if (myslot >= rowcap) {
+              reinterpret_cast<volatile int*>(p.mp.ws + p.mp.wl.flags)[s_cur] = 1;
+              hits = 0u;
+            }
 #pragma unroll
-          for (int k = 0; k < (KB <= CAND_KMAX ? KB : 0); ++k) {
-            const bool hit = (hits >> k) & 1u;
-            if (k < K && __any_sync(0xffffffffu, hit)) {
-              const float sv = cp == 0 ? sa[k] : sb[k];
-              int rec = -1;
-              if (hit) {
-                rec = atomicAdd(&cs->app[k], 1);
+            for (int k = 0; k < (KB <= CAND_KMAX ? KB : 0); ++k) {
+              if ((hits >> k) & 1u) {
+                const float sv = cp == 0 ? sa[k] : sb[k];
+                const int rec = atomicAdd(&cs->app[k], 1);
                 if (rec < rcap) {
                   rsc[(size_t)k * rcap + rec] = sv;
                   rix[(size_t)k * rcap + rec] = (int)(cp == 0 ? row_a : row_b);
+                  rsl[(size_t)k * rcap + rec] = myslot;
                   *reinterpret_cast<volatile unsigned*>(&recs[k * rcap + rec]) = __float_as_uint(sv);
-                } else {        // out of parking slots: poison the result (the reduce kernel writes NaN)
-                  atomicExch(reinterpret_cast<int*>(p.mp.ws + p.mp.wl.flags), 1);
-                  rec = -1;
+                } else {
+                  reinterpret_cast<volatile int*>(p.mp.ws + p.mp.wl.flags)[s_cur] = 1;
+                  hits &= ~(1u << k);
                 }
               }
-              const int ra = __shfl_sync(0xffffffffu, rec, lane & ~3), rb = __shfl_sync(0xffffffffu, rec, (lane & ~3) | 1);
-              if (ra >= 0) { ex_a |= 1u << k; slot_a[k] = ra; }
-              if (rb >= 0) { ex_b |= 1u << k; slot_b[k] = rb; }
             }
           }
+          ex_a = __shfl_sync(0xffffffffu, hits, lane & ~3);
+          ex_b = __shfl_sync(0xffffffffu, hits, (lane & ~3) | 1);
+          slot_a = __shfl_sync(0xffffffffu, myslot, lane & ~3);
+          slot_b = __shfl_sync(0xffffffffu, myslot, (lane & ~3) | 1);
         }
       }
       boot = false;
@@ -1041,24 +1084,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       // fragment layout movmatrix expects (thread (rg, cp): rows rg / rg + 8, feature pair 8i + 2cp), so a transpose is
       // one MOVM per 8x8 block and there is no shared-memory round trip.  fp32-faithful through the same hi/lo split as
       // the big GEMMs: h_hi p_hi + h_lo p_hi + h_hi p_lo.
-      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * K * rcap * L;
-      float* t0 = nullptr;
-      float* t1 = nullptr;
-      bool t0b = false, t1b = false;
-      unsigned rest_a = 0u, rest_b = 0u;
-      if (ex_a | ex_b) {
-#pragma unroll
-        for (int k = 0; k < KB; ++k) {
-          if ((ex_a >> k) & 1u) {
-            float* q = cand_h + ((size_t)k * rcap + slot_a[k]) * L;
-            if (t0 == nullptr) { t0 = q; t0b = false; } else if (t1 == nullptr) { t1 = q; t1b = false; } else rest_a |= 1u << k;
-          }
-          if ((ex_b >> k) & 1u) {
-            float* q = cand_h + ((size_t)k * rcap + slot_b[k]) * L;
-            if (t0 == nullptr) { t0 = q; t0b = true; } else if (t1 == nullptr) { t1 = q; t1b = true; } else rest_b |= 1u << k;
-          }
-        }
-      }
+      float* cand_h = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_h) + (size_t)cb * rowcap * L;
+      float* t0 = ex_a ? cand_h + (size_t)slot_a * L : nullptr;      // parked rows of this row group -> their h slots
+      float* t1 = ex_b ? cand_h + (size_t)slot_b * L : nullptr;
       __syncwarp();
       uint32_t bh[2], bl[2];      // B fragments: {p'[2cp][rg], p'[2cp+1][rg]}, {p'[2cp+8][rg], p'[2cp+9][rg]} as fp16 hi / lo
       {
@@ -1082,15 +1110,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
             const float2 blf = __half22float2(*reinterpret_cast<const __half2*>(&hl[2 * i + 1]));
             const float2 fa = make_float2(ah.x + al.x, ah.y + al.y), fb = make_float2(bhf.x + blf.x, bhf.y + blf.y);
             const int fcol = hf * 64 + i * 8 + cp * 2;
-            if (t0 != nullptr) *reinterpret_cast<float2*>(t0 + fcol) = t0b ? fb : fa;
-            if (t1 != nullptr) *reinterpret_cast<float2*>(t1 + fcol) = t1b ? fb : fa;
-            if (rest_a | rest_b) {   // a row group parked in more than two (row, branch) pairs: generic path
-#pragma unroll 1
-              for (int k = 0; k < K; ++k) {
-                if ((rest_a >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_a, k)) * L + fcol) = fa;
-                if ((rest_b >> k) & 1u) *reinterpret_cast<float2*>(cand_h + ((size_t)k * rcap + sel_k(slot_b, k)) * L + fcol) = fb;
-              }
-            }
+            if (t0 != nullptr) *reinterpret_cast<float2*>(t0 + fcol) = fa;
+            if (t1 != nullptr) *reinterpret_cast<float2*>(t1 + fcol) = fb;
           }
         }
 #pragma unroll
@@ -1119,7 +1140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     if (KB <= CAND_KMAX && e_idx == 0 && lane == 0) *reinterpret_cast<volatile int*>(&cs->cur_bag) = -2;     // stops the service warp
 #if GP_UMMA_PROF
     prof[7] = clock64() - t_start;
-    if (warp == 8 && lane == 0) PROF_FLUSH(24);
+    if (lane == 0) PROF_FLUSH(24 + 8 * e_idx);
 #endif
   }
 
@@ -1308,6 +1329,8 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
   t->n_masked_cap = cap;
   t->cand_div = 1;                      // one segment (and candidate holder) per CTA and bag
   t->rec_cap = cap > 0 ? REC_CAP : 0;
+  t->row_cap = cap > 0 ? REC_CAP : 0;   // one h slot per parked row, shared by the branches
+  t->h_branch_stride = 0;
   // segments: 2 per (cluster, bag) pair that intersects (one per CTA)
   int seg = 0;
   for (int s = 0; s < b.n_slides; ++s) {
@@ -1366,9 +1389,8 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
                 "tcgen05 kernel: masking with more than 6 branches is not supported (use ACMIL_IMPL_FFMA)");
   const size_t smem = smem_map(s.d_in, K == 1 ? 1 : (K <= 5 ? 5 : 8)).total + 1024;
   const int grid = p.seg.u_nclusters * 2;
-  ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, 16, st));
-  if (p.seg.n_masked_cap > 0)     // mirrored top-n lists: NaN = "not written in this launch" for the threshold service
-    ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.cand_score, 0xFF, p.wl.cand_idx - p.wl.cand_score, st));
+  if (p.seg.n_masked_cap > 0)     // one memset: per-bag overflow flags = -1 (clean), mirrored top-n lists = NaN
+    ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0xFF, p.wl.cand_idx - p.wl.flags, st));   // ("not written in this launch")
   if (K == 1) return launch_kb<1>(up, grid, smem, st);
   if (K <= 5) return launch_kb<5>(up, grid, smem, st);
   return launch_kb<8>(up, grid, smem, st);

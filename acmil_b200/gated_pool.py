@@ -136,8 +136,20 @@ class GatedPool:
             L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
                                          ws.numel(), _ptr(part), part.numel() * 4, st))
         ctx = dict(batch=batch, keepalive=(off, sb, x), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
-                   row_offsets=list(row_offsets))
+                   row_offsets=list(row_offsets), ws=ws, impl=impl if consts is not None else L.IMPL_FFMA)
         return part, ctx
+
+    def rescued_bags(self, ctx: dict) -> list:
+        """Diagnostics: per bag of the batch behind ``ctx``, 1 when the tcgen05 kernel's bounded candidate scratch ran out
+        (e.g. rows sorted by ascending score) and the exact FFMA kernel redid the bag on the device.  Synchronises."""
+        lib = L.load()
+        S = ctx["S"]
+        flags = (C.c_int32 * max(S, 1))()
+        with torch.cuda.device(ctx["dev"]):
+            st = C.c_void_p(torch.cuda.current_stream(ctx["dev"]).cuda_stream)
+            L.check(lib.acmil_gp_overflow_flags(C.byref(self._shape), C.byref(ctx["batch"]), ctx["impl"], _ptr(ctx["ws"]),
+                                                flags, st))
+        return [int(flags[i]) for i in range(S)]
 
     def finish(self, ctx: dict, records: torch.Tensor, n_ranks: int = 1, *, keep: Optional[Sequence[int]] = None,
                rsel: Optional[torch.Tensor] = None, branch_w=None, branch_b=None, head_w=None, head_b=None,

@@ -177,6 +177,12 @@ ACMIL_API int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* 
 ACMIL_API int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
                      const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes,
                      void* d_partial, size_t partial_bytes, void* stream);
+/* Diagnostics (synchronises `stream`): host_flags[s] = 1 for every bag of the LAST acmil_gp_partial call on this
+ * workspace that the tcgen05 kernel handed over to the exact FFMA kernel (its bounded scratch for rows that may be
+ * in a branch's top n ran out -- score orders such as "ascending along the rows").  The results are the same either
+ * way; this only tells how often the slow path ran. */
+ACMIL_API int acmil_gp_overflow_flags(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int impl,
+                                      const void* d_workspace, int32_t* host_flags, void* stream);
 /* 1 when ACMIL_IMPL_AUTO would pick the tcgen05 kernel for this shape (given valid consts). */
 ACMIL_API int acmil_gp_umma_supported(const acmil_gp_shape* shape);
 

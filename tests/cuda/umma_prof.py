@@ -17,11 +17,11 @@ for it in range(3):
     rec, ctx = op.partial(packed, x, off, n_masked=nmask)
 torch.cuda.synchronize()
 lib = L.load()
-buf = (C.c_longlong * (148 * 32))()
+buf = (C.c_longlong * (148 * 88))()
 lib.acmil_debug_umma_prof.argtypes = [C.POINTER(C.c_longlong), C.c_int]
-print("rc", lib.acmil_debug_umma_prof(buf, 148 * 32))
+print("rc", lib.acmil_debug_umma_prof(buf, 148 * 88))
 import numpy as np
-a = np.array(buf[:], dtype=np.int64).reshape(148, 32)
+a = np.array(buf[:], dtype=np.int64).reshape(148, 88)
 names = {0: "TMA wait_empty_x", 8: "MMA wait_w_ready", 9: "MMA idle: G1 blk d1_empty", 10: "MMA idle: G1 blk xop_full", 11: "MMA idle: G2 blk hop_full",
          12: "MMA idle: G2 blk d2_empty", 13: "MMA idle: G1 done", 14: "MMA idle: G2 done", 15: "MMA total", 16: "CVT wait_full_x", 17: "CVT wait_xop_empty", 23: "CVT total",
          24: "EPI wait_d1_full", 25: "EPI wait_d2_full", 26: "EPI epi1", 27: "EPI epi2(incl wait)", 28: "EPI softmax/cand",
@@ -31,3 +31,9 @@ for cta in (0, 1):
     print(f"--- cta rank {cta} (mean over {len(sel)} CTAs; tiles per CTA ~{S * 196 / 74:.1f})")
     for k, v in names.items():
         print(f"{v:28s} mean {sel[:, k].mean():12.0f}  max {sel[:, k].max():12.0f}")
+
+enames = ["wait_d1_full", "wait_d2_full", "epi1", "epi2(incl wait)", "softmax/cand", "pool", "flush", "total"]
+print("--- epilogue warps (mean over all CTAs), cycles per launch")
+print(" " * 18 + "".join(f"{'e' + str(e):>10s}" for e in range(8)))
+for i, nme in enumerate(enames):
+    print(f"{nme:18s}" + "".join(f"{a[:, 24 + 8 * e + i].mean():10.0f}" for e in range(8)))
