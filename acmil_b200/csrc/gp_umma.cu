@@ -25,29 +25,27 @@
 // Scratch in shared memory ("tbuf", 7 KB + "ps", 4 KB): per tile ps holds each warp's softmax numerators
 // [16 rows][8]; tbuf holds the first-tile selection flags [128][8] (bytes 0-1023) and the appended record
 // scores [K][rec_cap] (from byte 1024); at a bag's end both are reused as the 11 KB buffer of the 8-warp merge.
-#include <cuda.h>
-#include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
-#include "gp_common.cuh"
-#include "sm100.cuh"
+#include "gp_umma_shared.cuh"
 
 namespace {
 using namespace sm100;
+using namespace umma_shared;
 
 constexpr int UT = 512;
-constexpr int KC = 32;       // x columns per chunk (one 128-byte swizzle span of fp32)
-constexpr int NSTAGE = 3;    // fp32 staging ring (TMA destination)
 constexpr int NXOP = 4;      // TMEM x-operand ring
-constexpr int STAGE_BYTES = 128 * KC * 4;
 constexpr uint32_t TM_D1 = 0, TM_D2 = 128, TM_HHI = 256, TM_HLO = 320, TM_X = 384;
-constexpr float LOG2E = 1.4426950408889634f;
 
 #ifndef GP_UMMA_PROF
 #define GP_UMMA_PROF 0
 #endif
 // polling periods (ns) of the two service warps: they share their schedulers with epilogue warps
+#ifndef GP_EXP_IDLE_HS1
+#define GP_EXP_IDLE_HS1 0
+#endif
 #ifndef GP_MGR_SLEEP
 #define GP_MGR_SLEEP 400
 #endif
@@ -66,62 +64,6 @@ __device__ long long g_umma_prof[148][88];      // 0-7 TMA, 8-15 MMA, 16-23 conv
 #define PROF_DECL() do {} while (0)
 #define PROF_FLUSH(base) do {} while (0)
 #endif
-
-struct UmmaConsts {
-  float b1[128], bv[128], bu[128], ww[KMAX][128], bw[KMAX];
-  float inv_s1, inv_sv, inv_su;
-};
-
-struct UmmaParams {
-  GpMainParams mp;
-  UmmaConsts c;
-  CUtensorMap tmap;
-  const unsigned char* wimg;   // per-CTA weight images, cta_img_bytes each
-  uint32_t cta_img_bytes;
-  uint32_t w1_part_bytes;      // bytes of one (hi or lo) W1 half image
-};
-
-// Top-n tracking per CTA and bag (training-mode masking).  Rows that may belong to the bag's top n of a branch must stay
-// out of the softmax sums (the reference masks them before the softmax), so they are "parked": score / row index /
-// h row go to scratch records and rejoin the sums later unless they end up masked.  Nothing is ever subtracted.
-//  * Epilogue warps only APPEND: a row whose score beats tau = max(CTA's n-th best, bag-wide n-th best) takes the
-//    next record slot of its branch with one shared-memory atomicAdd and is parked.  No locks, no waiting; in the
-//    common case no row beats tau and the check costs a few instructions per branch.
-//  * Warp 2 is the list manager: it follows the appended records and keeps the CTA's top-n list of every branch
-//    (entry i <-> lane i), publishes the CTA's n-th best (tau) and mirrors the list to the workspace (cand_score).
-//  * Warp 3 keeps merging the mirrored lists of ALL CTAs that work on the current bag into gtau[k] = the bag-wide
-//    n-th best score seen so far by anybody (a lower bound of the final one).
-//  * The CTA's first tile of a bag has no threshold yet: there warp k selects the tile's top n of branch k directly
-//    (two CTA barriers, once per bag and CTA).
-//  * End of the bag: the manager catches up, records that are not in the final list are added back by the CTA, the
-//    n survivors go to the reduce kernel.
-// Which rows get parked depends on timing, so the summation order of the result does; the top-n set and the mask do not.
-constexpr int REC_CAP = 256;   // records per (CTA, bag, branch) and parked h rows per (CTA, bag): one slot per ROW
-constexpr int CAND_KMAX = 6;   // masking on this kernel: K <= 6
-constexpr unsigned REC_EMPTY = 0xFFFFFFFFu;     // record score not written yet (a NaN pattern no score can have)
-struct CandShared {
-  float ls[CAND_KMAX][32];               // list scores, +inf beyond cnt
-  int lrec[CAND_KMAX][32];               // ... and their record indices
-  unsigned active[CAND_KMAX][REC_CAP / 32];   // bag end: records that are still in the list
-  int cnt[8];                            // live list entries
-  int rows;                              // h row slots handed out for this bag (may run past row_cap: overflow)
-  int app[8];                            // records appended (may run past rec_cap: overflow)
-  int seen[8];                           // records the manager has looked at
-  float tau[8];                          // n-th best once the list is full, else -inf
-  unsigned long long gtau[8];            // bag << 32 | bits of the bag-wide n-th best so far (warp 3, one 8-byte store)
-  int cur_bag;                           // bag the epilogue is working on (-1: none yet, -2: kernel is finishing)
-  int epoch;                             // bumped when a bag's lists have been booted: the manager may work on them
-  int flush_req, flush_ack;              // epoch whose lists the epilogue wants final / the manager has finalised
-};
-
-// order-preserving float <-> uint (0 is below every float, +inf is below every NaN)
-__device__ __forceinline__ unsigned ord_enc(float f) {
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord_dec(unsigned u) {
-  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
-}
 
 // gate constants in smem, one record of 2 CREC floats per pair of adjacent units (2c, 2c+1), laid out as fp32 pairs
 // for the packed FFMA2 path: {ww[k][2c], ww[k][2c+1]} for k < KB, then the bv' pair and the bu' pair, where
@@ -153,24 +95,6 @@ struct Bars {
   uint64_t d1_full, d1_empty, hop_full, d2_full[2], d2_empty[2], wload, w_ready;
   uint32_t tmem_base;
 };
-
-// position of global pair-tile g: bag s, first row inside the bag for this CTA
-struct TilePos {
-  int s;
-  int64_t row_in_bag;
-};
-
-__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-  const __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// fp32 -> (fp16 hi, fp16 lo) with hi = top 11 significant bits (exact in fp16 for |v| in [2^-14, 65504])
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-  hi = pack_half2(ah, bh);
-  lo = pack_half2(a - ah, b - bh);
-}
 
 template <int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_kernel(const __grid_constant__ UmmaParams p) {
@@ -760,6 +684,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         { PROF_T0(); flush_stream(); PROF_ADD(6); }
         reset_stream(tp.s);
       }
+#if GP_EXP_IDLE_HS1
+      // timing experiment only (results are garbage): the second warp of every scheduler just keeps the barrier protocol
+      // alive, so that the phases of the first one run without a same-phase competitor
+      if (hs == 1) {
+        mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u);
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_cluster(&bars->hop_full, 0); mbar_arrive_cluster(&bars->d1_empty, 0); }
+        for (int qr = 0; qr < 4; ++qr) {
+          mbar_wait_cluster(&bars->d2_full[qr & 1], (uint32_t)(2 * t + (qr >> 1)) & 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&bars->d2_empty[qr & 1], 0);
+        }
+        continue;
+      }
+#endif
       const int64_t row_a = tp.row_in_bag + lane_base + rg, row_b = row_a + 8;
       const bool valid_a = row_a < n_rows, valid_b = row_b < n_rows;
 
@@ -1329,7 +1268,7 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
   t->n_masked_cap = cap;
   t->cand_div = 1;                      // one segment (and candidate holder) per CTA and bag
   t->rec_cap = cap > 0 ? REC_CAP : 0;
-  t->row_cap = cap > 0 ? REC_CAP : 0;   // one h slot per parked row, shared by the branches
+  t->row_cap = cap > 0 ? ROW_CAP : 0;   // one h slot per parked row, shared by the branches
   t->h_branch_stride = 0;
   // segments: 2 per (cluster, bag) pair that intersects (one per CTA)
   int seg = 0;
@@ -1366,6 +1305,10 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
   memcpy(up.c.bu, consts->bu, sizeof(up.c.bu));
   memcpy(up.c.ww, consts->ww, sizeof(up.c.ww));
   memcpy(up.c.bw, consts->bw, sizeof(up.c.bw));
+  for (int u = 0; u < 128; ++u) {
+    up.c.bvx[u] = consts->bv[u] * (-2.f * LOG2E);
+    up.c.bux[u] = consts->bu[u] * (-LOG2E);
+  }
   up.c.inv_s1 = consts->inv_scale[0];
   up.c.inv_sv = consts->inv_scale[1];
   up.c.inv_su = consts->inv_scale[2];
@@ -1391,6 +1334,12 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
   const int grid = p.seg.u_nclusters * 2;
   if (p.seg.n_masked_cap > 0)     // one memset: per-bag overflow flags = -1 (clean), mirrored top-n lists = NaN
     ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0xFF, p.wl.cand_idx - p.wl.flags, st));   // ("not written in this launch")
+  {
+    // ACMIL_GP_UMMA_VARIANT=3 selects the experimental two-tiles-in-flight kernel of gp_umma3.cu (parity-green, but
+    // measured slower than this file's kernel on B200: DESIGN.md section 3.1b); default 2 = the kernel below
+    static const int variant = [] { const char* e = getenv("ACMIL_GP_UMMA_VARIANT"); return e ? atoi(e) : 2; }();
+    if (variant == 3) return gp_launch_main_umma3(up, K, grid, st);
+  }
   if (K == 1) return launch_kb<1>(up, grid, smem, st);
   if (K <= 5) return launch_kb<5>(up, grid, smem, st);
   return launch_kb<8>(up, grid, smem, st);

@@ -85,3 +85,28 @@ if __name__ == "__main__":
     transmil_case("transmil_d64_n300", 46, 806, 1, 300, 96, 64, 2)
     transmil_case("transmil_d128_n1000", 47, 807, 1, 1000, 384, 128, 3)
     transmil_case("transmil_d64_b2_n50", 48, 808, 2, 50, 32, 64, 2)
+
+
+def transmil_seeded_case(name, model_seed, x_seed, n, d_feat, d_inner, n_class):
+    """Big cases: the weights are NOT stored (2.4 M parameters); the test rebuilds them with torch.manual_seed(model_seed)
+    through acmil_b200's TransMIL, whose constructor draws in the reference's order (checked here through a digest of
+    the reference module's state_dict).  Stored: logits, the seeds, sha256 of input and of the weights."""
+    import hashlib
+    torch.manual_seed(model_seed)
+    mod = ref_tm.TransMIL(Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class)).eval()
+    h = hashlib.sha256()
+    for k, v in mod.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().numpy().tobytes())
+    x = make_x(x_seed, (1, n, d_feat))
+    with torch.no_grad():
+        y = mod(x)
+    save(name, **meta(x, x_seed), out=y.numpy(), meta_cfg=np.array([d_feat, d_inner, n_class]),
+         meta_model_seed=model_seed, meta_w_sha=h.hexdigest())
+
+
+if __name__ == "__main__":
+    # SURVEY.md section 4, KAT4: TransMIL(512, 512, 2).eval() after torch.manual_seed(0), x = randn(1, 1000, 512), seed 1234
+    transmil_seeded_case("seeded_transmil_kat4_n1000", 0, 1234, 1000, 512, 512, 2)
+    # BASELINE.json configs[2] at its own size: N = 50 000, dim 512 -> 256 landmarks
+    transmil_seeded_case("seeded_transmil_c3_n50000", 5, 6, 50000, 512, 512, 2)

@@ -81,3 +81,28 @@ def test_torch_port_matches_reference(name):
     with torch.no_grad():
         y = T.transmil_forward(p, golden_x(meta)).numpy()
     np.testing.assert_allclose(y, meta["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", golden_names("seeded_transmil_"))
+def test_torch_port_matches_seeded_reference_fixtures(name):
+    """SURVEY KAT4 and BASELINE.json configs[2] at N = 50 000: reference logits with the weights given by seed (the
+    fixture stores a digest of the reference's state_dict; acmil_b200's constructor must draw the same values)."""
+    import hashlib
+    import torch
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    from oracle import torch_port as T
+    _, meta = load_golden(name)
+    d_feat, d_inner, n_class = (int(v) for v in meta["meta_cfg"])
+    torch.manual_seed(int(meta["meta_model_seed"]))
+    sd = TransMIL(Struct(D_feat=d_feat, D_inner=d_inner, n_class=n_class)).state_dict()
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().numpy().tobytes())
+    assert h.hexdigest() == str(meta["meta_w_sha"])
+    if int(meta["meta_x_shape"][1]) > 5000 and not bool(int(__import__("os").environ.get("ACMIL_SLOW_CPU_TESTS", "0"))):
+        pytest.skip("N = 50k on the CPU port takes ~10 s per run: set ACMIL_SLOW_CPU_TESTS=1 (the GPU suite checks it)")
+    with torch.no_grad():
+        y = T.transmil_forward({k: v for k, v in sd.items()}, golden_x(meta)).numpy()
+    np.testing.assert_allclose(y, meta["out"], rtol=1e-4, atol=1e-5)
