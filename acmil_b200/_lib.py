@@ -57,6 +57,16 @@ class GpOutputs(C.Structure):
         "d_sub", "d_slide", "d_afeat", "d_bag_feat", "d_lse_m", "d_lse_l", "d_topk_idx", "d_masked_idx")]
 
 
+MAX_PEERS = 16
+
+
+class GpExchange(C.Structure):
+    """acmil_gp_exchange (include/acmil_b200.h): peer-mapped gather buffers / flag words of every rank."""
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("d_gather", C.c_void_p * MAX_PEERS),
+                ("d_flags", C.c_void_p * MAX_PEERS), ("d_epoch", C.c_void_p), ("d_ticket", C.c_void_p),
+                ("gather_bytes", C.c_size_t)]
+
+
 class GemmDesc(C.Structure):
     """acmil_gemm_desc (include/acmil_transmil.h)."""
     _fields_ = ([(n, C.c_void_p) for n in ("a", "b", "c", "ct", "bias", "addend", "split_ws")]
@@ -109,6 +119,11 @@ SYMBOLS = {
     "acmil_gp_pack": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpWeights), C.c_void_p, C.c_size_t,
                                 C.POINTER(GpConsts), C.c_void_p]),
     "acmil_gp_umma_supported": (C.c_int, [C.POINTER(GpShape)]),
+    "acmil_gp_partial_x": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpConsts), C.POINTER(GpBatch), C.c_int,
+                                     C.c_void_p, C.c_size_t, C.POINTER(GpExchange), C.c_void_p]),
+    "acmil_gp_finish_x": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.POINTER(GpExchange), C.POINTER(C.c_int32),
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(GpHeads),
+                                    C.POINTER(GpOutputs), C.c_void_p]),
     "acmil_gp_sizes": (C.c_int, [C.POINTER(GpShape), C.POINTER(GpBatch), C.c_int, _SIZE_P, _SIZE_P]),
     "acmil_gp_partial": (C.c_int, [C.POINTER(GpShape), C.c_void_p, C.POINTER(GpConsts), C.POINTER(GpBatch), C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -23,6 +23,8 @@ void acmil_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+#define RT_FINISH_THREADS 256
+
 namespace {
 
 struct ProfState {
@@ -203,12 +205,32 @@ int acmil_gp_sizes(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int
   return ACMIL_OK;
 }
 
-int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
-                     const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes, void* d_partial,
-                     size_t partial_bytes, void* stream) {
+static int to_device_exchange(const acmil_gp_exchange* x, const GpRecord& rec, int n_slides, GpExchange* gx) {
+  ACMIL_REQUIRE(x->n_ranks >= 1 && x->n_ranks <= ACMIL_MAX_PEERS, ACMIL_E_INVALID, "exchange: n_ranks must be in [1, %d]",
+                ACMIL_MAX_PEERS);
+  ACMIL_REQUIRE(x->rank >= 0 && x->rank < x->n_ranks, ACMIL_E_INVALID, "exchange: bad rank");
+  ACMIL_REQUIRE(x->d_epoch && x->d_ticket, ACMIL_E_INVALID, "exchange: d_epoch / d_ticket is NULL");
+  ACMIL_REQUIRE(x->gather_bytes >= 2 * (size_t)x->n_ranks * rec.stride() * 4 * (size_t)n_slides, ACMIL_E_WORKSPACE,
+                "exchange: gather buffer too small");
+  memset(gx, 0, sizeof(*gx));
+  gx->n_ranks = x->n_ranks;
+  gx->rank = x->rank;
+  for (int r = 0; r < x->n_ranks; ++r) {
+    ACMIL_REQUIRE(x->d_gather[r] && x->d_flags[r], ACMIL_E_INVALID, "exchange: peer pointer %d is NULL", r);
+    gx->gather[r] = reinterpret_cast<float*>(x->d_gather[r]);
+    gx->flags[r] = x->d_flags[r];
+  }
+  gx->epoch = x->d_epoch;
+  gx->ticket = x->d_ticket;
+  return ACMIL_OK;
+}
+
+static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                             const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes,
+                             void* d_partial, size_t partial_bytes, const acmil_gp_exchange* x, void* stream) {
   if (int rc = check_shape(shape)) return rc;
   if (int rc = check_batch(batch)) return rc;
-  ACMIL_REQUIRE(d_packed && d_workspace && d_partial, ACMIL_E_INVALID, "NULL device buffer");
+  ACMIL_REQUIRE(d_packed && d_workspace && (d_partial || x), ACMIL_E_INVALID, "NULL device buffer");
   ACMIL_REQUIRE(batch->d_x != nullptr || batch->row_offsets[batch->n_slides] == 0, ACMIL_E_INVALID, "d_x is NULL");
   ACMIL_REQUIRE(batch->d_a_out == nullptr || batch->a_ld >= batch->row_offsets[batch->n_slides], ACMIL_E_INVALID,
                 "a_ld smaller than the number of rows");
@@ -226,8 +248,15 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
   const GpRecord rec = gp_record(*shape, batch->n_masked);
   ACMIL_REQUIRE(workspace_bytes >= p.wl.total_bytes, ACMIL_E_WORKSPACE, "workspace too small: %zu < %zu",
                 workspace_bytes, p.wl.total_bytes);
-  ACMIL_REQUIRE(partial_bytes >= rec.stride() * 4 * (size_t)batch->n_slides, ACMIL_E_WORKSPACE,
+  ACMIL_REQUIRE(x != nullptr || partial_bytes >= rec.stride() * 4 * (size_t)batch->n_slides, ACMIL_E_WORKSPACE,
                 "partial buffer too small");
+  GpExchange gx;
+  const bool rescue = use == ACMIL_IMPL_UMMA && batch->n_masked > 0;
+  if (x) {
+    if (int rc = to_device_exchange(x, rec, batch->n_slides, &gx)) return rc;
+    gx.reduce_ctas = batch->n_slides * shape->n_branch * (rescue ? 2 : 1);
+  }
+  const GpExchange* gxp = x ? &gx : nullptr;
   p.x = batch->d_x;
   p.a_out = batch->d_a_out;
   p.a_ld = batch->a_ld;
@@ -252,8 +281,7 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
                : gp_launch_main_ffma(p, st);
   if (rc) return rc;
   if (e1) ACMIL_CHECK_CUDA(cudaEventRecord(e1, st));
-  if (use != ACMIL_IMPL_UMMA || batch->n_masked == 0)
-    return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), nullptr, GP_REDUCE_ALL, st);
+  if (!rescue) return gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), nullptr, GP_REDUCE_ALL, gxp, st);
   // Training-mode masking on the tcgen05 kernel: a bag whose score order defeats the bounded parking scratch (e.g. rows
   // sorted by ascending score) is flagged per bag; the exact FFMA kernel redoes exactly those bags (its CTAs return at
   // once otherwise) and each reduce launch takes the bags of its side.  No host round trip, graph-capturable.
@@ -267,8 +295,23 @@ int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const ac
                 rescue_offset(p.wl.total_bytes) + q.wl.total_bytes);
   q.rescue_flags = d_flags;
   if ((rc = gp_launch_main_ffma(q, st))) return rc;
-  if ((rc = gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_UNFLAGGED, st))) return rc;
-  return gp_launch_reduce(q, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_FLAGGED, st);
+  if ((rc = gp_launch_reduce(p, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_UNFLAGGED, gxp, st))) return rc;
+  return gp_launch_reduce(q, rec, reinterpret_cast<float*>(d_partial), d_flags, GP_REDUCE_FLAGGED, gxp, st);
+}
+
+int acmil_gp_partial(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                     const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes, void* d_partial,
+                     size_t partial_bytes, void* stream) {
+  ACMIL_REQUIRE(d_partial != nullptr, ACMIL_E_INVALID, "d_partial is NULL");
+  return gp_partial_common(shape, d_packed, consts, batch, impl, d_workspace, workspace_bytes, d_partial, partial_bytes,
+                           nullptr, stream);
+}
+
+int acmil_gp_partial_x(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                       const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes,
+                       const acmil_gp_exchange* x, void* stream) {
+  ACMIL_REQUIRE(x != nullptr, ACMIL_E_INVALID, "exchange is NULL");
+  return gp_partial_common(shape, d_packed, consts, batch, impl, d_workspace, workspace_bytes, nullptr, 0, x, stream);
 }
 
 int acmil_gp_overflow_flags(const acmil_gp_shape* shape, const acmil_gp_batch* batch, int impl, const void* d_workspace,
@@ -293,10 +336,10 @@ int acmil_gp_overflow_flags(const acmil_gp_shape* shape, const acmil_gp_batch* b
 static int gp_finish_common(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,
                             size_t partial_bytes, int n_ranks, const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
                             const float* d_rand, int32_t rand_ld, const acmil_gp_heads* heads, const acmil_gp_outputs* out,
-                            void* stream) {
+                            void* stream, const acmil_gp_exchange* x = nullptr) {
   if (int rc = check_shape(shape)) return rc;
   if (int rc = check_batch(batch)) return rc;
-  ACMIL_REQUIRE(d_partials && heads && out, ACMIL_E_INVALID, "NULL argument");
+  ACMIL_REQUIRE((d_partials || x) && heads && out, ACMIL_E_INVALID, "NULL argument");
   ACMIL_REQUIRE(n_ranks >= 1 && n_ranks <= 64, ACMIL_E_INVALID, "n_ranks must be in [1, 64]");
   ACMIL_REQUIRE(heads->n_class >= 0 && heads->n_class <= ACMIL_MAX_CLASS, ACMIL_E_INVALID, "n_class must be <= %d",
                 ACMIL_MAX_CLASS);
@@ -305,8 +348,12 @@ static int gp_finish_common(const acmil_gp_shape* shape, const acmil_gp_batch* b
   memset(&p, 0, sizeof(p));
   p.sh = *shape;
   p.rec = gp_record(*shape, batch->n_masked);
-  ACMIL_REQUIRE(partial_bytes >= p.rec.stride() * 4 * (size_t)batch->n_slides * n_ranks, ACMIL_E_WORKSPACE,
+  ACMIL_REQUIRE(x != nullptr || partial_bytes >= p.rec.stride() * 4 * (size_t)batch->n_slides * n_ranks, ACMIL_E_WORKSPACE,
                 "partials buffer too small for %d ranks", n_ranks);
+  if (x) {
+    if (int rc = to_device_exchange(x, p.rec, batch->n_slides, &p.x)) return rc;
+    ACMIL_REQUIRE(n_ranks <= RT_FINISH_THREADS, ACMIL_E_INVALID, "exchange: too many ranks");
+  }
   p.records = reinterpret_cast<const float*>(d_partials);
   p.n_ranks = n_ranks;
   p.n_slides = batch->n_slides;
@@ -338,6 +385,15 @@ int acmil_gp_finish(const acmil_gp_shape* shape, const acmil_gp_batch* batch, co
                     size_t partial_bytes, int n_ranks, const int32_t* keep, const int64_t* d_rsel, int32_t keep_ld,
                     const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream) {
   return gp_finish_common(shape, batch, d_partials, partial_bytes, n_ranks, keep, d_rsel, keep_ld, nullptr, 0, heads, out, stream);
+}
+
+int acmil_gp_finish_x(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const acmil_gp_exchange* x,
+                      const int32_t* keep, const int64_t* d_rsel, const float* d_rand, int32_t rand_ld, int32_t keep_ld,
+                      const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream) {
+  ACMIL_REQUIRE(x != nullptr, ACMIL_E_INVALID, "exchange is NULL");
+  ACMIL_REQUIRE(!(d_rsel && d_rand), ACMIL_E_INVALID, "give d_rsel or d_rand, not both");
+  return gp_finish_common(shape, batch, nullptr, 0, x->n_ranks, keep, d_rsel, keep_ld, d_rand, d_rand ? rand_ld : 0, heads, out,
+                          stream, x);
 }
 
 int acmil_gp_finish_rand(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const void* d_partials,

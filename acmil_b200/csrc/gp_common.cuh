@@ -221,9 +221,19 @@ struct GpMainParams {
 // which bags a reduce launch handles, by the tcgen05 kernel's per-bag overflow flag
 enum { GP_REDUCE_ALL = 0, GP_REDUCE_UNFLAGGED = 1, GP_REDUCE_FLAGGED = 2 };
 
+// device-side view of acmil_gp_exchange (NULL-able: n_ranks == 0 means "no exchange, plain local record buffer")
+struct GpExchange {
+  int n_ranks, rank;
+  float* gather[ACMIL_MAX_PEERS];
+  uint32_t* flags[ACMIL_MAX_PEERS];
+  uint32_t* epoch;
+  unsigned* ticket;
+  int reduce_ctas;       // CTAs of all reduce launches of one step (the last one to finish publishes the flags)
+};
+
 int gp_launch_main_ffma(const GpMainParams& p, cudaStream_t st);
 int gp_launch_reduce(const GpMainParams& p, const GpRecord& rec, float* d_record, const int* d_flags, int flag_mode,
-                     cudaStream_t st);
+                     const GpExchange* x, cudaStream_t st);
 
 struct GpFinishParams {
   acmil_gp_shape sh;
@@ -243,6 +253,7 @@ struct GpFinishParams {
   int64_t shard_begin[SMAX];
   acmil_gp_heads heads;
   acmil_gp_outputs out;
+  GpExchange x;           // n_ranks > 0: records = x.gather[x.rank] (parity from *x.epoch), wait for the peers' flags
 };
 int gp_launch_finish(const GpFinishParams& p, cudaStream_t st);
 int gp_launch_stats(const float* d_a, int64_t a_ld, int K, const int64_t* row_offsets, int S, const float* d_m,

@@ -24,7 +24,34 @@ struct GpReduceParams {
   float* record;  // [S][stride]
   const int* flags;   // per-bag overflow flags of the tcgen05 kernel (or NULL)
   int flag_mode;      // GP_REDUCE_*
+  GpExchange x;       // n_ranks > 0: the record goes to every rank's gather buffer (NVLink stores) + flag handshake
 };
+
+// system-scope accesses for the flag handshake between GPUs
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// End of a reduce CTA when the exchange is fused in: every CTA of the step takes a ticket (also the ones that had
+// nothing to do); the last one knows that all records of this rank are written (each writer fenced at system scope
+// before its ticket) and raises this rank's flag on every peer.
+__device__ void exchange_publish(const GpExchange& x, uint32_t epoch) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(x.ticket, 1u);
+    if (t == (unsigned)x.reduce_ctas - 1u) {
+      *x.ticket = 0u;
+      __threadfence_system();
+      for (int r = 0; r < x.n_ranks; ++r) st_release_sys(x.flags[r] + x.rank, epoch + 1u);
+    }
+  }
+}
 
 // block-wide argmax of (score desc, idx asc); returns winner position (or -1) to every thread
 __device__ int block_argbest(float s, int i, int pos, float* r_s, int* r_i, int* r_p) {
@@ -82,9 +109,13 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
 
   const int L = p.sh.d_inner, K = p.sh.n_branch;
   const int k = blockIdx.x % K, s = blockIdx.x / K;
+  const uint32_t epoch = p.x.n_ranks > 0 ? *p.x.epoch : 0u;
   if (p.flag_mode != GP_REDUCE_ALL) {
     const bool flagged = p.flags[s] == 1;      // the tcgen05 kernel ran out of parking slots on this bag
-    if (flagged != (p.flag_mode == GP_REDUCE_FLAGGED)) return;
+    if (flagged != (p.flag_mode == GP_REDUCE_FLAGGED)) {
+      if (p.x.n_ranks > 0) exchange_publish(p.x, epoch);
+      return;
+    }
   }
   const int seg0 = p.seg.seg_begin[s], nseg = p.seg.seg_begin[s + 1] - seg0;
   const int nm = p.seg.nm[s], cap = p.seg.n_masked_cap, cdiv = p.seg.cand_div;
@@ -201,7 +232,10 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   }
   const float lstar = block_sum(ls, red);
 
-  float* rec = p.record + (size_t)s * p.rec.stride();
+  // with the exchange: this rank's slot of its own gather buffer, [parity][rank][bag]
+  float* rec = p.x.n_ranks > 0
+                   ? p.x.gather[p.x.rank] + (((size_t)(epoch & 1u) * p.x.n_ranks + p.x.rank) * p.seg.n_slides + s) * p.rec.stride()
+                   : p.record + (size_t)s * p.rec.stride();
   for (int qd = tid; qd < nq; qd += RR) {      // fixed-order sum over the 32 warps: deterministic
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int w = 0; w < RR / 32; ++w) {
@@ -230,6 +264,22 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
     rec[p.rec.l() + k] = lstar;
     reinterpret_cast<int*>(rec)[p.rec.cnt() + k] = nsel;
   }
+  if (p.x.n_ranks > 0) {
+    // branch k's pieces of the record -> the same slot of every peer's gather buffer, straight over NVLink
+    __syncthreads();      // (block scope: the pieces were written by this CTA)
+    const size_t off = rec - p.x.gather[p.x.rank];
+    const size_t piece[7][2] = {{p.rec.m() + k, 1}, {p.rec.l() + k, 1}, {p.rec.acc() + (size_t)k * L, (size_t)L},
+                                {p.rec.cnt() + k, 1}, {p.rec.score() + (size_t)k * nmc, (size_t)nmc},
+                                {p.rec.idx() + (size_t)k * nmc, (size_t)nmc}, {p.rec.h() + (size_t)k * nmc * L, (size_t)nmc * L}};
+    for (int r = 0; r < p.x.n_ranks; ++r) {
+      if (r == p.x.rank) continue;
+      float* dst = p.x.gather[r] + off;
+#pragma unroll
+      for (int q = 0; q < 7; ++q)
+        for (size_t i = tid; i < piece[q][1]; i += RR) dst[piece[q][0] + i] = rec[piece[q][0] + i];
+    }
+    exchange_publish(p.x, epoch);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -252,7 +302,19 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
   int* e_flag = e_idx + (size_t)K * ne;                 // 0 dead, 1 live, 2 top (unmasked), 3 masked
   int* top_pos = e_flag + (size_t)K * ne;               // [K][NMAX]
 
-  auto recp = [&](int r) { return p.records + ((size_t)r * p.n_slides + s) * stride; };
+  const float* records = p.records;
+  uint32_t epoch = 0u;
+  if (p.x.n_ranks > 0) {
+    // records pushed by the ranks' reduce kernels: wait until every source has published this step
+    epoch = *p.x.epoch;
+    if (tid < P) {
+      const uint32_t* f = p.x.flags[p.x.rank] + tid;
+      while (ld_acquire_sys(f) < epoch + 1u) __nanosleep(64);
+    }
+    __syncthreads();
+    records = p.x.gather[p.x.rank] + (size_t)(epoch & 1u) * P * p.n_slides * stride;
+  }
+  auto recp = [&](int r) { return records + ((size_t)r * p.n_slides + s) * stride; };
 
   const int keep = p.keep[s];
   // ---- 1. global top-n and the masked subset (one warp per branch) ----
@@ -420,6 +482,17 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
       if (lane == 0) p.out.d_slide[(size_t)s * C + c] = t + p.heads.d_bs[c];
     }
   }
+  if (p.x.n_ranks > 0) {      // the last CTA of the step moves this rank on to the next step (other parity)
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(p.x.ticket + 1, 1u);
+      if (t == gridDim.x - 1u) {
+        p.x.ticket[1] = 0u;
+        __threadfence();
+        *p.x.epoch = epoch + 1u;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -520,8 +593,10 @@ __global__ void __launch_bounds__(512) softmax_rows_kernel(const float* __restri
 }  // namespace
 
 int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_record, const int* d_flags, int flag_mode,
-                     cudaStream_t st) {
+                     const GpExchange* x, cudaStream_t st) {
   GpReduceParams p;
+  memset(&p.x, 0, sizeof(p.x));
+  if (x) p.x = *x;
   p.flags = d_flags;
   p.flag_mode = d_flags ? flag_mode : GP_REDUCE_ALL;
   p.sh = mp.sh;

@@ -108,9 +108,12 @@ class GatedPool:
 
     # ------------------------------------------------------------------ forward
     def partial(self, packed: torch.Tensor, x: torch.Tensor, row_offsets: Sequence[int], *, n_masked: int = 0,
-                want_scores: bool = True, shard_begin: Optional[Sequence[int]] = None, impl: Optional[int] = None):
+                want_scores: bool = True, shard_begin: Optional[Sequence[int]] = None, impl: Optional[int] = None,
+                exchange=None):
         """Row pass over this device's rows.  Returns (record, ctx): ``record`` is the flat fp32 partial
-        record (what sharded ranks all-gather), ``ctx`` carries the batch description for finish()."""
+        record (what sharded ranks all-gather), ``ctx`` carries the batch description for finish().
+        With ``exchange`` (a sharding.PeerExchange) the reduce kernel stores the records into every peer's gather buffer
+        over NVLink instead and ``record`` is None."""
         lib = L.load()
         sp = self.spec
         _require_cuda(x, "x")
@@ -129,14 +132,20 @@ class GatedPool:
         ws_b, part_b = C.c_size_t(0), C.c_size_t(0)
         L.check(lib.acmil_gp_sizes(C.byref(self._shape), C.byref(batch), impl, C.byref(ws_b), C.byref(part_b)))
         ws = self._buf("ws", ws_b.value, dev)
-        part = torch.empty(max(part_b.value, 4) // 4, dtype=torch.float32, device=dev)
+        part = None if exchange is not None else torch.empty(max(part_b.value, 4) // 4, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             consts = C.byref(self._consts) if (packed is self._packed and self._consts.valid) else None
-            L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
-                                         ws.numel(), _ptr(part), part.numel() * 4, st))
+            if exchange is not None:
+                xs = exchange.c_struct(part_b.value)
+                L.check(lib.acmil_gp_partial_x(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
+                                               ws.numel(), C.byref(xs), st))
+            else:
+                L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
+                                             ws.numel(), _ptr(part), part.numel() * 4, st))
         ctx = dict(batch=batch, keepalive=(off, sb, x), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
-                   row_offsets=list(row_offsets), ws=ws, impl=impl if consts is not None else L.IMPL_FFMA)
+                   row_offsets=list(row_offsets), ws=ws, impl=impl if consts is not None else L.IMPL_FFMA,
+                   exchange=exchange, partial_bytes=part_b.value)
         return part, ctx
 
     def rescued_bags(self, ctx: dict) -> list:
@@ -198,7 +207,11 @@ class GatedPool:
                            _ptr(topk), _ptr(masked))
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            if rand is not None:
+            if ctx.get("exchange") is not None:
+                xs = ctx["exchange"].c_struct(ctx["partial_bytes"])
+                L.check(lib.acmil_gp_finish_x(C.byref(self._shape), C.byref(ctx["batch"]), C.byref(xs), keep_arr, _ptr(rsel),
+                                              _ptr(rand), rand_ld, keep_ld, C.byref(heads), C.byref(outs), st))
+            elif rand is not None:
                 L.check(lib.acmil_gp_finish_rand(C.byref(self._shape), C.byref(ctx["batch"]), _ptr(records), records.numel() * 4,
                                                  int(n_ranks), keep_arr, _ptr(rand), rand_ld, keep_ld, C.byref(heads),
                                                  C.byref(outs), st))
@@ -215,13 +228,19 @@ class GatedPool:
             head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
             slide_head: bool = False, shared_head: bool = False, want_scores: bool = True,
             shard_begin: Optional[Sequence[int]] = None, group=None, impl: Optional[int] = None,
-            rand: Optional[torch.Tensor] = None) -> GatedPoolResult:
+            rand: Optional[torch.Tensor] = None, exchange=None) -> GatedPoolResult:
         """x: [R, d_in] fp32 CUDA, rows of S bags concatenated; row_offsets: S+1 host ints.
 
         With ``group`` (a torch.distributed process group) every rank passes its row shard of each bag and
         ``shard_begin`` (global index of its first row per bag); the per-bag partial records (a few KB)
         are all-gathered over NCCL and every rank finishes redundantly -- no other exchange.
         """
+        if exchange is not None:
+            # records travel inside the kernels (NVLink stores + flags): no collective, graph-capturable
+            _, ctx = self.partial(packed, x, row_offsets, n_masked=n_masked, want_scores=want_scores,
+                                  shard_begin=shard_begin, impl=impl, exchange=exchange)
+            return self.finish(ctx, None, exchange.world, keep=keep, rsel=rsel, branch_w=branch_w, branch_b=branch_b,
+                               head_w=head_w, head_b=head_b, slide_head=slide_head, shared_head=shared_head, rand=rand)
         part, ctx = self.partial(packed, x, row_offsets, n_masked=n_masked, want_scores=want_scores,
                                  shard_begin=shard_begin, impl=impl)
         from .sharding import gather_records

@@ -337,6 +337,50 @@ class ACMIL_GA(_GatedPoolModule):
         (res, diff), _ = self._run(x, use_attention_mask, False)
         return res.bag_feat if res is not None else diff[1]
 
+    @torch.no_grad()
+    def forward_bags(self, x_cat, row_offsets, *, shard_begin=None, n_total=None, exchange=None, group=None,
+                     want_scores=True, rand=None):
+        """Several bags in ONE launch (inference / the forward of a training step; no autograd): ``x_cat`` [R, D_feat] =
+        the rows of S bags back to back, ``row_offsets`` S + 1 host ints.  Returns (sub [S, K, C], slide [S, C],
+        scores [K, R] or None) -- bag s equals ``forward(x_cat[row_offsets[s]:row_offsets[s + 1]][None])``, including
+        the mask draw: one ``torch.rand(K, min(n_masked_patch, N_s))`` per bag, in bag order (transformer.py:316).
+
+        Sharded bags (each rank holds a contiguous run of rows of every bag): ``shard_begin[s]`` = global index of this
+        rank's first row of bag s, ``n_total[s]`` = rows of the whole bag, and either ``exchange`` (sharding.PeerExchange:
+        records travel inside the kernels over NVLink) or ``group`` (NCCL all-gather of the records).  Every rank must
+        mask the same patches: the draw of rank 0 is broadcast unless ``rand`` [S, K, n_masked_patch] is given."""
+        if not x_cat.is_cuda:
+            raise RuntimeError("acmil_b200 modules run on CUDA only")
+        S = len(row_offsets) - 1
+        sizes = [int(row_offsets[i + 1] - row_offsets[i]) for i in range(S)] if n_total is None else [int(v) for v in n_total]
+        use_mask = self.training and self.n_masked_patch > 0
+        n_masked, keep, rand = 0, [0] * S, None
+        if use_mask:
+            if self.n_masked_patch > L.MAX_MASKED:
+                raise ValueError(f"n_masked_patch > {L.MAX_MASKED} is not supported by the kernels")
+            k = self.attention.K
+            nm_max = min(self.n_masked_patch, max(sizes) if sizes else 0)
+            for i, n in enumerate(sizes):
+                keep[i] = int(min(self.n_masked_patch, n) * self.mask_drop)
+            if rand is None:
+                rand = torch.ones(S, k, max(nm_max, 1), device=x_cat.device)
+                for i, n in enumerate(sizes):      # the reference's draw, bag by bag (same generator stream)
+                    nm = min(self.n_masked_patch, n)
+                    rand[i, :, :nm] = torch.rand(k, nm, device=x_cat.device)
+                if shard_begin is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+                    torch.distributed.broadcast(rand, src=0)
+            n_masked = self.n_masked_patch if any(keep) else 0
+        w = self._weights()
+        op = self._op
+        packed = op.pack(w.get("w1"), w.get("b1"), w["wv"], w.get("bv"), w.get("wu"), w.get("bu"), w["ww"], w.get("bw"))
+        res = op.run(packed, x_cat.to(torch.float32).contiguous(), [int(v) for v in row_offsets], n_masked=n_masked, keep=keep,
+                     rand=rand if n_masked else None,
+                     branch_w=torch.stack([c.fc.weight for c in self.classifier]),
+                     branch_b=torch.stack([c.fc.bias for c in self.classifier]),
+                     head_w=self.Slide_classifier.fc.weight, head_b=self.Slide_classifier.fc.bias, slide_head=True,
+                     want_scores=want_scores, shard_begin=shard_begin, exchange=exchange, group=group)
+        return res.sub, res.slide, res.scores
+
 
 # --------------------------------------------------------------------------------------------
 def _xavier_like_reference(module):

@@ -50,6 +50,9 @@ def parse():
                     help="graph: the step (mask draw + row pass + reduce + finish) is captured once per bag group in a CUDA "
                          "graph and replayed (falls back to eager launches if capture fails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the stock-PyTorch-on-this-GPU comparator (N = 1 only)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-bag partial records travel: inside the kernels over peer memory, or NCCL")
     ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit", "resnet"],
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
     ap.add_argument("--dim", type=int, default=512, help="transmil: D_inner")
@@ -129,7 +132,7 @@ def run_reference(a):
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "slides/sec (ACMIL ga, N=50k, D=384)", "value": rate, "unit": "slides/s",
-        "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": sec * 1e3,
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, 1, cpu=True),
         "cpu_baseline": {"value": rate, "unit": "slides/s", "cores": cores, "kind": "port",
@@ -151,10 +154,40 @@ def workload_config(a, world, cpu=False):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def gpu_eager_rate(dev, n_rows, mode, steps=10, warmup=3):
+    """slides/sec of the reference's op sequence (oracle/torch_port.py: the same torch calls as transformer.py:305-330)
+    run by stock PyTorch ON THE B200, fp32 with TF32 off, device-resident bags, CUDA-event timed: what a user of the
+    reference gets on this GPU today (BASELINE.md section 4 / SURVEY.md section 8d)."""
+    from oracle import torch_port as T
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        p = {k: v.to(dev) for k, v in T.random_state(D_FEAT, D_INNER, 128, K_BRANCH, N_CLASS, seed=0).items()}
+        g = torch.Generator(device=dev).manual_seed(0)
+        xs = [torch.randn(1, n_rows, D_FEAT, generator=g, device=dev) for _ in range(3)]      # 3 x 76.8 MB > L2
+        with torch.no_grad():
+            for i in range(warmup):
+                T.acmil_ga_forward(p, xs[i % 3], mode == "train", N_MASKED, MASK_DROP)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                T.acmil_ga_forward(p, xs[i % 3], mode == "train", N_MASKED, MASK_DROP)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": 1e3 / ms, "unit": "slides/s", "ms_per_slide": ms, "kind": "stock PyTorch eager on this GPU, fp32 (TF32 off)",
+                "sample": f"{steps} bags of {n_rows}x{D_FEAT} fp32, device-resident, one bag per call, after {warmup} warm-ups "
+                          f"(oracle/torch_port.py = the reference's op sequence)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 def run_ours(a):
     import torch.distributed as dist
     from acmil_b200 import ACMIL_GA, Struct, _lib
-    from acmil_b200.sharding import shard_bounds
+    from acmil_b200.sharding import PeerExchange, ShardedACMIL, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,26 +226,47 @@ def run_ours(a):
     nm = min(N_MASKED, a.rows)
     keep = int(nm * MASK_DROP)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- the exchange of the sharded bags' partial records: inside the kernels over peer memory (NVLink stores + flags,
+    # include/acmil_b200.h acmil_gp_exchange), or -- if symmetric memory cannot be set up on this box -- an NCCL all-gather
+    exchange, exchange_kind = None, "none (1 GPU)"
+    if world > 1:
+        exchange_kind = "NCCL all_gather_into_tensor of the records (torch.distributed)"
+        if a.exchange == "peer":
+            try:
+                part_bytes = (2 * K_BRANCH + K_BRANCH * D_INNER + K_BRANCH + 2 * K_BRANCH * N_MASKED
+                              + K_BRANCH * N_MASKED * D_INNER) * 4 * S
+                exchange = PeerExchange(part_bytes, dev)
+                exchange_kind = ("in-kernel: the reduce kernel stores the records into every peer's buffer over NVLink and raises "
+                                 "a flag, the finish kernel waits for the flags (symmetric memory; no collective per step)")
+            except Exception as exc:      # no P2P / symmetric memory on this box
+                print(f"[rank {rank}] peer exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                exchange = None
+            ok = torch.tensor([1.0 if exchange is not None else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 0.5:
+                exchange = None
+
+    rng_in_sync = [world == 1]
+
     def step(i):
         r = None
         if masking:
-            # per bag: the draw of transformer.py:316; its argsort is taken inside acmil_gp_finish_rand.  Every rank seeds
-            # its generator identically (torch.manual_seed(0) above) and makes the same calls, so all ranks draw the same
-            # numbers without an exchange; `rng_in_sync` below checks that once and falls back to a broadcast otherwise.
+            # per bag: the draw of transformer.py:316; its argsort is taken inside the finish kernel.  Every rank seeds its
+            # generator identically (torch.manual_seed(0) above) and makes the same calls, so all ranks draw the same
+            # numbers without an exchange; `rng_in_sync` checks that once and falls back to a broadcast otherwise.
             r = torch.rand(S, K_BRANCH, nm, device=dev)
             if world > 1 and not rng_in_sync[0]:
                 dist.broadcast(r, src=0)
         return op.run(packed, groups[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
                       keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
                       head_w=head_w, head_b=head_b, slide_head=True, shard_begin=shard_begin if world > 1 else None,
-                      group=dist.group.WORLD if world > 1 else None)
+                      group=dist.group.WORLD if (world > 1 and exchange is None) else None, exchange=exchange)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    rng_in_sync = [world == 1]
     if world > 1:      # do the ranks' default CUDA generators agree?  (compare one probe draw with rank 0's)
         probe = torch.rand(64, device=dev)
         ref0 = probe.clone()
@@ -221,10 +275,42 @@ def run_ours(a):
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         rng_in_sync[0] = bool(same.item() > 0.5)
 
+    # ---- sharded-versus-unsharded parity on real hardware: the same seeded bags once row-sharded over the ranks (the
+    # path timed below) and once whole on every rank; logits within 1e-3, mask indices identical
+    parity = None
+    if world > 1:
+        with torch.no_grad():
+            Sc = min(S, 4)
+            gfull = torch.Generator(device=dev).manual_seed(99)
+            xfull = torch.randn(Sc * a.rows, D_FEAT, generator=gfull, device=dev)          # same on every rank
+            rnd = torch.rand(Sc, K_BRANCH, nm, generator=gfull, device=dev)
+            xloc = torch.cat([xfull[s * a.rows + b[rank]: s * a.rows + b[rank + 1]] for s in range(Sc)])
+            kw = dict(n_masked=N_MASKED if masking else 0, keep=[keep if masking else 0] * Sc, rand=rnd if masking else None,
+                      branch_w=branch_w, branch_b=branch_b, head_w=head_w, head_b=head_b, slide_head=True)
+            whole = op.run(packed, xfull, [i * a.rows for i in range(Sc + 1)], **kw)
+            # the parity step uses its own (smaller) batch; a PeerExchange is sized for the timed batch, which is larger
+            shard = op.run(packed, xloc, [i * n_loc for i in range(Sc + 1)], shard_begin=[b[rank]] * Sc,
+                           group=dist.group.WORLD if exchange is None else None, exchange=exchange, **kw)
+            err = float(((shard.slide - whole.slide).abs() / (whole.slide.abs() + 1e-5)).max())
+            err = max(err, float(((shard.sub - whole.sub).abs() / (whole.sub.abs() + 1e-5)).max()))
+            mask_ok = True
+            if masking:
+                mask_ok = bool(torch.equal(torch.sort(shard.masked_idx, -1).values, torch.sort(whole.masked_idx, -1).values))
+            loc = torch.cat([whole.scores[:, s * a.rows + b[rank]: s * a.rows + b[rank + 1]] for s in range(Sc)], dim=1)
+            sc_err = float(((shard.scores - loc).abs() / (loc.abs() + 1e-5)).clamp(max=1.0).max())
+            t = torch.tensor([err, sc_err, 0.0 if mask_ok else 1.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            parity = {"parity_ok": bool(t[0] < 1e-3 and t[1] < 1e-3 and t[2] == 0), "logits_max_rel_err": float(t[0]),
+                      "scores_max_rel_err": float(t[1]), "mask_indices_identical": bool(t[2] == 0), "bags": Sc,
+                      "what": "row-sharded over the ranks (this run's exchange) versus the whole bags on one GPU, same seeds"}
+
     with torch.no_grad():
-        # multi-GPU: NCCL opens its channels lazily over the first collectives of each size, so a few more untimed steps
-        n_warm = max(a.warmup, 3) + (8 if world > 1 else 0)
-        for i in range(n_warm):
+        # NCCL opens its channels lazily over the first collectives of each size (peer-memory exchange: none): a few
+        # untimed communication pre-warm steps, reported separately from the W warm-up steps the command line asked for
+        comm_prewarm = 8 if (world > 1 and exchange is None) else 0
+        for i in range(comm_prewarm):
+            step(i)
+        for i in range(a.warmup):
             step(i)
         barrier()
         l0 = _lib.launch_count()
@@ -232,10 +318,11 @@ def run_ours(a):
         torch.cuda.synchronize()
         launches_per_step = _lib.launch_count() - l0
 
-        # the step is launch-bound next to its 0.27 ms row pass (9 small launches): capture it once per bag group
+        # the step is launch-bound next to its row pass (small reduce / finish launches): capture it once per bag group.
+        # With the in-kernel exchange a multi-GPU step is plain kernel launches too and is captured the same way.
         graphs, graph_res, launch_mode = None, None, "eager"
-        if a.launch == "graph" and world > 1 and os.environ.get("ACMIL_BENCH_NCCL_GRAPH", "0") != "1":
-            launch_mode = "eager (the step holds NCCL collectives; graph replay is used at 1 GPU only)"
+        if a.launch == "graph" and world > 1 and exchange is None and os.environ.get("ACMIL_BENCH_NCCL_GRAPH", "0") != "1":
+            launch_mode = "eager (the step holds NCCL collectives; graph replay needs the peer-memory exchange)"
         elif a.launch == "graph":
             try:
                 side = torch.cuda.Stream()
@@ -252,6 +339,7 @@ def run_ours(a):
                         r = step(gi)
                     graphs.append(g)
                     graph_res.append(r)
+                barrier()
                 for gi in range(a.groups):
                     graphs[gi].replay()
                 barrier()
@@ -266,7 +354,8 @@ def run_ours(a):
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
-        for i in range(3):      # the GPU idled while the clock sampler started: back to steady state before the timed region
+        settle = 3
+        for i in range(settle):      # the GPU idled while the clock sampler started: back to steady state before the timed region
             if graphs is None:
                 step(i)
             else:
@@ -303,78 +392,94 @@ def run_ours(a):
             ms = float(t.item())
         checksum = float(res.slide.sum().item())
 
-        # ---- end to end: pinned host bag -> H2D -> module forward (the call a user makes) -> logits D2H ----
+        # ---- end to end: pinned host bags -> H2D -> the public batched forward (the call a user makes) -> logits D2H ----
         e2e = None
         if a.e2e_steps > 0:
-            host = [torch.randn(n_loc, D_FEAT).pin_memory() for _ in range(2)]
-            shard = None
-            if world > 1:
-                from acmil_b200.sharding import ShardedACMIL
-                shard = ShardedACMIL(model, dist.group.WORLD)
+            Se = a.slides                      # bags per call (each sharded over the ranks at world > 1)
+            shard = ShardedACMIL(model, dist.group.WORLD if world > 1 else None, exchange) if world > 1 else None
+            e_off = [i * n_loc for i in range(Se + 1)]
+            e_tot, e_beg = [a.rows] * Se, [b[rank]] * Se
+            if exchange is not None:
+                pass      # (sized for S >= Se bags per step)
 
-            def head_call(xd):
-                if shard is None:
-                    _, slide, _ = model(xd)
-                else:
-                    _, slide, _ = shard(xd, a.rows, b[rank])
-                return slide
-
-            n_e2e = a.e2e_steps * a.slides
-
-            def timed_loop(host_bufs, dtype):
-                """n_e2e bags, each: H2D from pinned memory -> module forward -> logits .cpu().  A double-buffered feeder
-                (copy stream + events) lets the copy of bag i + 1 overlap the forward and the read-back of bag i."""
-                xb = [torch.empty(1, n_loc, D_FEAT, device=dev, dtype=dtype) for _ in range(2)]
+            def timed_loop(host_bufs, dtype, calls):
+                """`calls` calls of Se bags each: H2D of the call's bags from pinned memory -> forward_bags -> logits to the
+                host.  A double-buffered feeder (copy stream + events) lets the copy of call i + 1 overlap the kernels and
+                the read-back of call i; every call's logits are on the host before the next-but-one call starts."""
+                xb = [torch.empty(Se * n_loc, D_FEAT, device=dev, dtype=dtype) for _ in range(2)]
                 cstream = torch.cuda.Stream(device=dev)
                 ready = [torch.cuda.Event() for _ in range(2)]
                 free = [torch.cuda.Event() for _ in range(2)]
+                out_host = [torch.empty(Se, N_CLASS).pin_memory() for _ in range(2)]
+                done = [torch.cuda.Event() for _ in range(2)]
 
                 def issue(i):
                     k = i % 2
                     with torch.cuda.stream(cstream):
                         cstream.wait_event(free[k])                 # the forward that read this buffer has finished
-                        xb[k][0].copy_(host_bufs[k], non_blocking=True)
+                        xb[k].copy_(host_bufs[k], non_blocking=True)
                         ready[k].record(cstream)
 
                 def loop(n):
                     issue(0)
-                    out = None
+                    last = None
                     for i in range(n):
                         k = i % 2
                         if i + 1 < n:
                             issue(i + 1)
                         torch.cuda.current_stream().wait_event(ready[k])
-                        slide = head_call(xb[k])
+                        rnd = torch.rand(Se, K_BRANCH, nm, device=dev) if (masking and world > 1 and rng_in_sync[0]) else None
+                        if shard is None:
+                            _, slide, _ = model.forward_bags(xb[k], e_off, want_scores=False)
+                        else:
+                            _, slide, _ = model.forward_bags(xb[k], e_off, shard_begin=e_beg, n_total=e_tot, exchange=exchange,
+                                                             group=dist.group.WORLD if exchange is None else None,
+                                                             want_scores=False, rand=rnd)
                         free[k].record()
-                        out = slide.cpu()                           # per-bag result on the host (synchronises this bag)
-                    return out
+                        if i >= 2:
+                            done[k].synchronize()                   # logits of call i - 2 are on the host
+                        out_host[k].copy_(slide, non_blocking=True)
+                        done[k].record()
+                        last = k
+                    torch.cuda.synchronize()
+                    return out_host[last]
 
                 loop(2)
                 barrier()
                 t0 = time.perf_counter()
-                loop(n_e2e)
+                loop(calls)
                 barrier()
                 return time.perf_counter() - t0
 
-            dt = timed_loop(host, torch.float32)
+            host = [torch.randn(Se * n_loc, D_FEAT).pin_memory() for _ in range(2)]
+            calls = a.e2e_steps
+            dt = timed_loop(host, torch.float32, calls)
             if world > 1:
                 t = torch.tensor([dt], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
+            n_e2e = calls * Se
             # the same call fed with fp16 features, the dtype the reference stores them in (Step2_feature_extract.py:165;
             # Step3_WSI_classification_ACMIL.py:193 casts after the copy): half the PCIe bytes, cast on the device
             fp16 = None
             if world == 1:
-                dt16 = timed_loop([h.half().pin_memory() for h in host], torch.float16)
-                fp16 = {"value": n_e2e / dt16, "unit": "slides/s", "h2d_bytes_per_step": a.slides * n_loc * D_FEAT * 2,
+                dt16 = timed_loop([h.half().pin_memory() for h in host], torch.float16, calls)
+                fp16 = {"value": n_e2e / dt16, "unit": "slides/s", "h2d_bytes_per_step": Se * n_loc * D_FEAT * 2,
                         "note": "fp16 features in pinned host memory (the H5 storage dtype), cast to fp32 on the device"}
-            # at world > 1 one bag (sharded) per call; n_e2e bags in total
             e2e = {"value": n_e2e / dt, "unit": "slides/s", "fp16_features": fp16,
-                   "h2d_bytes_per_step": a.slides * n_loc * D_FEAT * 4 * world,
-                   "d2h_bytes_per_step": a.slides * N_CLASS * 4 * world,
-                   "api": "ACMIL_GA.forward(x[1,N,D]) per bag: pinned host -> device copy (double-buffered feeder on a copy stream), "
-                          "fused kernels, logits .cpu() per bag",
-                   "bags": n_e2e}
+                   "h2d_bytes_per_step": Se * n_loc * D_FEAT * 4 * world,
+                   "d2h_bytes_per_step": Se * N_CLASS * 4 * world,
+                   "api": f"ACMIL_GA.forward_bags(x_cat, row_offsets): {Se} bags per call (sharded over the ranks at N > 1): pinned "
+                          "host -> device copy (double-buffered feeder on a copy stream), fused kernels, logits copied to pinned "
+                          "host memory per call",
+                   "bags": n_e2e, "bags_per_call": Se}
+
+    eager = None
+    if rank == 0 and world == 1 and not a.no_gpu_eager:
+        try:
+            eager = gpu_eager_rate(dev, a.rows, a.mode)
+        except Exception as exc:      # never let the comparator take the bench line down
+            eager = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
@@ -402,7 +507,7 @@ def run_ours(a):
         pass
     line = {
         "metric": "slides/sec (ACMIL ga, N=50k, D=384)", "value": value, "unit": "slides/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3) + (8 if world > 1 else 0), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -410,10 +515,18 @@ def run_ours(a):
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps), "launch": launch_mode,
+        "untimed_extra_steps": {"comm_prewarm_steps": comm_prewarm, "settle_steps_after_clock_sampler_start": settle,
+                                "note": "outside --warmup and outside the timed region"},
+        "exchange": exchange_kind,
         "mask_draw": "identical generator state on every rank (checked), no exchange" if (world > 1 and rng_in_sync[0]) else
                      ("broadcast from rank 0" if world > 1 else "local"),
         "kernel_impl": a.kernel, "checksum": checksum,
     }
+    if parity is not None:
+        line["parity"] = parity
+        line["parity_ok"] = parity["parity_ok"]
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
     if not a.no_cpu_baseline:
         rate, sec = cpu_port_rate(a.rows, 6, 2, a.mode)
         line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",

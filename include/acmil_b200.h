@@ -186,6 +186,38 @@ ACMIL_API int acmil_gp_overflow_flags(const acmil_gp_shape* shape, const acmil_g
 /* 1 when ACMIL_IMPL_AUTO would pick the tcgen05 kernel for this shape (given valid consts). */
 ACMIL_API int acmil_gp_umma_supported(const acmil_gp_shape* shape);
 
+/* ---- bag sharding over the GPUs of one box: the exchange fused into the kernels ------------------------------
+ * Instead of all-gathering the partial records with NCCL, the reduce kernel of acmil_gp_partial_x stores this rank's
+ * records straight into every peer's gather buffer over NVLink (peer-mapped pointers, e.g. from
+ * torch.distributed._symmetric_memory) and then raises a per-source flag on every peer; the finish kernel of
+ * acmil_gp_finish_x waits for the n_ranks flags in-kernel.  No host synchronisation, no collective launch: the whole
+ * step is plain kernel launches and can be captured in a CUDA graph.
+ *   gather buffer of one rank: [2 parities][n_ranks][n_slides][record]  (step e uses parity e & 1: double-buffered, a
+ *   rank can run at most one step ahead of its peers because its finish waits for their flags)
+ *   flags of one rank: n_ranks words, flag[src] = number of steps src has published
+ * Both live in caller-owned memory that every peer has mapped; d_epoch / d_ticket are LOCAL device words, all zero
+ * before the first step (d_ticket: 4 words).  Every acmil_gp_partial_x must be followed by one acmil_gp_finish_x on the
+ * same stream (it advances d_epoch). */
+#define ACMIL_MAX_PEERS 16
+typedef struct acmil_gp_exchange {
+  int32_t n_ranks, rank;
+  void* d_gather[ACMIL_MAX_PEERS];      /* gather buffer of rank r as mapped into THIS process ([rank] is the local one) */
+  uint32_t* d_flags[ACMIL_MAX_PEERS];   /* flag words of rank r, mapped likewise */
+  uint32_t* d_epoch;                    /* local: steps completed on this rank */
+  uint32_t* d_ticket;                   /* local scratch: 4 words */
+  size_t gather_bytes;                  /* bytes of ONE rank's gather buffer (>= 2 * n_ranks * partial_bytes) */
+} acmil_gp_exchange;
+
+/* acmil_gp_partial with the exchange fused in (d_partial is implied: the local gather buffer of `x`). */
+ACMIL_API int acmil_gp_partial_x(const acmil_gp_shape* shape, const void* d_packed, const acmil_gp_consts* consts,
+                                 const acmil_gp_batch* batch, int impl, void* d_workspace, size_t workspace_bytes,
+                                 const acmil_gp_exchange* x, void* stream);
+/* acmil_gp_finish / acmil_gp_finish_rand over the records pushed by every rank's acmil_gp_partial_x (exactly one of
+ * d_rsel / d_rand when masking is on). */
+ACMIL_API int acmil_gp_finish_x(const acmil_gp_shape* shape, const acmil_gp_batch* batch, const acmil_gp_exchange* x,
+                                const int32_t* keep, const int64_t* d_rsel, const float* d_rand, int32_t rand_ld,
+                                int32_t keep_ld, const acmil_gp_heads* heads, const acmil_gp_outputs* out, void* stream);
+
 /* Merges n_ranks partial records (d_partials = n_ranks records back to back, as produced by an
  * all-gather; n_ranks == 1 for a single GPU), picks the global top-n per branch, masks
  * d_rsel-selected ones (rsel[S, K, keep] = argsort(rand)[:, :keep] drawn by the caller with

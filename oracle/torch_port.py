@@ -22,10 +22,10 @@ def acmil_ga_forward(p: dict, x: torch.Tensor, training: bool = False, n_masked_
         k, n = a.shape
         nm = min(n_masked_patch, n)
         _, idx = torch.topk(a, nm, dim=-1)
-        r = torch.rand(*idx.shape) if rand is None else rand
+        r = torch.rand(*idx.shape) if rand is None else rand                                     # :316 (drawn on the host)
         rsel = torch.argsort(r, dim=-1)[:, :int(nm * mask_drop)]
-        masked = idx[torch.arange(k).unsqueeze(-1), rsel]
-        keep = torch.ones(k, n)
+        masked = idx[torch.arange(k).unsqueeze(-1), rsel.to(idx.device)]
+        keep = torch.ones(k, n).to(a.device)                                                     # :318
         keep.scatter_(-1, masked, 0)
         a = a.masked_fill(keep == 0, -1e9)
     a_out = a

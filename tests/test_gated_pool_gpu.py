@@ -457,3 +457,73 @@ def test_sorted_bag_does_not_nan(order):
         assert rescued[0] == 1, "expected the bounded scratch to overflow on this order (is the test still adversarial?)"
     if order in ("descending", "random", "equal"):
         assert rescued[0] == 0
+
+
+class _LocalExchange:
+    """acmil_gp_exchange whose "peers" are buffers of the same GPU: the in-kernel exchange protocol (records stored into
+    every rank's gather buffer, per-source flags, epoch parity) exercised without a second device.  Same interface as
+    acmil_b200.sharding.PeerExchange."""
+
+    def __init__(self, world, rank, bufs, capacity):
+        self.world, self.rank, self.bufs, self.capacity = world, rank, bufs, capacity
+        self.state = torch.zeros(8, dtype=torch.int32, device="cuda")
+
+    def c_struct(self, partial_bytes):
+        import acmil_b200._lib as L
+        assert partial_bytes <= self.capacity
+        x = L.GpExchange()
+        x.n_ranks, x.rank = self.world, self.rank
+        for r, b in enumerate(self.bufs):
+            x.d_flags[r] = b.data_ptr()
+            x.d_gather[r] = b.data_ptr() + 256
+        x.d_epoch = self.state.data_ptr()
+        x.d_ticket = self.state.data_ptr() + 16
+        x.gather_bytes = 2 * self.world * self.capacity
+        return x
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("ranks", [1, 2, 8])
+def test_in_kernel_exchange_matches_unsharded(ranks, impl):
+    """The fused exchange (acmil_gp_partial_x / acmil_gp_finish_x): every "rank" pushes its records into all gather
+    buffers and raises its flag, every rank's finish kernel waits for the flags and must reproduce the unsharded result,
+    masks included -- over three consecutive steps (both parities of the double-buffered gather area, epoch advance)."""
+    m = _random_acmil(13, scale_ww=10.0).cuda().train()
+    m._op.impl = impl
+    sizes = [6007, 3001]
+    g = torch.Generator().manual_seed(21)
+    w = m._weights()
+    op = m._op
+    packed = op.pack(w.get("w1"), None, w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
+    branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
+    head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
+    capacity = (2 * 5 + 5 * 128 + 5 + 2 * 5 * 10 + 5 * 10 * 128) * 4 * len(sizes)
+    bufs = [torch.zeros((256 + 2 * ranks * capacity) // 4, device="cuda") for _ in range(ranks)]
+    xch = [_LocalExchange(ranks, r, bufs, capacity) for r in range(ranks)]
+    off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    for step in range(3):
+        x = torch.randn(sum(sizes), 384, generator=g).cuda()
+        rand = torch.rand(len(sizes), 5, 10, generator=g).cuda()
+        kw = dict(n_masked=10, keep=[6, 6], rand=rand, branch_w=branch[0], branch_b=branch[1], head_w=head[0], head_b=head[1],
+                  slide_head=True)
+        with torch.no_grad():
+            full = op.run(packed, x, off, **kw)
+            ctxs, locs = [], []
+            for r in range(ranks):      # all pushes first (one stream: a finish would wait for flags nobody raised yet)
+                b = [[n * q // ranks for q in range(ranks + 1)] for n in sizes]
+                xs = torch.cat([x[off[s] + b[s][r]: off[s] + b[s][r + 1]] for s in range(len(sizes))])
+                lo = np.concatenate([[0], np.cumsum([b[s][r + 1] - b[s][r] for s in range(len(sizes))])]).tolist()
+                _, ctx = op.partial(packed, xs, lo, n_masked=10, shard_begin=[b[s][r] for s in range(len(sizes))], exchange=xch[r])
+                ctxs.append(ctx)
+                locs.append((b, lo))
+            fkw = {k: v for k, v in kw.items() if k != "n_masked"}
+            outs = [op.finish(ctxs[r], None, ranks, **fkw) for r in range(ranks)]
+        for r, o in enumerate(outs):
+            assert torch.equal(o.masked_idx.sort(-1).values, full.masked_idx.sort(-1).values), (step, r)
+            close(o.sub, full.sub.cpu().numpy(), rtol=2e-5, atol=1e-6)
+            close(o.slide, full.slide.cpu().numpy(), rtol=2e-5, atol=1e-6)
+            b, lo = locs[r]
+            for s in range(len(sizes)):
+                close(o.scores[:, lo[s]:lo[s + 1]], full.scores[:, off[s] + b[s][r]: off[s] + b[s][r + 1]].cpu().numpy(),
+                      rtol=1e-6, atol=1e-7)
+        assert all(int(xc.state[0]) == step + 1 for xc in xch)      # every rank's epoch advanced once per step
