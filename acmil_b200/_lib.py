@@ -19,6 +19,14 @@ IMPL_AUTO, IMPL_FFMA, IMPL_UMMA = 0, 1, 2
 ACT_IDS = {"tanh": ACT_TANH, "relu": ACT_RELU, "gelu": ACT_GELU}
 
 
+def record_floats(n_branch: int, d_inner: int, n_masked: int) -> int:
+    """4-byte units of one bag's partial record (GpRecord in csrc/gp_common.cuh: m, l, acc, cnt, score, idx, h; every
+    section padded to a multiple of 4).  acmil_gp_sizes reports the same number times n_slides times 4 as partial_bytes."""
+    pad4 = lambda n: (n + 3) & ~3  # noqa: E731
+    k, l, nmc = n_branch, d_inner, max(n_masked, 0)
+    return pad4(k) * 3 + pad4(k * l) + 2 * pad4(k * nmc) + pad4(k * nmc * l)
+
+
 class AcmilError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"acmil_b200 error {code}: {msg}")

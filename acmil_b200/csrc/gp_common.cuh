@@ -182,17 +182,20 @@ static inline GpWorkspace gp_workspace_layout(const acmil_gp_shape& s, const GpS
 // One record per bag, all 4-byte units (ints stored bit-exact in the same buffer so that one
 // all-gather moves everything):
 //   m[K] l[K] acc[K][L] cnt[K](int) score[K][nmc] idx[K][nmc](int, global row in bag) h[K][nmc][L]
+// (each section padded to a multiple of 4 units)
 // with nmc = n_masked requested (fixed per call so that every rank agrees on the stride).
 struct GpRecord {
   int K, L, nmc;
+  // every section starts on a 16-byte boundary (float4 loads of the acc / h rows in the finish kernel)
+  static __host__ __device__ size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
   __host__ __device__ size_t m() const { return 0; }
-  __host__ __device__ size_t l() const { return (size_t)K; }
-  __host__ __device__ size_t acc() const { return (size_t)2 * K; }
-  __host__ __device__ size_t cnt() const { return acc() + (size_t)K * L; }
-  __host__ __device__ size_t score() const { return cnt() + K; }
-  __host__ __device__ size_t idx() const { return score() + (size_t)K * nmc; }
-  __host__ __device__ size_t h() const { return idx() + (size_t)K * nmc; }
-  __host__ __device__ size_t stride() const { return h() + (size_t)K * nmc * L; }
+  __host__ __device__ size_t l() const { return pad4((size_t)K); }
+  __host__ __device__ size_t acc() const { return l() + pad4((size_t)K); }
+  __host__ __device__ size_t cnt() const { return acc() + pad4((size_t)K * L); }
+  __host__ __device__ size_t score() const { return cnt() + pad4((size_t)K); }
+  __host__ __device__ size_t idx() const { return score() + pad4((size_t)K * nmc); }
+  __host__ __device__ size_t h() const { return idx() + pad4((size_t)K * nmc); }
+  __host__ __device__ size_t stride() const { return h() + pad4((size_t)K * nmc * L); }
 };
 
 static inline GpRecord gp_record(const acmil_gp_shape& s, int n_masked) {

@@ -119,11 +119,13 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
 
-  // ---- which segment ----
-  const int seg = blockIdx.x;
+  // ---- which segments: blockIdx.x, blockIdx.x + gridDim.x, ... (one each unless this is a rescue pass, which is launched
+  // with a small grid because it normally has nothing to do) ----
   int s = 0;
+  for (int seg = blockIdx.x; seg < p.seg.n_seg; seg += gridDim.x) {
   while (seg >= p.seg.seg_begin[s + 1]) ++s;
-  if (p.rescue_flags != nullptr && p.rescue_flags[s] != 1) return;   // rescue pass: only the bags the tcgen05 kernel gave up on
+  if (p.rescue_flags != nullptr && p.rescue_flags[s] != 1) continue;   // rescue pass: only the bags the tcgen05 kernel gave up on
+  __syncthreads();      // (the previous segment's last reads of shared memory are done)
   const int j = seg - p.seg.seg_begin[s];
   const int64_t row0_bag = p.seg.row_off[s];
   const int64_t n_rows = p.seg.row_off[s + 1] - row0_bag;
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
     int* g_cnt = reinterpret_cast<int*>(p.ws + p.wl.cand_cnt) + (size_t)seg * K;
     if (tid < K) g_cnt[tid] = 0;
   }
+  }      // segments of this CTA
 }
 
 }  // namespace
@@ -490,7 +493,13 @@ int gp_launch_main_ffma(const GpMainParams& p, cudaStream_t st) {
     configured = smem;
   }
   if (p.rescue_flags == nullptr) ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0, SMAX * 4, st));
-  gp_main_ffma_kernel<<<p.seg.n_seg, FT, smem, st>>>(p);
+  int grid = p.seg.n_seg;
+  if (p.rescue_flags != nullptr) {      // rescue pass: one resident wave is plenty (CTAs loop over the segments)
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (grid > sms) grid = sms;
+  }
+  gp_main_ffma_kernel<<<grid, FT, smem, st>>>(p);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;

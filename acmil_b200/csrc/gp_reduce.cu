@@ -13,6 +13,14 @@
 namespace {
 
 constexpr int RT = 256;
+#ifndef GP_EXP_NO_SYSFENCE
+#define GP_EXP_NO_SYSFENCE 0      // timing experiment: device-scope fences in the exchange (NOT correct across GPUs)
+#endif
+#if GP_EXP_NO_SYSFENCE
+#define GP_SYS_FENCE() __threadfence()
+#else
+#define GP_SYS_FENCE() __threadfence_system()
+#endif
 constexpr float MASK_FILL = -1e9f;
 
 struct GpReduceParams {
@@ -36,19 +44,27 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // End of a reduce CTA when the exchange is fused in: every CTA of the step takes a ticket (also the ones that had
 // nothing to do); the last one knows that all records of this rank are written (each writer fenced at system scope
 // before its ticket) and raises this rank's flag on every peer.
-__device__ void exchange_publish(const GpExchange& x, uint32_t epoch) {
-  __threadfence_system();
-  __syncthreads();
+__device__ void exchange_publish(const GpExchange& x, uint32_t epoch, bool wrote) {
+  __syncthreads();      // the CTA's stores happen-before thread 0's fence (one system-scope fence per CTA, not per thread)
   if (threadIdx.x == 0) {
+    if (wrote) GP_SYS_FENCE();
     const unsigned t = atomicAdd(x.ticket, 1u);
     if (t == (unsigned)x.reduce_ctas - 1u) {
       *x.ticket = 0u;
-      __threadfence_system();
-      for (int r = 0; r < x.n_ranks; ++r) st_release_sys(x.flags[r] + x.rank, epoch + 1u);
+      GP_SYS_FENCE();      // ONE system-scope fence orders every record store of this rank before the flags
+      for (int r = 0; r < x.n_ranks; ++r) st_relaxed_sys(x.flags[r] + x.rank, epoch + 1u);
     }
   }
 }
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   if (p.flag_mode != GP_REDUCE_ALL) {
     const bool flagged = p.flags[s] == 1;      // the tcgen05 kernel ran out of parking slots on this bag
     if (flagged != (p.flag_mode == GP_REDUCE_FLAGGED)) {
-      if (p.x.n_ranks > 0) exchange_publish(p.x, epoch);
+      if (p.x.n_ranks > 0) exchange_publish(p.x, epoch, false);
       return;
     }
   }
@@ -208,20 +224,29 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   nsel = s_nsel;
 
   // ---- 3. candidates that were not selected rejoin the sums ----
-  for (int c = warp; c < ncand; c += RR / 32) {
-    if (c_slot[c] >= 0 && !c_sel[c]) {
-      const int sg = c / nm;
-      const float w = expf(c_score[c] - mstar);
-      if (lane == 0) ls += w;
-      const float* hr = g_h + ((size_t)(cb0 + sg) * rowcap + hoff + c_slot[c]) * L;
+  // (two candidates per round with all their loads in flight together: the rows sit in L2 at best)
+  for (int c0 = warp; c0 < ncand; c0 += 2 * (RR / 32)) {
+    float wv[2];
+    float4 uv[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int c = c0 + t * (RR / 32);
+      const bool on = c < ncand && c_slot[c] >= 0 && !c_sel[c];
+      wv[t] = on ? expf(c_score[c] - mstar) : 0.f;
+      const float* hr = g_h + ((size_t)(cb0 + (on ? c / nm : 0)) * rowcap + hoff + (on ? c_slot[c] : 0)) * L;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int qd = lane + 32 * j;
-        if (qd < nq) {
-          const float4 u = *reinterpret_cast<const float4*>(hr + qd * 4);
-          a4[j].x = fmaf(w, u.x, a4[j].x); a4[j].y = fmaf(w, u.y, a4[j].y);
-          a4[j].z = fmaf(w, u.z, a4[j].z); a4[j].w = fmaf(w, u.w, a4[j].w);
-        }
+        uv[t][j] = (on && qd < nq) ? __ldcg(reinterpret_cast<const float4*>(hr + qd * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (lane == 0) ls += wv[t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a4[j].x = fmaf(wv[t], uv[t][j].x, a4[j].x); a4[j].y = fmaf(wv[t], uv[t][j].y, a4[j].y);
+        a4[j].z = fmaf(wv[t], uv[t][j].z, a4[j].z); a4[j].w = fmaf(wv[t], uv[t][j].w, a4[j].w);
       }
     }
   }
@@ -271,45 +296,63 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
     const size_t piece[7][2] = {{p.rec.m() + k, 1}, {p.rec.l() + k, 1}, {p.rec.acc() + (size_t)k * L, (size_t)L},
                                 {p.rec.cnt() + k, 1}, {p.rec.score() + (size_t)k * nmc, (size_t)nmc},
                                 {p.rec.idx() + (size_t)k * nmc, (size_t)nmc}, {p.rec.h() + (size_t)k * nmc * L, (size_t)nmc * L}};
-    for (int r = 0; r < p.x.n_ranks; ++r) {
-      if (r == p.x.rank) continue;
-      float* dst = p.x.gather[r] + off;
+    // every thread reads its share of the pieces once (independent loads), then stores it to all peers
+    constexpr int VMAX = 12;
+    for (size_t base = 0;; base += (size_t)VMAX * RR) {      // (one round unless n_masked * d_inner is very large)
+      float v[VMAX];
+      size_t at[VMAX];
+      int n = 0;
+      size_t seen = 0;
 #pragma unroll
-      for (int q = 0; q < 7; ++q)
-        for (size_t i = tid; i < piece[q][1]; i += RR) dst[piece[q][0] + i] = rec[piece[q][0] + i];
+      for (int q = 0; q < 7; ++q) {
+        for (size_t i = tid; i < piece[q][1]; i += RR) {
+          const size_t ord = seen + i / RR;      // position of this element in the thread's own sequence
+          if (ord >= base / RR && n < VMAX) { at[n] = piece[q][0] + i; ++n; }
+        }
+        seen += (piece[q][1] + RR - 1) / RR;
+      }
+      for (int j = 0; j < n; ++j) v[j] = __ldcg(rec + at[j]);
+      for (int r = 0; r < p.x.n_ranks; ++r) {
+        if (r == p.x.rank) continue;
+        float* dst = p.x.gather[r] + off;
+        for (int j = 0; j < n; ++j) dst[at[j]] = v[j];
+      }
+      if (seen * RR <= base + (size_t)VMAX * RR) break;
     }
-    exchange_publish(p.x, epoch);
+    exchange_publish(p.x, epoch, true);
   }
 }
 
 // ------------------------------------------------------------------------------------------
+// One CTA per (bag, branch): warp 0 forms the global top-n / masked set and the softmax normalisers of its branch (short,
+// serial), then all 8 warps stream the rank partials and the candidate rows (the bulk of the bytes: n_ranks * n_masked
+// rows of d_inner floats per branch) in a fixed assignment, so the result does not depend on timing.  The bag feature and
+// the slide head need all branches: gp_heads_kernel, launched right behind.
 __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ GpFinishParams p) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ float red[RT / 32];
-  __shared__ float s_m[KMAX], s_l[KMAX];
-  __shared__ int s_ntop[KMAX];
+  __shared__ float s_m, s_l;
 
   const int L = p.sh.d_inner, K = p.sh.n_branch, P = p.n_ranks, nmc = p.rec.nmc;
-  const int s = blockIdx.x;
+  const int s = blockIdx.x / K, k = blockIdx.x % K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t stride = p.rec.stride();
-  const int ne = P * nmc;  // candidate entries per branch (dense, holes = -inf)
+  const int ne = P * nmc;  // candidate entries of this branch (dense, holes = -inf)
 
-  float* af = reinterpret_cast<float*>(dsm);            // [K][L]
-  float* bag = af + (size_t)K * L;                      // [L]
-  float* e_score = bag + L;                             // [K][ne]
-  int* e_idx = reinterpret_cast<int*>(e_score + (size_t)K * ne);
-  int* e_flag = e_idx + (size_t)K * ne;                 // 0 dead, 1 live, 2 top (unmasked), 3 masked
-  int* top_pos = e_flag + (size_t)K * ne;               // [K][NMAX]
+  float4* wpart = reinterpret_cast<float4*>(dsm);                         // [8 warps][L / 4]
+  float* af = reinterpret_cast<float*>(wpart + (size_t)(RT / 32) * (L / 4));   // [L]
+  float* e_score = af + L;                                                 // [ne]
+  int* e_idx = reinterpret_cast<int*>(e_score + ne);
+  int* e_flag = e_idx + ne;                 // 0 dead, 1 live, 2 top (unmasked), 3 masked
+  int* top_pos = e_flag + ne;               // [NMAX]
 
   const float* records = p.records;
-  uint32_t epoch = 0u;
   if (p.x.n_ranks > 0) {
     // records pushed by the ranks' reduce kernels: wait until every source has published this step
-    epoch = *p.x.epoch;
+    const uint32_t epoch = *p.x.epoch;
     if (tid < P) {
       const uint32_t* f = p.x.flags[p.x.rank] + tid;
-      while (ld_acquire_sys(f) < epoch + 1u) __nanosleep(64);
+      while (ld_relaxed_sys(f) < epoch + 1u) __nanosleep(64);
+      GP_SYS_FENCE();      // acquire side: the records behind the flag are visible to the loads below
     }
     __syncthreads();
     records = p.x.gather[p.x.rank] + (size_t)(epoch & 1u) * P * p.n_slides * stride;
@@ -317,28 +360,28 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
   auto recp = [&](int r) { return records + ((size_t)r * p.n_slides + s) * stride; };
 
   const int keep = p.keep[s];
-  // ---- 1. global top-n and the masked subset (one warp per branch) ----
-  for (int k = warp; k < K; k += RT / 32) {
+  // ---- 1. global top-n and the masked subset; m*, l* (warp 0; the entries are loaded by everybody) ----
+  for (int e = tid; e < ne; e += RT) {
+    const int r = e / nmc, i = e % nmc;
+    const float* rc = recp(r);
+    const int cnt = reinterpret_cast<const int*>(rc)[p.rec.cnt() + k];
+    const bool ok = i < cnt;
+    e_score[e] = ok ? rc[p.rec.score() + (size_t)k * nmc + i] : -INFINITY;
+    e_idx[e] = ok ? reinterpret_cast<const int*>(rc)[p.rec.idx() + (size_t)k * nmc + i] : 0x7fffffff;
+    e_flag[e] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
     int live = 0;
-    for (int e = lane; e < ne; e += 32) {
-      const int r = e / nmc, i = e % nmc;
-      const float* rc = recp(r);
-      const int cnt = reinterpret_cast<const int*>(rc)[p.rec.cnt() + k];
-      const bool ok = i < cnt;
-      e_score[k * ne + e] = ok ? rc[p.rec.score() + (size_t)k * nmc + i] : -INFINITY;
-      e_idx[k * ne + e] = ok ? reinterpret_cast<const int*>(rc)[p.rec.idx() + (size_t)k * nmc + i] : 0x7fffffff;
-      e_flag[k * ne + e] = ok ? 1 : 0;
-      live += ok ? 1 : 0;
-    }
+    for (int e = lane; e < ne; e += 32) live += e_flag[e];
     live = (int)(warp_sum((float)live) + 0.5f);
     const int ntop = min(p.n_masked, live);
-    __syncwarp();
     for (int round = 0; round < ntop; ++round) {
       float bs = -INFINITY;
       int bi = 0x7fffffff, bp = -1;
       for (int e = lane; e < ne; e += 32) {
-        if (e_flag[k * ne + e] == 1 && (bp < 0 || cand_better(e_score[k * ne + e], e_idx[k * ne + e], bs, bi))) {
-          bs = e_score[k * ne + e]; bi = e_idx[k * ne + e]; bp = e;
+        if (e_flag[e] == 1 && (bp < 0 || cand_better(e_score[e], e_idx[e], bs, bi))) {
+          bs = e_score[e]; bi = e_idx[e]; bp = e;
         }
       }
 #pragma unroll
@@ -349,21 +392,20 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
         if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
       }
       if (lane == 0) {
-        top_pos[k * NMAX + round] = bp;
-        e_flag[k * ne + bp] = 2;
+        top_pos[round] = bp;
+        e_flag[bp] = 2;
         if (p.out.d_topk_idx) p.out.d_topk_idx[((size_t)s * K + k) * p.n_masked + round] = bi;
       }
       __syncwarp();
     }
     if (p.out.d_topk_idx)
       for (int i = ntop + lane; i < p.n_masked; i += 32) p.out.d_topk_idx[((size_t)s * K + k) * p.n_masked + i] = -1;
-    if (lane == 0) s_ntop[k] = ntop;
     __syncwarp();
     auto mask_one = [&](int i, int64_t sel) {      // the i-th masked entry is the top row of rank `sel`
       if (sel >= 0 && sel < ntop) {
-        const int pos = top_pos[k * NMAX + (int)sel];
-        e_flag[k * ne + pos] = 3;
-        const int gi = e_idx[k * ne + pos];
+        const int pos = top_pos[(int)sel];
+        e_flag[pos] = 3;
+        const int gi = e_idx[pos];
         if (p.out.d_masked_idx) p.out.d_masked_idx[((size_t)s * K + k) * p.keep_ld + i] = gi;
         const int64_t loc = (int64_t)gi - p.shard_begin[s];
         if (p.a_out && loc >= 0 && loc < p.row_off[s + 1] - p.row_off[s])
@@ -383,116 +425,133 @@ __global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ G
     } else {
       for (int i = lane; i < keep; i += 32) mask_one(i, p.rsel[((size_t)s * K + k) * p.keep_ld + i]);
     }
-    // ---- 2. same warp: m*, l*, afeat of branch k (no block-level synchronisation per branch) ----
     __syncwarp();
-    {
-      float mx = -INFINITY;
-      for (int r = lane; r < P; r += 32) mx = fmaxf(mx, recp(r)[p.rec.m() + k]);
-      for (int e = lane; e < ne; e += 32) {
-        const int f = e_flag[k * ne + e];
-        if (f == 1 || f == 2) mx = fmaxf(mx, e_score[k * ne + e]);
-        if (f == 3) mx = fmaxf(mx, MASK_FILL);
-      }
-      const float mstar = warp_max(mx);
-      float ls = 0.f;
-      for (int r = lane; r < P; r += 32) {
-        const float* rc = recp(r);
-        if (rc[p.rec.m() + k] != -INFINITY) ls += expf(rc[p.rec.m() + k] - mstar) * rc[p.rec.l() + k];
-      }
-      for (int e = lane; e < ne; e += 32) {
-        const int f = e_flag[k * ne + e];
-        float w = 0.f;
-        if (f == 1 || f == 2) w = expf(e_score[k * ne + e] - mstar);
-        if (f == 3) w = expf(MASK_FILL - mstar);
-        e_score[k * ne + e] = w;            // from here on the slot holds the entry's softmax numerator
-        ls += w;
-      }
-      const float lstar = warp_sum(ls);
-      if (lane == 0) { s_m[k] = mstar; s_l[k] = lstar; }
-      __syncwarp();
-      const float inv_l = 1.f / lstar;
-      for (int j0 = 0; j0 < L; j0 += 128) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < P; ++r) {
-          const float* rc = recp(r);
-          const float m = rc[p.rec.m() + k];
-          const float w = m == -INFINITY ? 0.f : expf(m - mstar);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int jf = j0 + lane + 32 * j;
-            if (jf < L) a[j] = fmaf(w, rc[p.rec.acc() + (size_t)k * L + jf], a[j]);
-          }
-        }
-        for (int e = 0; e < ne; ++e) {
-          const float w = e_score[k * ne + e];
-          if (w != 0.f) {
-            const float* hr = recp(e / nmc) + p.rec.h() + ((size_t)k * nmc + e % nmc) * L;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int jf = j0 + lane + 32 * j;
-              if (jf < L) a[j] = fmaf(w, hr[jf], a[j]);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int jf = j0 + lane + 32 * j;
-          if (jf < L) {
-            const float v = a[j] * inv_l;
-            af[(size_t)k * L + jf] = v;
-            if (p.out.d_afeat) p.out.d_afeat[((size_t)s * K + k) * L + jf] = v;
-          }
-        }
-      }
+    float mx = -INFINITY;
+    for (int r = lane; r < P; r += 32) mx = fmaxf(mx, recp(r)[p.rec.m() + k]);
+    for (int e = lane; e < ne; e += 32) {
+      const int f = e_flag[e];
+      if (f == 1 || f == 2) mx = fmaxf(mx, e_score[e]);
+      if (f == 3) mx = fmaxf(mx, MASK_FILL);
+    }
+    const float mstar = warp_max(mx);
+    float ls = 0.f;
+    for (int r = lane; r < P; r += 32) {
+      const float* rc = recp(r);
+      if (rc[p.rec.m() + k] != -INFINITY) ls += expf(rc[p.rec.m() + k] - mstar) * rc[p.rec.l() + k];
+    }
+    for (int e = lane; e < ne; e += 32) {
+      const int f = e_flag[e];
+      float w = 0.f;
+      if (f == 1 || f == 2) w = expf(e_score[e] - mstar);
+      if (f == 3) w = expf(MASK_FILL - mstar);
+      e_score[e] = w;            // from here on the slot holds the entry's softmax numerator
+      ls += w;
+    }
+    const float lstar = warp_sum(ls);
+    if (lane == 0) {
+      s_m = mstar;
+      s_l = lstar;
+      if (p.out.d_lse_m) p.out.d_lse_m[(size_t)s * K + k] = mstar;
+      if (p.out.d_lse_l) p.out.d_lse_l[(size_t)s * K + k] = lstar;
     }
   }
   __syncthreads();
-  if (tid < K) {
-    if (p.out.d_lse_m) p.out.d_lse_m[(size_t)s * K + tid] = s_m[tid];
-    if (p.out.d_lse_l) p.out.d_lse_l[(size_t)s * K + tid] = s_l[tid];
+  const float mstar = s_m, inv_l = 1.f / s_l;
+
+  // ---- 2. afeat of this branch: warp w takes ranks w, w + 8, ... and candidate entries w, w + 8, ...; lane l owns
+  // features j0 + 4 l .. + 3 (one 16-byte load per row), four rows in flight per round ----
+  const int nq = L / 4;
+  for (int j0 = 0; j0 < L; j0 += 128) {
+    const int jf = j0 + 4 * lane;
+    const bool in = jf < L;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = warp; r0 < P; r0 += 4 * (RT / 32)) {
+      float mv[4];
+      float4 av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * (RT / 32);
+        const float* rc = recp(r < P ? r : 0);
+        mv[u] = r < P ? __ldcg(rc + p.rec.m() + k) : -INFINITY;
+        av[u] = (r < P && in) ? __ldcg(reinterpret_cast<const float4*>(rc + p.rec.acc() + (size_t)k * L + jf))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = mv[u] == -INFINITY ? 0.f : expf(mv[u] - mstar);
+        a.x = fmaf(w, av[u].x, a.x); a.y = fmaf(w, av[u].y, a.y); a.z = fmaf(w, av[u].z, a.z); a.w = fmaf(w, av[u].w, a.w);
+      }
+    }
+    for (int e0 = warp; e0 < ne; e0 += 4 * (RT / 32)) {
+      float wv[4];
+      float4 hv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * (RT / 32);
+        wv[u] = e < ne ? e_score[e] : 0.f;
+        const float* hr = recp((e < ne ? e : 0) / nmc) + p.rec.h() + ((size_t)k * nmc + (e < ne ? e : 0) % nmc) * L;
+        hv[u] = (wv[u] != 0.f && in) ? __ldcg(reinterpret_cast<const float4*>(hr + jf)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a.x = fmaf(wv[u], hv[u].x, a.x); a.y = fmaf(wv[u], hv[u].y, a.y);
+        a.z = fmaf(wv[u], hv[u].z, a.z); a.w = fmaf(wv[u], hv[u].w, a.w);
+      }
+    }
+    if (in) wpart[warp * nq + jf / 4] = a;
   }
-  // bag feature = mean over branches of afeat  (== mean_k softmax(A_k) @ h, transformer.py:328-329)
-  for (int jf = tid; jf < L; jf += RT) {
+  __syncthreads();
+  for (int qd = tid; qd < nq; qd += RT) {      // fixed-order sum over the 8 warps: deterministic
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < RT / 32; ++w) {
+      const float4 u = wpart[w * nq + qd];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    t.x *= inv_l; t.y *= inv_l; t.z *= inv_l; t.w *= inv_l;
+    *reinterpret_cast<float4*>(af + qd * 4) = t;
+    if (p.out.d_afeat) *reinterpret_cast<float4*>(p.out.d_afeat + ((size_t)s * K + k) * L + qd * 4) = t;
+  }
+  __syncthreads();
+
+  // ---- 3. this branch's logits: one warp per class ----
+  const int C = p.heads.n_class;
+  if (p.out.d_sub && (p.heads.n_branch_heads > 0 || p.heads.shared_head)) {
+    for (int c = warp; c < C; c += RT / 32) {
+      const float* w = p.heads.n_branch_heads > 0 ? p.heads.d_wc + ((size_t)k * C + c) * L : p.heads.d_ws + (size_t)c * L;
+      const float b = p.heads.n_branch_heads > 0 ? p.heads.d_bc[k * C + c] : p.heads.d_bs[c];
+      float t = 0.f;
+      for (int jf = lane; jf < L; jf += 32) t = fmaf(w[jf], af[jf], t);
+      t = warp_sum(t);
+      if (lane == 0) p.out.d_sub[((size_t)s * K + k) * C + c] = t + b;
+    }
+  }
+}
+
+// bag feature = mean over branches of afeat (== mean_k softmax(A_k) @ h, transformer.py:328-329) and the slide head;
+// one CTA per bag, behind gp_finish_kernel.  With the exchange, block 0 also moves this rank on to the next step.
+__global__ void __launch_bounds__(128) gp_heads_kernel(const __grid_constant__ GpFinishParams p) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  float* bag = reinterpret_cast<float*>(dsm);      // [L]
+  const int L = p.sh.d_inner, K = p.sh.n_branch, s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int jf = tid; jf < L; jf += 128) {
     float t = 0.f;
-    for (int k = 0; k < K; ++k) t += af[(size_t)k * L + jf];
+    for (int k = 0; k < K; ++k) t += p.out.d_afeat[((size_t)s * K + k) * L + jf];
     t /= (float)K;
     bag[jf] = t;
     if (p.out.d_bag_feat) p.out.d_bag_feat[(size_t)s * L + jf] = t;
   }
   __syncthreads();
-
-  // ---- 3. heads: one warp per output logit ----
   const int C = p.heads.n_class;
-  if (p.out.d_sub && (p.heads.n_branch_heads > 0 || p.heads.shared_head)) {
-    for (int o = warp; o < K * C; o += RT / 32) {
-      const int k = o / C, c = o % C;
-      const float* w = p.heads.n_branch_heads > 0 ? p.heads.d_wc + ((size_t)k * C + c) * L : p.heads.d_ws + (size_t)c * L;
-      const float b = p.heads.n_branch_heads > 0 ? p.heads.d_bc[k * C + c] : p.heads.d_bs[c];
-      float t = 0.f;
-      for (int jf = lane; jf < L; jf += 32) t = fmaf(w[jf], af[(size_t)k * L + jf], t);
-      t = warp_sum(t);
-      if (lane == 0) p.out.d_sub[((size_t)s * K + k) * C + c] = t + b;
-    }
-  }
   if (p.out.d_slide && p.heads.slide_head) {
-    for (int c = warp; c < C; c += RT / 32) {
+    for (int c = warp; c < C; c += 4) {
       float t = 0.f;
       for (int jf = lane; jf < L; jf += 32) t = fmaf(p.heads.d_ws[(size_t)c * L + jf], bag[jf], t);
       t = warp_sum(t);
       if (lane == 0) p.out.d_slide[(size_t)s * C + c] = t + p.heads.d_bs[c];
     }
   }
-  if (p.x.n_ranks > 0) {      // the last CTA of the step moves this rank on to the next step (other parity)
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned t = atomicAdd(p.x.ticket + 1, 1u);
-      if (t == gridDim.x - 1u) {
-        p.x.ticket[1] = 0u;
-        __threadfence();
-        *p.x.epoch = epoch + 1u;
-      }
-    }
-  }
+  if (p.x.n_ranks > 0 && s == 0 && tid == 0) *p.x.epoch = *p.x.epoch + 1u;      // (every finish CTA of this step has retired)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -634,15 +693,17 @@ int gp_launch_finish(const GpFinishParams& p, cudaStream_t st) {
   if (p.n_slides == 0) return ACMIL_OK;
   const int K = p.sh.n_branch, L = p.sh.d_inner;
   const size_t ne = (size_t)p.n_ranks * p.rec.nmc;
-  const size_t smem = ((size_t)K * L + L + 3 * K * ne + (size_t)K * NMAX) * 4 + 16;
+  const size_t smem = ((size_t)(RT / 32) * L + L + 3 * ne + NMAX) * 4 + 16;
   ACMIL_REQUIRE(smem <= 200 * 1024, ACMIL_E_INVALID, "finish: n_ranks * n_masked too large (%zu entries)", ne);
+  ACMIL_REQUIRE(p.out.d_afeat != nullptr, ACMIL_E_INVALID, "outputs: d_afeat is required");
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gp_finish_kernel<<<p.n_slides, RT, smem, st>>>(p);
-  ++g_acmil_launches;
+  gp_finish_kernel<<<p.n_slides * K, RT, smem, st>>>(p);
+  gp_heads_kernel<<<p.n_slides, 128, (size_t)L * 4, st>>>(p);
+  g_acmil_launches += 2;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
 }

@@ -238,8 +238,7 @@ def run_ours(a):
         exchange_kind = "NCCL all_gather_into_tensor of the records (torch.distributed)"
         if a.exchange == "peer":
             try:
-                part_bytes = (2 * K_BRANCH + K_BRANCH * D_INNER + K_BRANCH + 2 * K_BRANCH * N_MASKED
-                              + K_BRANCH * N_MASKED * D_INNER) * 4 * S
+                part_bytes = _lib.record_floats(K_BRANCH, D_INNER, N_MASKED) * 4 * S
                 exchange = PeerExchange(part_bytes, dev)
                 exchange_kind = ("in-kernel: the reduce kernel stores the records into every peer's buffer over NVLink and raises "
                                  "a flag, the finish kernel waits for the flags (symmetric memory; no collective per step)")

@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 100 python tests/cuda/shard_time.py 8 2>&1 | tee gpurun_out/s13_shard.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gp_reduce_kernel|gp_finish_kernel" -s 12 -c 3 -f -o gpurun_out/s13_tail python tests/cuda/shard_time.py 8 > gpurun_out/s13_ncu.log 2>&1
+tail -3 gpurun_out/s13_ncu.log
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/s13_launches_shard8.csv python tests/cuda/shard_time.py 8 > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows = [r for r in csv.reader(open('gpurun_out/s13_launches_shard8.csv')) if len(r) > 10]
+hdr = rows[0]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+agg = collections.defaultdict(list)
+for r in rows[1:]:
+    agg[r[ki][:60]].append(float(r[vi].replace(',', '')))
+for k, v in agg.items():
+    if 'gp_' in k: print(f"{k:60s} n={len(v):3d} mean {sum(v) / len(v) / 1e3:8.1f} us")
+PY

@@ -83,8 +83,8 @@ def test_host_only_entry_points_and_validation():
     batch = L.GpBatch(None, off, 2, 10, None, None, 50007)
     ws, part = C.c_size_t(0), C.c_size_t(0)
     assert lib.acmil_gp_sizes(C.byref(shape), C.byref(batch), L.IMPL_FFMA, C.byref(ws), C.byref(part)) == 0
-    stride = 2 * 5 + 5 * 128 + 5 + 2 * 5 * 10 + 5 * 10 * 128
-    assert part.value == 2 * stride * 4
+    assert part.value == 2 * L.record_floats(5, 128, 10) * 4      # m, l, acc, cnt, score, idx, h (sections padded to 4)
+    assert L.record_floats(5, 128, 10) == 8 + 8 + 640 + 8 + 52 + 52 + 6400
     assert ws.value > 0
     # validation errors come back as codes + messages, never exceptions/aborts
     bad = L.GpShape(384, 128, 128, 9, 1, 0, 1, 0, 1, 1, 1, 0)

@@ -497,7 +497,8 @@ def test_in_kernel_exchange_matches_unsharded(ranks, impl):
     packed = op.pack(w.get("w1"), None, w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
     branch = (torch.stack([c.fc.weight for c in m.classifier]), torch.stack([c.fc.bias for c in m.classifier]))
     head = (m.Slide_classifier.fc.weight, m.Slide_classifier.fc.bias)
-    capacity = (2 * 5 + 5 * 128 + 5 + 2 * 5 * 10 + 5 * 10 * 128) * 4 * len(sizes)
+    import acmil_b200._lib as L_
+    capacity = L_.record_floats(5, 128, 10) * 4 * len(sizes)
     bufs = [torch.zeros((256 + 2 * ranks * capacity) // 4, device="cuda") for _ in range(ranks)]
     xch = [_LocalExchange(ranks, r, bufs, capacity) for r in range(ranks)]
     off = np.concatenate([[0], np.cumsum(sizes)]).tolist()
