@@ -7,6 +7,7 @@ from . import _lib  # noqa: F401
 from .gated_pool import GatedPool, GatedPoolResult, GatedPoolSpec  # noqa: F401
 from .heads import (ABMIL, ACMIL_GA, Attention2, Attention_Gated, Attention_with_Classifier,  # noqa: F401
                     AttentionGated, Classifier_1fc, DAttention, DimReduction)
+from .mha import ACMIL_MHA, MHA, MutiHeadAttention, MutiHeadAttention_modify  # noqa: F401
 from .transmil import PPEG, NystromAttention, TransLayer, TransMIL  # noqa: F401
 from .utils import Struct, set_seed  # noqa: F401
 

@@ -1185,7 +1185,8 @@ extern "C" __attribute__((visibility("default"))) int acmil_debug_umma_prof(long
 #endif
 
 int gp_umma_supported(const acmil_gp_shape& s) {
-  return s.front == 1 && s.front_act == ACMIL_ACT_RELU && s.act_a == ACMIL_ACT_TANH && s.gated == 1 && s.d_inner == 128 &&
+  // (no front-layer bias: Epi1 is relu(D1 / S1) only -- CLAM's Linear+bias front layer runs on the FFMA kernel)
+  return s.front == 1 && s.front_bias == 0 && s.front_act == ACMIL_ACT_RELU && s.act_a == ACMIL_ACT_TANH && s.gated == 1 && s.d_inner == 128 &&
          s.d_attn == 128 && s.d_in % 64 == 0 && s.d_in >= 64 && s.d_in <= 384 && s.n_branch >= 1 && s.n_branch <= KMAX;
 }
 
