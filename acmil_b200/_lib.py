@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.environ.get("ACMIL_B200_LIB_DIR") or os.path.join(_HERE, "lib"), "libacmil_b200.so")
 
-MAX_BRANCH, MAX_MASKED, MAX_SLIDES, MAX_CLASS = 8, 32, 64, 16
+MAX_BRANCH, MAX_MASKED, MAX_SLIDES, MAX_CLASS = 8, 32, 128, 16
 ACT_TANH, ACT_RELU, ACT_GELU = 0, 1, 2
 IMPL_AUTO, IMPL_FFMA, IMPL_UMMA = 0, 1, 2
 ACT_IDS = {"tanh": ACT_TANH, "relu": ACT_RELU, "gelu": ACT_GELU}

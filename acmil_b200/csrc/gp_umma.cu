@@ -12,8 +12,10 @@
 //    160 KB resident for the whole launch and nothing but x is streamed.
 //  * A operands (converted x, and h = relu(xW1^T)) live in TMEM, written with tcgen05.st by the thread
 //    that owns the row, so the MMAs read only B from shared memory.
-//  * TMEM (512 columns): D1 h-accumulator 128 | D2 gate accumulator 128 (two halves per tile) |
-//    h operand hi/lo 128 | x operand ring 4 x 32.
+//  * TMEM (512 columns): two D1 h-accumulators of 128 columns, each rewritten IN PLACE by Epi1 as the packed fp16
+//    hi/lo h operand of the gate GEMM (per 64-feature half: 32 columns hi, 32 columns lo), so the projection of tile
+//    t + 1 runs while the epilogue is still working on tile t | D2 gate accumulator 128 (two 64-column buffers, four
+//    quarters per tile) | x operand ring 4 x 32.
 //
 // Roles per CTA (512 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA; warp-uniform code with
 // elect.sync around the tcgen05 instructions), warp 2 TMEM allocator + top-n list manager, warp 3 bag-wide
@@ -37,15 +39,13 @@ using namespace umma_shared;
 
 constexpr int UT = 512;
 constexpr int NXOP = 4;      // TMEM x-operand ring
-constexpr uint32_t TM_D1 = 0, TM_D2 = 128, TM_HHI = 256, TM_HLO = 320, TM_X = 384;
+// D1 / h buffer b at columns 128 b; inside it, after Epi1: half hf (features 64 hf ...) hi at 64 hf, lo at 64 hf + 32
+constexpr uint32_t TM_DH = 0, TM_D2 = 256, TM_X = 384;
 
 #ifndef GP_UMMA_PROF
 #define GP_UMMA_PROF 0
 #endif
 // polling periods (ns) of the two service warps: they share their schedulers with epilogue warps
-#ifndef GP_EXP_IDLE_HS1
-#define GP_EXP_IDLE_HS1 0
-#endif
 #ifndef GP_MGR_SLEEP
 #define GP_MGR_SLEEP 400
 #endif
@@ -92,7 +92,7 @@ __host__ __device__ inline SmemMap smem_map(int din, int kb) {
 struct Bars {
   uint64_t full_x[NSTAGE], empty_x[NSTAGE];
   uint64_t xop_full[NXOP], xop_empty[NXOP];
-  uint64_t d1_full, d1_empty, hop_full, d2_full[2], d2_empty[2], wload, w_ready;
+  uint64_t d1_full[2], d1_empty[2], hop_full, d2_full[2], d2_empty[2], wload, w_ready;
   uint32_t tmem_base;
 };
 
@@ -119,8 +119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full_x[i], 1); mbar_init(&bars->empty_x[i], 4); }
     for (int i = 0; i < NXOP; ++i) { mbar_init(&bars->xop_full[i], 8); mbar_init(&bars->xop_empty[i], 1); }
-    mbar_init(&bars->d1_full, 1);
-    mbar_init(&bars->d1_empty, 16);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->d1_full[i], 1); mbar_init(&bars->d1_empty[i], 16); }
     mbar_init(&bars->hop_full, 16);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->d2_full[i], 1); mbar_init(&bars->d2_empty[i], 16); }
     mbar_init(&bars->wload, 1);
@@ -202,7 +201,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
       uint32_t xc = 0;  // x-operand chunks consumed so far (ring position / phase)
       // chunk c of tile t of the projection GEMM; returns false (nothing issued) when its inputs are not there yet
       auto g1_try = [&](int t, int c) -> bool {
-        if (c == 0 && t > 0 && !mbar_test_wait(&bars->d1_empty, (uint32_t)(t - 1) & 1u)) return false;   // D1 drained?
+        // buffer t & 1 was tile t - 2's accumulator, gate operand and pool operand: free once that tile's pool is done
+        if (c == 0 && t > 1 && !mbar_test_wait(&bars->d1_empty[t & 1], (uint32_t)((t >> 1) - 1) & 1u)) return false;
         const uint32_t q = xc % NXOP, ph = (xc / NXOP) & 1u;
         if (!mbar_test_wait(&bars->xop_full[q], ph)) return false;
         tc_fence_after();
@@ -212,12 +212,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
-            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
-            umma_ts<2>(tm + TM_D1, xa_lo + ks * 8, bhi, idesc, 1u);
-            umma_ts<2>(tm + TM_D1, xa_hi + ks * 8, blo, idesc, 1u);
+            umma_ts<2>(tm + TM_DH + (uint32_t)(t & 1) * 128u, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
+            umma_ts<2>(tm + TM_DH + (uint32_t)(t & 1) * 128u, xa_lo + ks * 8, bhi, idesc, 1u);
+            umma_ts<2>(tm + TM_DH + (uint32_t)(t & 1) * 128u, xa_hi + ks * 8, blo, idesc, 1u);
           }
           umma_commit_2sm(&bars->xop_empty[q], 3);
-          if (c == NCH - 1) umma_commit_2sm(&bars->d1_full, 3);
+          if (c == NCH - 1) umma_commit_2sm(&bars->d1_full[t & 1], 3);
         }
         __syncwarp();
         ++xc;
@@ -237,9 +237,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           for (int ks = 0; ks < 8; ++ks) {
             const uint32_t boff = (uint32_t)(qr * 2 + (ks >> 2)) * 4096u + (uint32_t)(ks & 3) * 32u;
             const uint64_t bhi = umma_desc_k_sw128(wg_hi + boff), blo = umma_desc_k_sw128(wg_lo + boff);
-            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, bhi, idesc64, ks ? 1u : 0u);
-            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HLO + ks * 8, bhi, idesc64, 1u);
-            umma_ts<2>(tm + TM_D2 + b * 64, tm + TM_HHI + ks * 8, blo, idesc64, 1u);
+            const uint32_t ha = tm + TM_DH + (uint32_t)(t & 1) * 128u + (uint32_t)(ks >> 2) * 64u + (uint32_t)(ks & 3) * 8u;
+            umma_ts<2>(tm + TM_D2 + b * 64, ha, bhi, idesc64, ks ? 1u : 0u);
+            umma_ts<2>(tm + TM_D2 + b * 64, ha + 32u, bhi, idesc64, 1u);
+            umma_ts<2>(tm + TM_D2 + b * 64, ha, blo, idesc64, 1u);
           }
           umma_commit_2sm(&bars->d2_full[b], 3);
         }
@@ -262,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           {   // nothing could be issued: attribute the idle poll to what blocks each GEMM
             const long long dt = clock64() - t_it;
             if (c < nc) {
-              if (c == 0 && !mbar_test_wait(&bars->d1_empty, (uint32_t)t & 1u)) prof[1] += dt; else prof[2] += dt;
+              if (c == 0 && t > 0 && !mbar_test_wait(&bars->d1_empty[(t + 1) & 1], (uint32_t)(((t + 1) >> 1) - 1) & 1u)) prof[1] += dt; else prof[2] += dt;
             } else prof[5] += dt;
             if (qr < 4) {
               if (qr == 0 && !mbar_test_wait(&bars->hop_full, (uint32_t)t & 1u)) prof[3] += dt; else prof[4] += dt;
@@ -415,6 +416,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     PROF_DECL();
 #if GP_UMMA_PROF
     const long long t_start = clock64();
+    unsigned long long ns_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_start));
 #endif
     for (int t = 0; t < T; ++t) {
       for (int c = 0; c < NCH; ++c, ++ctr) {
@@ -445,6 +448,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     }
 #if GP_UMMA_PROF
     prof[7] = clock64() - t_start;
+    {   // wall-clock span of the same loop: cycles / ns = the SM clock this kernel really ran at
+      unsigned long long ns_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+      prof[6] = (long long)(ns_end - ns_start);
+    }
     if (warp == 4 && lane == 0) PROF_FLUSH(16);
 #endif
   } else {
@@ -684,26 +692,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         { PROF_T0(); flush_stream(); PROF_ADD(6); }
         reset_stream(tp.s);
       }
-#if GP_EXP_IDLE_HS1
-      // timing experiment only (results are garbage): the second warp of every scheduler just keeps the barrier protocol
-      // alive, so that the phases of the first one run without a same-phase competitor
-      if (hs == 1) {
-        mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u);
-        __syncwarp();
-        if (lane == 0) { mbar_arrive_cluster(&bars->hop_full, 0); mbar_arrive_cluster(&bars->d1_empty, 0); }
-        for (int qr = 0; qr < 4; ++qr) {
-          mbar_wait_cluster(&bars->d2_full[qr & 1], (uint32_t)(2 * t + (qr >> 1)) & 1u);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&bars->d2_empty[qr & 1], 0);
-        }
-        continue;
-      }
-#endif
       const int64_t row_a = tp.row_in_bag + lane_base + rg, row_b = row_a + 8;
       const bool valid_a = row_a < n_rows, valid_b = row_b < n_rows;
 
       // ---------------- Epi1: D1 -> relu -> fp16 hi/lo operand of the gate GEMM ----------------
-      { PROF_T0(); mbar_wait_cluster(&bars->d1_full, (uint32_t)t & 1u); PROF_ADD(0); }
+      const uint32_t tm_dh = tm + lane_addr + TM_DH + (uint32_t)(t & 1) * 128u;
+      { PROF_T0(); mbar_wait_cluster(&bars->d1_full[t & 1], (uint32_t)(t >> 1) & 1u); PROF_ADD(0); }
       tc_fence_after();
 #if GP_UMMA_PROF
       const long long t_e1 = clock64();
@@ -711,7 +705,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t v[32];
-        tmem_ld_16x256b_x8(tm + lane_addr + TM_D1 + hf * 64, v);
+        tmem_ld_16x256b_x8(tm_dh + hf * 64, v);
         tmem_wait_ld();
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -721,16 +715,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           split2(fmaxf(__uint_as_float(v[4 * i + 2]) * p.c.inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) * p.c.inv_s1, 0.f),
                  hi[2 * i + 1], lo[2 * i + 1]);
         }
-        tmem_st_16x128b_x8(tm + lane_addr + TM_HHI + hf * 32, hi);
-        tmem_st_16x128b_x8(tm + lane_addr + TM_HLO + hf * 32, lo);
+        tmem_st_16x128b_x8(tm_dh + hf * 64, hi);            // in place: the 64 fp32 columns just read become 32 + 32
+        tmem_st_16x128b_x8(tm_dh + hf * 64 + 32, lo);       // packed fp16 columns (this warp owns these 16 lanes)
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(&bars->hop_full, 0);
-        mbar_arrive_cluster(&bars->d1_empty, 0);
-      }
+      if (lane == 0) mbar_arrive_cluster(&bars->hop_full, 0);
 #if GP_UMMA_PROF
       prof[2] += clock64() - t_e1;
       const long long t_e2 = clock64();
@@ -1037,8 +1028,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t hh[16], hl[16];     // regs {2i, 2i+1}: rows rg / rg + 8, features 64 hf + 8i + 2cp + {0,1}
-        tmem_ld_16x128b_x8(tm + lane_addr + TM_HHI + hf * 32, hh);
-        tmem_ld_16x128b_x8(tm + lane_addr + TM_HLO + hf * 32, hl);
+        tmem_ld_16x128b_x8(tm_dh + hf * 64, hh);
+        tmem_ld_16x128b_x8(tm_dh + hf * 64 + 32, hl);
         tmem_wait_ld();
         if (ex_a | ex_b) {   // park the rows that entered a list this tile (fp32 h = hi + lo)
 #pragma unroll
@@ -1070,7 +1061,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           mma_16816_f16(acc[hf * 4 + jj], ahi, bl);
         }
       }
-      __syncwarp();      // psw is rewritten by the next tile
+      tc_fence_before();
+      __syncwarp();      // psw is rewritten by the next tile; the h operand has been read: its buffer may take tile t + 2
+      if (lane == 0) mbar_arrive_cluster(&bars->d1_empty[t & 1], 0);
 #if GP_UMMA_PROF
       prof[5] += clock64() - t_e4;
 #endif

@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slides", type=int, default=8, help="bags per step per GPU")
+    ap.add_argument("--slides", type=int, default=16, help="bags per step per GPU")
     ap.add_argument("--groups", type=int, default=3, help="distinct device-resident bag groups rotated over steps")
     ap.add_argument("--kernel", default="auto", choices=["auto", "ffma", "umma"])
     ap.add_argument("--mode", default="train", choices=["train", "eval"])

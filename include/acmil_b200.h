@@ -63,7 +63,7 @@ enum { ACMIL_IMPL_AUTO = 0, ACMIL_IMPL_FFMA = 1, ACMIL_IMPL_UMMA = 2 };
 
 #define ACMIL_MAX_BRANCH 8     /* n_token */
 #define ACMIL_MAX_MASKED 32    /* n_masked_patch */
-#define ACMIL_MAX_SLIDES 64    /* bags per launch */
+#define ACMIL_MAX_SLIDES 128   /* bags per launch */
 #define ACMIL_MAX_CLASS 16
 
 /* Static description of one gated-attention pooling head. */

@@ -32,6 +32,7 @@ for cta in (0, 1):
     for k, v in names.items():
         print(f"{v:28s} mean {sel[:, k].mean():12.0f}  max {sel[:, k].max():12.0f}")
 
+print(f"SM clock during the kernel: {a[:, 23].mean() / a[:, 22].mean() * 1e3:.0f} MHz  (converter loop: {a[:, 23].mean():.0f} cycles in {a[:, 22].mean() / 1e3:.1f} us)")
 enames = ["wait_d1_full", "wait_d2_full", "epi1", "epi2(incl wait)", "softmax/cand", "pool", "flush", "total"]
 print("--- epilogue warps (mean over all CTAs), cycles per launch")
 print(" " * 18 + "".join(f"{'e' + str(e):>10s}" for e in range(8)))
