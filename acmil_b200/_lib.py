@@ -75,6 +75,15 @@ class GpExchange(C.Structure):
                 ("gather_bytes", C.c_size_t)]
 
 
+class GpBwdGateArgs(C.Structure):
+    """acmil_gp_bwd_gate_args (include/acmil_b200.h)."""
+    _fields_ = ([(n, C.c_void_p) for n in ("d_h", "d_z", "d_scores", "d_lse_m", "d_lse_l", "d_afeat", "d_g_afeat", "d_g_bag",
+                                           "d_g_scores", "d_ww")]
+                + [(n, C.c_int64) for n in ("n", "a_ld", "gs_ld", "ldt")]
+                + [(n, C.c_int32) for n in ("d_inner", "d_attn", "n_branch", "act_a", "gated", "reserved")]
+                + [(n, C.c_void_p) for n in ("d_dz", "d_dzt", "d_dhp", "d_partials", "d_small")])
+
+
 class GemmDesc(C.Structure):
     """acmil_gemm_desc (include/acmil_transmil.h)."""
     _fields_ = ([(n, C.c_void_p) for n in ("a", "b", "c", "ct", "bias", "addend", "split_ws")]
@@ -146,6 +155,14 @@ SYMBOLS = {
     "acmil_gp_attn_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "acmil_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "acmil_gp_bwd_workspace_floats": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "acmil_gp_bwd_gate": (C.c_int, [C.POINTER(GpBwdGateArgs), C.c_void_p]),
+    "acmil_gp_bwd_relu_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "acmil_transpose_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "acmil_div_loss_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "acmil_div_loss_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_void_p]),
     # include/acmil_transmil.h
     "acmil_gemm_nt": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "acmil_layernorm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,

@@ -236,9 +236,8 @@ static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, 
                 "a_ld smaller than the number of rows");
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
   int use = pick_impl(*shape, impl);
-  if (impl == ACMIL_IMPL_AUTO && use == ACMIL_IMPL_UMMA &&
-      (!(consts && consts->valid == ACMIL_ABI_VERSION) || (shape->n_branch > 6 && batch->n_masked > 0)))
-    use = ACMIL_IMPL_FFMA;   // no host constants supplied / masking with > 6 branches: stay on the general kernel
+  if (impl == ACMIL_IMPL_AUTO && use == ACMIL_IMPL_UMMA && shape->n_branch > 6 && batch->n_masked > 0)
+    use = ACMIL_IMPL_FFMA;   // masking with > 6 branches: stay on the general kernel
   ACMIL_REQUIRE(use != ACMIL_IMPL_UMMA || gp_umma_supported(*shape), ACMIL_E_UNSUPPORTED,
                 "tcgen05 kernel does not support this shape");
   GpMainParams p;

@@ -68,7 +68,8 @@ static inline GpPackLayout gp_pack_layout(const acmil_gp_shape& s) {
   l.f32_floats = o;
   l.umma_off = ((o * 4 + 1023) / 1024) * 1024;
   // [absmax, pad to 1024][per-CTA images: hi/lo fp16 of a W1 half (64 x d_in) and of Wv or Wu (128 x 128)]
-  l.umma_bytes = 1024 + 2 * ((size_t)((s.d_in + 63) / 64) * 8192 * 2 + 65536);
+  // ... followed by 8 KB for the device-resident constants (UmmaConsts, gp_umma_shared.cuh)
+  l.umma_bytes = 1024 + 2 * ((size_t)((s.d_in + 63) / 64) * 8192 * 2 + 65536) + 8192;
   l.total_bytes = l.umma_off + l.umma_bytes;
   return l;
 }

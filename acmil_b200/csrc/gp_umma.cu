@@ -137,9 +137,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     for (int u = tid; u < 128; u += UT) {      // record of the unit pair (2c, 2c+1): {ww[k][2c], ww[k][2c+1]}_k, bv' pair, bu' pair
       float* rec = cst + (u >> 1) * (2 * CREC) + (u & 1);
 #pragma unroll
-      for (int k = 0; k < KB; ++k) rec[2 * k] = p.c.ww[k][u];
-      rec[2 * KB] = p.c.bv[u] * (-2.f * LOG2E);
-      rec[2 * KB + 2] = p.c.bu[u] * (-LOG2E);
+      for (int k = 0; k < KB; ++k) rec[2 * k] = p.dc->ww[k][u];
+      rec[2 * KB] = p.dc->bv[u] * (-2.f * LOG2E);
+      rec[2 * KB + 2] = p.dc->bu[u] * (-LOG2E);
     }
   }
   if (KB <= 6) {
@@ -471,7 +471,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
     constexpr int CREC = cst_rec(KB);
     const int L = 128;
     const int cap = seg.n_masked_cap;
-    const float cva = p.c.inv_sv * (-2.f * LOG2E), cua = p.c.inv_su * (-LOG2E);
+    const float cva = p.dc->inv_sv * (-2.f * LOG2E), cua = p.dc->inv_su * (-LOG2E), inv_s1 = p.dc->inv_s1;
+    float bwk[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) bwk[k] = p.dc->bw[k];
 
     // Softmax-pool state of this warp's stream.  Numerators are p' = exp(s - m_ref[k]) * 2^PSH against a per-warp
     // reference m_ref[k] that only grows, and only when a taken row exceeds it by more than REF_SLACK nats (then l and
@@ -710,9 +713,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          split2(fmaxf(__uint_as_float(v[4 * i]) * p.c.inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) * p.c.inv_s1, 0.f),
+          split2(fmaxf(__uint_as_float(v[4 * i]) * inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) * inv_s1, 0.f),
                  hi[2 * i], lo[2 * i]);
-          split2(fmaxf(__uint_as_float(v[4 * i + 2]) * p.c.inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) * p.c.inv_s1, 0.f),
+          split2(fmaxf(__uint_as_float(v[4 * i + 2]) * inv_s1, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) * inv_s1, 0.f),
                  hi[2 * i + 1], lo[2 * i + 1]);
         }
         tmem_st_16x128b_x8(tm_dh + hf * 64, hi);            // in place: the 64 fp32 columns just read become 32 + 32
@@ -791,8 +794,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 1);
         sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], 2);
         sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 2);
-        sa[k] += p.c.bw[k];
-        sb[k] += p.c.bw[k];
+        sa[k] += bwk[k];
+        sb[k] += bwk[k];
       }
 #if GP_UMMA_PROF
       prof[3] += clock64() - t_e2;
@@ -1143,6 +1146,23 @@ __global__ void umma_pack_kernel(acmil_gp_shape sh, acmil_gp_weights w, const fl
   }
 }
 
+// the device-resident constants of the row pass, from the fp32 section of the packed blob (already laid out and
+// zero-filled where a bias is absent) and the operand scales
+__global__ void umma_consts_kernel(const float* __restrict__ f32, GpPackLayout lay, const float* __restrict__ absmax,
+                                   UmmaConsts* __restrict__ out) {
+  const int u = threadIdx.x;      // 128 threads
+  out->bv[u] = f32[lay.bv + u];
+  out->bu[u] = f32[lay.bu + u];
+  for (int k = 0; k < KMAX; ++k) out->ww[k][u] = f32[lay.ww + (size_t)k * 128 + u];
+  if (u < KMAX) out->bw[u] = f32[lay.bw + u];
+  if (u == 0) {
+    out->inv_s1 = 1.f / pow2_scale(absmax[0]);
+    out->inv_sv = 1.f / pow2_scale(absmax[1]);
+    out->inv_su = 1.f / pow2_scale(absmax[2]);
+    out->pad = 0.f;
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1198,8 +1218,13 @@ int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned ch
   umma_pack_kernel<<<148, 256, 0, st>>>(s, w, d_absmax, img, cta_img, w1_part);
   g_acmil_launches += 4;
   ACMIL_CHECK_CUDA(cudaGetLastError());
+  UmmaConsts* dc = reinterpret_cast<UmmaConsts*>(img + 2 * (size_t)cta_img);
+  umma_consts_kernel<<<1, 128, 0, st>>>(d_f32, lay, d_absmax, dc);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
   if (consts) {
-    // host copy of the small vectors (already laid out, zero-filled where absent, by the fp32 pack)
+    // optional host copy for callers that want to look at the vectors: the only part of packing that synchronises.
+    // The kernels never read it (non-finite score weights give non-finite scores, as in the reference).
     float absmax[4] = {0, 0, 0, 0};
     ACMIL_CHECK_CUDA(cudaMemcpyAsync(absmax, d_absmax, 16, cudaMemcpyDeviceToHost, st));
     ACMIL_CHECK_CUDA(cudaMemcpyAsync(consts->b1, d_f32 + lay.b1, 128 * 4, cudaMemcpyDeviceToHost, st));
@@ -1220,15 +1245,7 @@ int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned ch
       consts->inv_scale[i] = 1.f / sc;
     }
     consts->inv_scale[3] = 1.f;
-    // the tcgen05 kernel's softmax follows a running reference, so any finite score range is fine; non-finite score
-    // weights are left to the exact FFMA kernel (which propagates them like the reference does)
-    float bound = 0.f;
-    for (int k = 0; k < s.n_branch; ++k) {
-      float bk = fabsf(consts->bw[k]);
-      for (int u = 0; u < 128; ++u) bk += fabsf(consts->ww[k][u]);
-      if (!(bk <= bound)) bound = bk;   // NaN-propagating max
-    }
-    consts->valid = isfinite(bound) ? ACMIL_ABI_VERSION : 0;
+    consts->valid = ACMIL_ABI_VERSION;
   }
   return ACMIL_OK;
 }
@@ -1289,23 +1306,11 @@ int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t) {
 int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, const unsigned char* d_umma, cudaStream_t st) {
   const acmil_gp_shape& s = p.sh;
   ACMIL_REQUIRE(gp_umma_supported(s), ACMIL_E_UNSUPPORTED, "tcgen05 kernel does not support this shape");
-  ACMIL_REQUIRE(consts != nullptr && consts->valid == ACMIL_ABI_VERSION, ACMIL_E_INVALID,
-                "tcgen05 kernel needs the acmil_gp_consts filled by acmil_gp_pack");
+  (void)consts;      // the constants live in the packed blob (device); the host copy is informational
   if (p.seg.u_total_pt == 0) return ACMIL_OK;
   static thread_local UmmaParams up;   // large: keep off the stack
   up.mp = p;
-  memcpy(up.c.b1, consts->b1, sizeof(up.c.b1));
-  memcpy(up.c.bv, consts->bv, sizeof(up.c.bv));
-  memcpy(up.c.bu, consts->bu, sizeof(up.c.bu));
-  memcpy(up.c.ww, consts->ww, sizeof(up.c.ww));
-  memcpy(up.c.bw, consts->bw, sizeof(up.c.bw));
-  for (int u = 0; u < 128; ++u) {
-    up.c.bvx[u] = consts->bv[u] * (-2.f * LOG2E);
-    up.c.bux[u] = consts->bu[u] * (-LOG2E);
-  }
-  up.c.inv_s1 = consts->inv_scale[0];
-  up.c.inv_sv = consts->inv_scale[1];
-  up.c.inv_su = consts->inv_scale[2];
+  up.dc = reinterpret_cast<const UmmaConsts*>(d_umma + 1024 + 2 * (size_t)umma_cta_img_bytes(s));
   up.wimg = d_umma + 1024;
   up.cta_img_bytes = umma_cta_img_bytes(s);
   up.w1_part_bytes = (uint32_t)(s.d_in / 64) * 8192u;
@@ -1328,12 +1333,6 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
   const int grid = p.seg.u_nclusters * 2;
   if (p.seg.n_masked_cap > 0)     // one memset: per-bag overflow flags = -1 (clean), mirrored top-n lists = NaN
     ACMIL_CHECK_CUDA(cudaMemsetAsync(p.ws + p.wl.flags, 0xFF, p.wl.cand_idx - p.wl.flags, st));   // ("not written in this launch")
-  {
-    // ACMIL_GP_UMMA_VARIANT=3 selects the experimental two-tiles-in-flight kernel of gp_umma3.cu (parity-green, but
-    // measured slower than this file's kernel on B200: DESIGN.md section 3.1b); default 2 = the kernel below
-    static const int variant = [] { const char* e = getenv("ACMIL_GP_UMMA_VARIANT"); return e ? atoi(e) : 2; }();
-    if (variant == 3) return gp_launch_main_umma3(up, K, grid, st);
-  }
   if (K == 1) return launch_kb<1>(up, grid, smem, st);
   if (K <= 5) return launch_kb<5>(up, grid, smem, st);
   return launch_kb<8>(up, grid, smem, st);

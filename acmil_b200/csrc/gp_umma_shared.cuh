@@ -1,5 +1,5 @@
-// Declarations shared by the two tcgen05 row-pass kernels (gp_umma.cu: one tile in flight, all-in-one epilogue
-// warps; gp_umma3.cu: two tiles in flight, role-specialised epilogue warps).
+// Declarations of the tcgen05 row-pass kernel (gp_umma.cu).  (A role-specialised two-tiles-in-flight variant, gp_umma3.cu,
+// lived next to it for a while: parity-green but slower; git history f79081b.)
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -15,15 +15,19 @@ constexpr int NSTAGE = 3;    // fp32 staging ring (TMA destination)
 constexpr int STAGE_BYTES = 128 * KC * 4;
 constexpr float LOG2E = 1.4426950408889634f;
 
+// Small per-head vectors and operand scales, DEVICE-resident inside the packed blob (written by umma_consts_kernel
+// at pack time, read by the row pass in its prologue): packing needs no host round trip, so an optimizer step followed
+// by a re-pack stays asynchronous and graph-capturable.
 struct alignas(16) UmmaConsts {
-  float b1[128], bv[128], bu[128], ww[KMAX][128], bw[KMAX];
-  float bvx[128], bux[128];    // the gate biases in the exponent domain: -2 log2e bv, -log2e bu
+  float bv[128], bu[128], ww[KMAX][128], bw[KMAX];
   float inv_s1, inv_sv, inv_su, pad;
 };
+constexpr size_t UMMA_CONSTS_BYTES = 8192;   // room reserved for UmmaConsts at the end of the blob's umma section
+static_assert(sizeof(UmmaConsts) <= UMMA_CONSTS_BYTES, "UmmaConsts outgrew its slot");
 
 struct UmmaParams {
   GpMainParams mp;
-  UmmaConsts c;
+  const UmmaConsts* dc;        // device copy of the constants (inside the packed blob)
   CUtensorMap tmap;
   const unsigned char* wimg;   // per-CTA weight images, cta_img_bytes each
   uint32_t cta_img_bytes;
@@ -93,6 +97,3 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 
 
 }  // namespace umma_shared
-
-// gp_umma3.cu
-int gp_launch_main_umma3(const umma_shared::UmmaParams& up, int n_branch, int grid, cudaStream_t st);

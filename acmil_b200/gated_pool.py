@@ -72,7 +72,6 @@ class GatedPool:
         self._shape = spec.c_struct()
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
-        self._consts = L.GpConsts()       # host copy of the small vectors for the tcgen05 kernel
         self._bufs: dict = {}
 
     # ------------------------------------------------------------------ weights
@@ -93,8 +92,8 @@ class GatedPool:
         packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
-            L.check(lib.acmil_gp_pack(C.byref(self._shape), C.byref(w), _ptr(packed), nbytes.value,
-                                      C.byref(self._consts), C.c_void_p(st)))
+            # consts = NULL: the kernels' constants are written into the blob on the device; no host copy, no stream sync
+            L.check(lib.acmil_gp_pack(C.byref(self._shape), C.byref(w), _ptr(packed), nbytes.value, None, C.c_void_p(st)))
         self._packed, self._packed_key = packed, key
         self._keepalive = keep
         return packed
@@ -135,7 +134,7 @@ class GatedPool:
         part = None if exchange is not None else torch.empty(max(part_b.value, 4) // 4, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            consts = C.byref(self._consts) if (packed is self._packed and self._consts.valid) else None
+            consts = None      # (acmil_gp_consts is an optional host copy; the kernels read the device copy in the blob)
             if exchange is not None:
                 xs = exchange.c_struct(part_b.value)
                 L.check(lib.acmil_gp_partial_x(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
@@ -144,7 +143,7 @@ class GatedPool:
                 L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
                                              ws.numel(), _ptr(part), part.numel() * 4, st))
         ctx = dict(batch=batch, keepalive=(off, sb, x), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
-                   row_offsets=list(row_offsets), ws=ws, impl=impl if consts is not None else L.IMPL_FFMA,
+                   row_offsets=list(row_offsets), ws=ws, impl=impl,
                    exchange=exchange, partial_bytes=part_b.value)
         return part, ctx
 

@@ -16,6 +16,7 @@ kernel selected, so parameters train with the same losses as the reference.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -78,7 +79,9 @@ def _torch_gate(h, m, act_a="tanh", gated=True):
 
 
 class _PoolFn(torch.autograd.Function):
-    """forward = fused kernels; backward = torch recomputation with the kernel's mask."""
+    """forward = fused kernels; backward = the kernel path of gp_backward.py (recompute-based: tcgen05 GEMMs + csrc/gp_bwd.cu)
+    where it supports the head's shape, else a torch-op recomputation with the kernel's mask (ACMIL_POOL_BACKWARD=torch
+    forces the latter: it is the yardstick of tests/test_gated_pool_gpu.py)."""
 
     @staticmethod
     def forward(ctx, runner, x, n_named, *params):
@@ -97,6 +100,14 @@ class _PoolFn(torch.autograd.Function):
     def backward(ctx, g_afeat, g_bag, g_scores):
         x, *tensors = ctx.saved_tensors
         spec = ctx.runner.spec
+        from . import gp_backward as B
+        if B.supported(spec) and os.environ.get("ACMIL_POOL_BACKWARD", "kernel") != "torch":
+            # kernel path: tcgen05 GEMMs + csrc/gp_bwd.cu, recomputed from x, the raw scores and the softmax statistics
+            res = ctx.res
+            got = B.pool_backward(spec, x, dict(zip(ctx.names, tensors)), res.scores, res.lse_m[0], res.lse_l[0], res.afeat[0],
+                                  g_afeat, g_bag, g_scores, need_dx=x.requires_grad)
+            gp = [got.get(nm) if t.requires_grad else None for nm, t in zip(ctx.names, tensors)]
+            return (None, got.get("x"), None) + (None,) * len(ctx.names) + tuple(gp)
         with torch.enable_grad():
             leaves = [t.detach().requires_grad_(True) for t in tensors]
             m = dict(zip(ctx.names, leaves))

@@ -51,7 +51,10 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
     a3 = a if a.dim() == 3 else a.unsqueeze(0)
     b3 = b if b.dim() == 3 else b.unsqueeze(0)
     batch = max(a3.shape[0], b3.shape[0])
-    a3, b3 = a3.contiguous(), b3.contiguous()
+    def rows_ok(t):      # a row-strided 2-D view (e.g. the first k columns of a padded K-major buffer) is used in place
+        return t.shape[0] == 1 and t.stride(2) == 1 and t.stride(1) % 4 == 0 and t.stride(1) >= t.shape[2] and t.data_ptr() % 16 == 0
+    a3 = a3 if rows_ok(a3) else a3.contiguous()
+    b3 = b3 if rows_ok(b3) else b3.contiguous()
     m, k = a3.shape[1:]
     n = b3.shape[1]
     if b3.shape[2] != k:
@@ -63,7 +66,7 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
     g = L.GemmDesc()
     g.a, g.b, g.c = _ptr(a3), _ptr(b3), _ptr(o3)
     g.m, g.n, g.k, g.batch = m, n, k, batch
-    g.lda, g.ldb, g.ldc = k, k, o3.stride(1)
+    g.lda, g.ldb, g.ldc = a3.stride(1), b3.stride(1), o3.stride(1)
     g.a_batch_stride = m * k if a3.shape[0] > 1 else 0
     g.b_batch_stride = n * k if b3.shape[0] > 1 else 0
     g.c_batch_stride = o3.stride(0) if batch > 1 else 0

@@ -50,6 +50,7 @@ def parse():
                     help="graph: the step (mask draw + row pass + reduce + finish) is captured once per bag group in a CUDA "
                          "graph and replayed (falls back to eager launches if capture fails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the training-step comparison (N = 1 only)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the stock-PyTorch-on-this-GPU comparator (N = 1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-bag partial records travel: inside the kernels over peer memory, or NCCL")
@@ -182,6 +183,100 @@ def gpu_eager_rate(dev, n_rows, mode, steps=10, warmup=3):
                           f"(oracle/torch_port.py = the reference's op sequence)"}
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def train_step_rates(dev, n_rows, steps=12, warmup=4):
+    """One TRAINING step per bag (Step3_WSI_classification_ACMIL.py:188-221: forward, sub/slide cross-entropy + branch-diversity
+    loss, backward, AdamW) at N = n_rows, CUDA-event timed: ours (fused forward kernels, kernel backward of
+    acmil_b200.gp_backward, acmil_b200.losses.diversity_loss, the whole step replayed from one CUDA graph) next to the
+    reference's own op sequence in stock eager PyTorch on this GPU (fp32, TF32 off)."""
+    import torch.nn.functional as F
+    from acmil_b200 import ACMIL_GA, Struct
+    from acmil_b200.losses import diversity_loss
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev).manual_seed(5)
+    xs = [torch.randn(1, n_rows, D_FEAT, generator=g, device=dev) for _ in range(3)]
+    y = torch.tensor([1], device=dev)
+
+    def ref_loss(sub, slide, a):       # Step3_WSI_classification_ACMIL.py:201-216
+        p = torch.softmax(a, dim=-1)
+        d = sum(torch.cosine_similarity(p[:, i], p[:, j], dim=-1).mean() for i in range(K_BRANCH) for j in range(i + 1, K_BRANCH))
+        return F.cross_entropy(sub, y.repeat_interleave(K_BRANCH)) + F.cross_entropy(slide, y) + d / (K_BRANCH * (K_BRANCH - 1) / 2)
+
+    def ref_forward(m, x):             # transformer.py:305-330 with torch ops on the module's own parameters
+        h = F.relu(F.linear(x[0], m.dimreduction.fc1.weight))
+        gt = m.attention
+        a = F.linear(torch.tanh(gt.attention_V[0](h)) * torch.sigmoid(gt.attention_U[0](h)), gt.attention_weights.weight,
+                     gt.attention_weights.bias).t()
+        k, n = a.shape
+        _, idx = torch.topk(a, N_MASKED, dim=-1)
+        rsel = torch.argsort(torch.rand(k, N_MASKED, device=a.device), dim=-1)[:, :int(N_MASKED * MASK_DROP)]
+        mi = idx[torch.arange(k, device=a.device).unsqueeze(-1), rsel]
+        mask = torch.ones(k, n, device=a.device)
+        mask.scatter_(-1, mi, 0)
+        a = a.masked_fill(mask == 0, -1e9)
+        af = F.softmax(a, dim=1) @ h
+        sub = torch.stack([c.fc(af[i]) for i, c in enumerate(m.classifier)])
+        bag = torch.mm(F.softmax(a, dim=1).mean(0, keepdim=True), h)
+        return sub, m.Slide_classifier.fc(bag), a.unsqueeze(0)
+
+    def measure(ours):
+        torch.manual_seed(0)
+        conf = Struct(D_feat=D_FEAT, D_inner=D_INNER, n_class=N_CLASS, n_token=K_BRANCH)
+        m = ACMIL_GA(conf, n_token=K_BRANCH, n_masked_patch=N_MASKED, mask_drop=MASK_DROP).to(dev).train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-4, capturable=ours)
+        xin = torch.empty_like(xs[0])
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            if ours:
+                sub, slide, a = m(xin)
+                loss = F.cross_entropy(sub, y.repeat_interleave(K_BRANCH)) + F.cross_entropy(slide, y) + diversity_loss(a)
+            else:
+                loss = ref_loss(*ref_forward(m, xin))
+            loss.backward()
+            opt.step()
+
+        run, launch = step, "eager launches"
+        if ours:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    xin.copy_(xs[i % 3])
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                step()
+            run, launch = graph.replay, "one CUDA graph per step, replayed"
+        for i in range(warmup):
+            xin.copy_(xs[i % 3])
+            run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            xin.copy_(xs[i % 3])      # a fresh bag every step (device copy, inside the timed region for both arms)
+            run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ok = all(bool(torch.isfinite(p).all()) for p in m.parameters())
+        return e0.elapsed_time(e1) / steps, launch, ok
+
+    try:
+        ms_ours, launch, ok = measure(True)
+        ms_ref, _, _ = measure(False)
+        return {"ours_ms_per_step": ms_ours, "stock_pytorch_ms_per_step": ms_ref, "speedup": ms_ref / ms_ours,
+                "launch": launch, "weights_finite": ok,
+                "what": f"forward + CE/diversity loss + backward + AdamW on one bag of {n_rows}x{D_FEAT} fp32 per step "
+                        f"(Step3_WSI_classification_ACMIL.py:188-221), masking on; stock = the reference's op sequence in eager "
+                        f"PyTorch on this GPU, TF32 off"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_ours(a):
@@ -526,6 +621,11 @@ def run_ours(a):
         line["parity_ok"] = parity["parity_ok"]
     if eager is not None:
         line["gpu_eager_baseline"] = eager
+    if rank == 0 and world == 1 and not a.no_train_step:
+        try:
+            line["train_step"] = train_step_rates(dev, a.rows)
+        except Exception as exc:      # noqa: BLE001  (an extra: never take the headline line down with it)
+            line["train_step"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     if not a.no_cpu_baseline:
         rate, sec = cpu_port_rate(a.rows, 6, 2, a.mode)
         line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",

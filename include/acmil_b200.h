@@ -249,6 +249,53 @@ ACMIL_API int acmil_gp_attn_stats(const float* d_a, int64_t a_ld, int32_t n_bran
 ACMIL_API int acmil_softmax_rows(const float* d_a, int64_t a_ld, int32_t n_rows, int64_t n, float* d_out,
                        int64_t out_ld, void* stream);
 
+/* ---- backward of the pool (recompute-based; Step3_WSI_classification_ACMIL.py:216-221 loss.backward()) ------------
+ * The products over the hidden widths and over the N rows run on acmil_gemm_nt (acmil_transmil.h); these entry points
+ * are the row-local kernels between them (csrc/gp_bwd.cu has the formulas).  One bag per call.
+ *   z        [n, zc]  gate pre-activations, bias included: V units [0, d_attn), U units [d_attn, 2 d_attn) when gated
+ *   scores   [K, n]   the forward's raw scores (-1e9 at the masked positions), leading dimension a_ld
+ *   lse_m/l  [K]      softmax statistics of the forward (acmil_gp_outputs.lse_m / lse_l)
+ *   g_afeat  [K, d_inner] / g_bag [d_inner] / g_scores [K, n] (ld gs_ld): upstream gradients, each may be NULL
+ * outputs: dz [n, zc], dzt [zc, ldt] (transposed copy, ldt >= n), dhp [n, d_inner] (pool-path gradient of h),
+ *   small [KMAX * d_attn + KMAX + 2 * d_attn] = dWw rows (row k at k * d_attn) | dbw | column sums of dz;
+ *   partials: workspace of acmil_gp_bwd_workspace_floats() floats. */
+typedef struct acmil_gp_bwd_gate_args {
+  const float* d_h;
+  const float* d_z;
+  const float* d_scores;
+  const float* d_lse_m;
+  const float* d_lse_l;
+  const float* d_afeat;
+  const float* d_g_afeat;
+  const float* d_g_bag;
+  const float* d_g_scores;
+  const float* d_ww;
+  int64_t n, a_ld, gs_ld, ldt;
+  int32_t d_inner, d_attn, n_branch, act_a, gated, reserved;
+  float* d_dz;
+  float* d_dzt;
+  float* d_dhp;
+  float* d_partials;
+  float* d_small;
+} acmil_gp_bwd_gate_args;
+ACMIL_API int acmil_gp_bwd_workspace_floats(int32_t d_inner, int64_t* gate_floats, int64_t* relu_floats);
+ACMIL_API int acmil_gp_bwd_gate(const acmil_gp_bwd_gate_args* args, void* stream);
+/* dz1 = dh * [h > 0] (row-major copy optional: d_dz1 may be NULL), dz1t [d_inner, ldt] its transpose, db1 [d_inner] the
+ * column sums (relu front layer, network.py:49-57). */
+ACMIL_API int acmil_gp_bwd_relu_mask(const float* d_dh, const float* d_h, int64_t n, int32_t d_inner, float* d_dz1, float* d_dz1t,
+                                     int64_t ldt, float* d_partials, float* d_db1, void* stream);
+/* out[c * ldo + r] = x[r * ldx + c] */
+ACMIL_API int acmil_transpose_f32(const float* d_x, int64_t ldx, int64_t rows, int32_t cols, float* d_out, int64_t ldo, void* stream);
+
+/* Branch-diversity loss of the training loop (Step3_WSI_classification_ACMIL.py:208-214) on the [K, n] score matrix of ONE
+ * bag: div = mean over branch pairs of cos(softmax(A_i), softmax(A_j)).  fwd writes ml [2 * ACMIL_MAX_BRANCH + 1] (the softmax
+ * statistics m, then l, then one word of scratch), gram [ACMIL_MAX_BRANCH^2] (P P^T) and the loss; bwd writes ds = g_out * d div / d A ([K, n], ld ds_ld;
+ * g_out is a DEVICE scalar: the upstream gradient).  Masked positions (-1e9) get a zero gradient like masked_fill's. */
+ACMIL_API int acmil_div_loss_fwd(const float* d_a, int64_t a_ld, int32_t n_branch, int64_t n, float* d_ml, float* d_gram, float* d_div,
+                                 void* stream);
+ACMIL_API int acmil_div_loss_bwd(const float* d_a, int64_t a_ld, int32_t n_branch, int64_t n, const float* d_ml, const float* d_gram,
+                                 const float* d_g_out, float* d_ds, int64_t ds_ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

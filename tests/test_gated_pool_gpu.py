@@ -528,3 +528,127 @@ def test_in_kernel_exchange_matches_unsharded(ranks, impl):
                 close(o.scores[:, lo[s]:lo[s + 1]], full.scores[:, off[s] + b[s][r]: off[s] + b[s][r + 1]].cpu().numpy(),
                       rtol=1e-6, atol=1e-7)
         assert all(int(xc.state[0]) == step + 1 for xc in xch)      # every rank's epoch advanced once per step
+
+
+def _grad_close(name, got, ref, strict=True):
+    """strict: every entry within 2e-3 of the tensor's largest entry.  Not strict (the two sides computed the front layer
+    independently): a pre-activation within rounding distance of the ReLU's kink (|z| ~ 1e-5) may fall on the other side,
+    which moves single entries of dz1 by their whole value and with them one row of dx / dW1 -- both answers are valid
+    subgradients -- so only the tensor-level l2 error is bounded (5e-3)."""
+    d = (got - ref).abs()
+    if strict:
+        err = float(d.max()) / (float(ref.abs().max()) + 1e-30)
+        assert err < 2e-3, (name, err)
+    else:
+        l2 = float(d.norm()) / (float(ref.norm()) + 1e-30)
+        assert l2 < 5e-3, (name, l2)
+
+
+@pytest.mark.parametrize("case", [
+    dict(d_in=384, d_inner=128, K=5, n=2999, masked=True),                                   # ACMIL_GA, n % 4 != 0
+    dict(d_in=384, d_inner=128, K=1, n=1024),                                                # ABMIL
+    dict(d_in=512, d_inner=256, K=3, n=1500, front_bias=True),                               # CLAM_MB-like (Linear + bias)
+    dict(d_in=512, d_inner=256, K=1, n=801, front_bias=True, gated=False),                   # CLAM_SB(gate=False)
+    dict(d_in=1024, d_inner=512, K=1, n=700, front_bias=True, act_a="gelu", biases=False),   # attmil.AttentionGated
+    dict(d_in=1024, d_inner=512, K=2, n=640, act_a="relu"),
+])
+def test_pool_backward_kernels_match_autograd(case):
+    """acmil_b200.gp_backward (tcgen05 GEMMs + csrc/gp_bwd.cu) against torch autograd of the same graph written with
+    torch ops in fp32 (TF32 off), for every gate flavour of the family; gradients w.r.t. all weights and x."""
+    import torch.nn.functional as F
+    from acmil_b200 import gp_backward as B
+    from acmil_b200.gated_pool import GatedPool, GatedPoolSpec
+    torch.backends.cuda.matmul.allow_tf32 = False
+    d_in, Li, K, n = case["d_in"], case["d_inner"], case["K"], case["n"]
+    gated, act_a, fb, biases = case.get("gated", True), case.get("act_a", "tanh"), case.get("front_bias", False), case.get("biases", True)
+    spec = GatedPoolSpec(d_in=d_in, d_inner=Li, n_branch=K, front_bias=fb, act_a=act_a, gated=gated, gate_bias=biases,
+                         score_bias=biases)
+    assert B.supported(spec)
+    g = torch.Generator().manual_seed(1000 + n)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).cuda()      # noqa: E731
+    w = dict(w1=rnd(Li, d_in, scale=d_in ** -0.5), b1=rnd(Li, scale=0.1) if fb else None, wv=rnd(128, Li, scale=Li ** -0.5),
+             bv=rnd(128, scale=0.1) if biases else None, wu=rnd(128, Li, scale=Li ** -0.5) if gated else None,
+             bu=rnd(128, scale=0.1) if (gated and biases) else None, ww=rnd(K, 128, scale=0.3),
+             bw=rnd(K, scale=0.1) if biases else None)
+    x = rnd(n, d_in)
+    op = GatedPool(spec)
+    packed = op.pack(w["w1"], w["b1"], w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
+    n_masked, keep, rand = (10, [6], torch.rand(1, K, 10, generator=g).cuda()) if case.get("masked") else (0, [0], None)
+    res = op.run(packed, x, [0, n], n_masked=n_masked, keep=keep, rand=rand)
+    g_afeat, g_bag, g_scores = rnd(K, Li), rnd(1, Li), rnd(K, n, scale=1e-3)
+    dbg = {}
+    got = B.pool_backward(spec, x, {k: v for k, v in w.items() if v is not None}, res.scores, res.lse_m[0], res.lse_l[0],
+                          res.afeat[0], g_afeat, g_bag, g_scores, need_dx=True, _debug=dbg)
+    # the same graph with torch ops.  The ReLU of the front layer uses the kernels' own sign pattern: a pre-activation
+    # within rounding distance of 0 (a handful of the n * d_inner entries) may otherwise fall on either side of the kink
+    leaves = {k: v.clone().requires_grad_(True) for k, v in w.items() if v is not None}
+    xr = x.clone().requires_grad_(True)
+    z1 = F.linear(xr, leaves["w1"], leaves.get("b1"))
+    flipped = z1.detach()[(dbg["h"] > 0) != (z1.detach() > 0)]
+    assert flipped.numel() <= max(3, int(1e-5 * z1.numel())) and (flipped.numel() == 0 or float(flipped.abs().max()) < 1e-4)
+    close(dbg["h"], F.relu(z1).detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    h = z1 * (dbg["h"] > 0)
+    zv = F.linear(h, leaves["wv"], leaves.get("bv"))
+    a = torch.tanh(zv) if act_a == "tanh" else (F.relu(zv) if act_a == "relu" else F.gelu(zv))
+    if gated:
+        a = a * torch.sigmoid(F.linear(h, leaves["wu"], leaves.get("bu")))
+    s = F.linear(a, leaves["ww"], leaves.get("bw")).t()
+    s = s.masked_fill(res.scores == -1e9, -1e9)
+    close(res.scores, s.detach().cpu().numpy(), rtol=1e-3, atol=1e-5)
+    af = torch.softmax(s, 1) @ h
+    outs = [af, af.mean(0, keepdim=True), s]
+    names = list(leaves)
+    ref = torch.autograd.grad(outs, [xr] + [leaves[k] for k in names], [g_afeat, g_bag, g_scores])
+    for k, r in zip(["x"] + names, ref):
+        assert got[k].shape == r.shape, k
+        _grad_close(k, got[k], r)
+
+
+def test_acmil_training_step_kernel_vs_torch_backward(monkeypatch):
+    """A full training step through the module (forward kernels + kernel backward + AdamW) gives the same updated weights
+    as the same step with the torch-op backward (ACMIL_POOL_BACKWARD=torch)."""
+    import torch.nn.functional as F
+    x = torch.randn(1, 4000, 384, generator=torch.Generator().manual_seed(8)).cuda()
+    y = torch.tensor([1], device="cuda")
+    results = []
+    for mode in ("kernel", "torch"):
+        monkeypatch.setenv("ACMIL_POOL_BACKWARD", mode)
+        m = _random_acmil(33).cuda().train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+        torch.manual_seed(5)
+        sub, slide, a = m(x)
+        p = torch.softmax(a, dim=-1)
+        d = sum(torch.cosine_similarity(p[:, i], p[:, j], dim=-1).mean() for i in range(5) for j in range(i + 1, 5)) / 10
+        (F.cross_entropy(sub, y.repeat_interleave(5)) + F.cross_entropy(slide, y) + d).backward()
+        results.append({k: v.grad.clone() for k, v in m.named_parameters()})
+        opt.step()
+    # (the score bias' gradient is zero up to rounding -- softmax is shift-invariant -- so errors are measured against the
+    # largest gradient of the step where a tensor's own norm is negligible)
+    top = max(float(v.norm()) for v in results[1].values())
+    for k in results[0]:
+        ref = results[1][k]
+        l2 = float((results[0][k] - ref).norm()) / max(float(ref.norm()), 1e-4 * top)
+        assert l2 < 5e-3, (k, l2)
+
+
+@pytest.mark.parametrize("K,n", [(5, 50000), (2, 777), (8, 4096)])
+def test_diversity_loss_matches_the_training_script(K, n):
+    """acmil_b200.losses.diversity_loss against Step3_WSI_classification_ACMIL.py:208-214 spelled with torch ops: value and
+    gradient w.r.t. the raw scores, with masked (-1e9) entries."""
+    from acmil_b200.losses import diversity_loss
+    g = torch.Generator().manual_seed(K * 1000 + n)
+    a = (torch.randn(1, K, n, generator=g) * 2).cuda()
+    a[0, :, 5] = -1e9
+    a[0, 0, 11] = -1e9
+    a1 = a.clone().requires_grad_(True)
+    p = torch.softmax(a1, dim=-1)
+    ref = sum(torch.cosine_similarity(p[:, i], p[:, j], dim=-1).mean() / (K * (K - 1) / 2) for i in range(K) for j in range(i + 1, K))
+    (3.0 * ref).backward()
+    a2 = a.clone().requires_grad_(True)
+    mine = diversity_loss(a2)
+    (3.0 * mine).backward()
+    assert abs(float(mine) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    err = float((a2.grad - a1.grad).abs().max()) / (float(a1.grad.abs().max()) + 1e-30)
+    assert err < 1e-3, err
+    assert float(a2.grad[0, :, 5].abs().max()) == 0.0
+    assert float(diversity_loss(a[:, :1])) == 0.0      # one branch: the reference's double loop is empty
