@@ -257,6 +257,7 @@ static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, 
   }
   const GpExchange* gxp = x ? &gx : nullptr;
   p.x = batch->d_x;
+  p.x_f16 = batch->x_f16 != 0;
   p.a_out = batch->d_a_out;
   p.a_ld = batch->a_ld;
   p.pack = reinterpret_cast<const float*>(d_packed);

@@ -220,6 +220,7 @@ struct GpMainParams {
   GpSegTable seg;
   // FFMA kernel as the rescue pass of the tcgen05 kernel: only the bags with rescue_flags[s] == 1 are processed
   const int* rescue_flags;
+  int x_f16;              // x holds fp16 rows (acmil_gp_batch.x_f16)
 };
 
 // which bags a reduce launch handles, by the tcgen05 kernel's per-bag overflow flag

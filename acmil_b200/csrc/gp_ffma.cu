@@ -12,9 +12,20 @@
 //
 // Masked rows are decided later (gp_reduce.cu) from the candidate lists, so nothing is ever
 // subtracted: rows that turn out not to be masked are added back exactly.
+#include <cuda_fp16.h>
+
 #include "gp_common.cuh"
 
 namespace {
+
+// four consecutive x values at element offset `off` of the tile: fp32 rows, or fp16 rows widened on load
+__device__ __forceinline__ float4 load_x4(const float* __restrict__ xf, const __half* __restrict__ xh, size_t off) {
+  if (xh == nullptr) return __ldg(reinterpret_cast<const float4*>(xf + off));
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(xh + off));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 
 constexpr int FR = 64;    // rows per tile
 constexpr int FKC = 32;   // k chunk
@@ -163,7 +174,9 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
   for (int t = t0; t < t1; ++t) {
     const int64_t trow = (int64_t)t * FR;  // first row of the tile inside the bag
     const int valid = (int)min((int64_t)FR, n_rows - trow);
-    const float* __restrict__ xt = p.x + (size_t)(row0_bag + trow) * DIN;
+    // fp32 rows, or fp16 rows widened on load (exact)
+    const float* __restrict__ xt = p.x_f16 ? nullptr : p.x + (size_t)(row0_bag + trow) * DIN;
+    const __half* __restrict__ xth = p.x_f16 ? reinterpret_cast<const __half*>(p.x) + (size_t)(row0_bag + trow) * DIN : nullptr;
 
     // ================= stage 1: h tile =================
     if (p.sh.front) {
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
             const int idx = tid + FT * i;
             const int r = idx >> 3, kq = idx & 7;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < valid) v = __ldg(reinterpret_cast<const float4*>(xt + (size_t)r * DIN + kc * FKC + kq * 4));
+            if (r < valid) v = load_x4(xt, xth, (size_t)r * DIN + kc * FKC + kq * 4);
             *reinterpret_cast<float4*>(sm.xs + r * XLD + kq * 4) = v;
           }
           load_w_chunk(sm.ws, w1t, L, kc * FKC, nb * FNB, tid);
@@ -200,7 +213,7 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
       for (int idx = tid; idx < FR * (L / 4); idx += FT) {
         const int r = idx / (L / 4), c4 = idx % (L / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid) v = __ldg(reinterpret_cast<const float4*>(xt + (size_t)r * DIN + c4 * 4));
+        if (r < valid) v = load_x4(xt, xth, (size_t)r * DIN + c4 * 4);
         *reinterpret_cast<float4*>(sm.hs + r * ldh + c4 * 4) = v;
       }
     }

@@ -102,7 +102,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
   // SWIZZLE_128B operand tiles need a 1024-byte aligned base (same offset in both CTAs of the pair)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int DIN = p.mp.sh.d_in;
-  const int NCH = DIN / KC;
+  // fp32 rows: 32-column chunks (128 B per row), split into hi / lo halves by the converters; fp16 rows (x_f16): the
+  // tile IS the hi operand and lo == 0, so a chunk is 64 columns (the same 128 B per row) and its x_lo MMAs are skipped
+  const bool XH = p.mp.x_f16 != 0;
+  const int NCH = XH ? DIN / 64 : DIN / KC;
   const SmemMap sm = smem_map(DIN, KB);
   Bars* bars = reinterpret_cast<Bars*>(smem + sm.bars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
           const uint32_t st = ctr % NSTAGE, ph = (ctr / NSTAGE) & 1u;
           { PROF_T0(); mbar_wait(&bars->empty_x[st], ph ^ 1u); PROF_ADD(0); }
           mbar_expect_tx(&bars->full_x[st], STAGE_BYTES);
-          tma_load_2d_hint(smem + sm.stage + st * STAGE_BYTES, &p.tmap, c * KC, (int)grow, &bars->full_x[st], kEvictFirst);
+          tma_load_2d_hint(smem + sm.stage + st * STAGE_BYTES, &p.tmap, c * (XH ? 64 : KC), (int)grow, &bars->full_x[st], kEvictFirst);
         }
       }
       PROF_FLUSH(0);
@@ -208,7 +211,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         tc_fence_after();
         const uint32_t xa_hi = tm + TM_X + q * 32, xa_lo = xa_hi + 16;
         const uint32_t boff = (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 64u;
-        if (elect_one()) {
+        if (XH) {      // fp16 rows: chunk c = W1 k-block c, four k-steps of 16, hi operand only
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t bo = (uint32_t)c * 8192u + (uint32_t)ks * 32u;
+              const uint64_t bhi = umma_desc_k_sw128(w1_hi + bo), blo = umma_desc_k_sw128(w1_lo + bo);
+              umma_ts<2>(tm + TM_DH + (uint32_t)(t & 1) * 128u, xa_hi + ks * 8, bhi, idesc, (c | ks) ? 1u : 0u);
+              umma_ts<2>(tm + TM_DH + (uint32_t)(t & 1) * 128u, xa_hi + ks * 8, blo, idesc, 1u);
+            }
+            umma_commit_2sm(&bars->xop_empty[q], 3);
+            if (c == NCH - 1) umma_commit_2sm(&bars->d1_full[t & 1], 3);
+          }
+        } else if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t bhi = umma_desc_k_sw128(w1_hi + boff + ks * 32), blo = umma_desc_k_sw128(w1_lo + boff + ks * 32);
@@ -429,10 +444,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(rowp + ((i ^ (r & 7)) << 4));
         uint32_t hi[16], lo[16];
+        if (XH) {      // the 128 bytes are 64 halves = the packed operand columns as they are (de-swizzled): no arithmetic
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          split2(v[i].x, v[i].y, hi[2 * i], lo[2 * i]);
-          split2(v[i].z, v[i].w, hi[2 * i + 1], lo[2 * i + 1]);
+          for (int i = 0; i < 4; ++i) {
+            hi[4 * i] = __float_as_uint(v[i].x); hi[4 * i + 1] = __float_as_uint(v[i].y);
+            hi[4 * i + 2] = __float_as_uint(v[i].z); hi[4 * i + 3] = __float_as_uint(v[i].w);
+            lo[4 * i] = __float_as_uint(v[4 + i].x); lo[4 * i + 1] = __float_as_uint(v[4 + i].y);
+            lo[4 * i + 2] = __float_as_uint(v[4 + i].z); lo[4 * i + 3] = __float_as_uint(v[4 + i].w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            split2(v[i].x, v[i].y, hi[2 * i], lo[2 * i]);
+            split2(v[i].z, v[i].w, hi[2 * i + 1], lo[2 * i + 1]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->empty_x[st]);   // staging slot may be refilled
@@ -1318,11 +1343,12 @@ int gp_launch_main_umma(const GpMainParams& p, const acmil_gp_consts* consts, co
   ACMIL_REQUIRE(enc != nullptr, ACMIL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const int64_t rows = p.seg.row_off[p.seg.n_slides];
   cuuint64_t dims[2] = {(cuuint64_t)s.d_in, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)s.d_in * 4};
-  cuuint32_t box[2] = {KC, 128};
+  cuuint64_t strides[1] = {(cuuint64_t)s.d_in * (p.x_f16 ? 2 : 4)};
+  cuuint32_t box[2] = {p.x_f16 ? 64u : (cuuint32_t)KC, 128};      // 128 bytes per row either way
   cuuint32_t es[2] = {1, 1};
   ACMIL_REQUIRE(((uintptr_t)p.x & 15) == 0, ACMIL_E_INVALID, "x must be 16-byte aligned for TMA");
-  const CUresult r = enc(&up.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.x), dims, strides, box, es,
+  const CUresult r = enc(&up.tmap, p.x_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<float*>(p.x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);

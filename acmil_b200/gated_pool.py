@@ -116,8 +116,9 @@ class GatedPool:
         lib = L.load()
         sp = self.spec
         _require_cuda(x, "x")
-        if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != sp.d_in:
-            raise ValueError(f"x must be a contiguous fp32 [R, {sp.d_in}] tensor")
+        if x.dtype not in (torch.float32, torch.float16) or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != sp.d_in:
+            raise ValueError(f"x must be a contiguous fp32 (or fp16: the H5 storage dtype, widened exactly inside the kernels) "
+                             f"[R, {sp.d_in}] tensor")
         dev = x.device
         S = len(row_offsets) - 1
         R = int(row_offsets[-1])
@@ -127,7 +128,7 @@ class GatedPool:
         off = (C.c_int64 * (S + 1))(*[int(v) for v in row_offsets])
         sb = (C.c_int64 * max(S, 1))(*[int(v) for v in shard_begin]) if shard_begin is not None else None
         scores = torch.empty((sp.n_branch, max(R, 1)), dtype=torch.float32, device=dev) if want_scores else None
-        batch = L.GpBatch(_ptr(x), off, S, int(n_masked), sb, _ptr(scores), max(R, 1))
+        batch = L.GpBatch(_ptr(x), off, S, int(n_masked), sb, _ptr(scores), max(R, 1), int(x.dtype == torch.float16), 0)
         ws_b, part_b = C.c_size_t(0), C.c_size_t(0)
         L.check(lib.acmil_gp_sizes(C.byref(self._shape), C.byref(batch), impl, C.byref(ws_b), C.byref(part_b)))
         ws = self._buf("ws", ws_b.value, dev)

@@ -111,7 +111,7 @@ class _PoolFn(torch.autograd.Function):
         with torch.enable_grad():
             leaves = [t.detach().requires_grad_(True) for t in tensors]
             m = dict(zip(ctx.names, leaves))
-            xin = x.detach().requires_grad_(x.requires_grad)
+            xin = x.detach().float().requires_grad_(x.requires_grad)
             h = xin
             if spec.front:
                 z = F.linear(xin, m["w1"], m.get("b1"))
@@ -160,7 +160,8 @@ class _GatedPoolModule(nn.Module):
                                "(the CPU reference lives in the upstream repository, not here)")
         w = self._weights()
         op: GatedPool = self._op
-        x2d = x2d.to(torch.float32).contiguous()
+        # fp16 features (the dtype the reference stores them in) go to the kernels as they are: widening is exact
+        x2d = (x2d if x2d.dtype == torch.float16 else x2d.to(torch.float32)).contiguous()
         n = x2d.shape[0]
 
         def runner(xin):
@@ -365,7 +366,7 @@ class ACMIL_GA(_GatedPoolModule):
         S = len(row_offsets) - 1
         sizes = [int(row_offsets[i + 1] - row_offsets[i]) for i in range(S)] if n_total is None else [int(v) for v in n_total]
         use_mask = self.training and self.n_masked_patch > 0
-        n_masked, keep, rand = 0, [0] * S, None
+        n_masked, keep = 0, [0] * S
         if use_mask:
             if self.n_masked_patch > L.MAX_MASKED:
                 raise ValueError(f"n_masked_patch > {L.MAX_MASKED} is not supported by the kernels")
@@ -384,8 +385,8 @@ class ACMIL_GA(_GatedPoolModule):
         w = self._weights()
         op = self._op
         packed = op.pack(w.get("w1"), w.get("b1"), w["wv"], w.get("bv"), w.get("wu"), w.get("bu"), w["ww"], w.get("bw"))
-        res = op.run(packed, x_cat.to(torch.float32).contiguous(), [int(v) for v in row_offsets], n_masked=n_masked, keep=keep,
-                     rand=rand if n_masked else None,
+        res = op.run(packed, (x_cat if x_cat.dtype == torch.float16 else x_cat.to(torch.float32)).contiguous(), [int(v) for v in row_offsets], n_masked=n_masked, keep=keep,
+                     rand=rand if (n_masked and use_mask) else None,
                      branch_w=torch.stack([c.fc.weight for c in self.classifier]),
                      branch_b=torch.stack([c.fc.bias for c in self.classifier]),
                      head_w=self.Slide_classifier.fc.weight, head_b=self.Slide_classifier.fc.bias, slide_head=True,

@@ -50,12 +50,15 @@ def parse():
                     help="graph: the step (mask draw + row pass + reduce + finish) is captured once per bag group in a CUDA "
                          "graph and replayed (falls back to eager launches if capture fails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp16", action="store_true", help="skip the fp16-feature variant of the step (N = 1 only)")
     ap.add_argument("--no-train-step", action="store_true", help="skip the training-step comparison (N = 1 only)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the stock-PyTorch-on-this-GPU comparator (N = 1 only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-bag partial records travel: inside the kernels over peer memory, or NCCL")
-    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit", "resnet"],
+    ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit", "resnet", "stream"],
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
+    ap.add_argument("--stream-slides", type=int, default=398, help="stream: slides in the Camelyon16-shaped set")
+    ap.add_argument("--stream-scale", type=float, default=1 / 64, help="stream: patch-count scale (1 = 10k..100k patches per slide)")
     ap.add_argument("--dim", type=int, default=512, help="transmil: D_inner")
     ap.add_argument("--d-feat", type=int, default=512, help="transmil: D_feat")
     return ap.parse_args()
@@ -480,6 +483,45 @@ def run_ours(a):
         lib.acmil_prof_collect(C.byref(main_ms), C.byref(n_main))
         lib.acmil_prof_enable(0)
         clocks = sampler.stop() if rank == 0 else None
+        # ---- the same step on fp16 features (the dtype the reference stores them in, Step2_feature_extract.py:165; widening
+        # is exact, the kernels read the halves directly): reported next to the fp32 headline, with its own roofline
+        fp16_line = None
+        if world == 1 and not a.no_fp16:
+            g16 = [g.half() for g in groups]
+            def step16(i):
+                r = torch.rand(S, K_BRANCH, nm, device=dev) if masking else None
+                return op.run(packed, g16[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
+                              keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
+                              head_w=head_w, head_b=head_b, slide_head=True)
+            for i in range(max(a.warmup, 3)):
+                step16(i)
+            torch.cuda.synchronize()
+            lib.acmil_prof_enable(1)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(a.steps):
+                r16 = step16(i)
+            f1.record()
+            torch.cuda.synchronize()
+            k_ms, k_n = C.c_double(0), C.c_int64(0)
+            lib.acmil_prof_collect(C.byref(k_ms), C.byref(k_n))
+            lib.acmil_prof_enable(0)
+            ms16 = f0.elapsed_time(f1) / a.steps
+            kms16 = k_ms.value / max(k_n.value, 1)
+            bytes16 = (ALGO_BYTES_PER_SLIDE - N_ROWS * D_FEAT * 2) * (a.rows / N_ROWS) * a.slides
+            try:
+                peak16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+            except Exception:
+                peak16 = 6650.0
+            fp16_line = {"value": S / (ms16 * 1e-3), "unit": "slides/s", "ms_per_step": ms16, "launch": "eager launches",
+                         "roofline": {"bound": "hbm", "achieved": bytes16 / (kms16 * 1e-3) / 1e9, "peak": peak16, "unit": "GB/s",
+                                      "frac": bytes16 / (kms16 * 1e-3) / 1e9 / peak16, "kernel_ms": kms16,
+                                      "algorithmic_bytes_per_launch": bytes16},
+                         "max_abs_logit_diff_vs_fp32_of_same_values": float((r16.slide - op.run(
+                             packed, g16[(a.steps - 1) % a.groups].float(), offsets, n_masked=0, keep=[0] * S, branch_w=branch_w,
+                             branch_b=branch_b, head_w=head_w, head_b=head_b, slide_head=True).slide).abs().max()) if not masking else None,
+                         "note": "x_f16 = 1: fp16 rows read by TMA as the hi operand, no x_lo products, half the HBM bytes"}
+            del g16
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -559,7 +601,7 @@ def run_ours(a):
             if world == 1:
                 dt16 = timed_loop([h.half().pin_memory() for h in host], torch.float16, calls)
                 fp16 = {"value": n_e2e / dt16, "unit": "slides/s", "h2d_bytes_per_step": Se * n_loc * D_FEAT * 2,
-                        "note": "fp16 features in pinned host memory (the H5 storage dtype), cast to fp32 on the device"}
+                        "note": "fp16 features in pinned host memory (the H5 storage dtype), read by the kernels as they are (x_f16)"}
             e2e = {"value": n_e2e / dt, "unit": "slides/s", "fp16_features": fp16,
                    "h2d_bytes_per_step": Se * n_loc * D_FEAT * 4 * world,
                    "d2h_bytes_per_step": Se * N_CLASS * 4 * world,
@@ -621,6 +663,8 @@ def run_ours(a):
         line["parity_ok"] = parity["parity_ok"]
     if eager is not None:
         line["gpu_eager_baseline"] = eager
+    if fp16_line is not None:
+        line["fp16_features"] = fp16_line
     if rank == 0 and world == 1 and not a.no_train_step:
         try:
             line["train_step"] = train_step_rates(dev, a.rows)
@@ -638,7 +682,7 @@ def run_ours(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.workload in ("transmil", "vit", "resnet"):
+    if args.workload in ("transmil", "vit", "resnet", "stream"):
         mod = __import__("bench_" + ("vit" if args.workload == "resnet" else args.workload))
         if args.impl == "reference":
             mod.run_reference(args)

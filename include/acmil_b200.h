@@ -111,7 +111,7 @@ typedef struct acmil_gp_consts {
 
 /* One batch of bags on one device (one rank's row shard of each bag when sharded). */
 typedef struct acmil_gp_batch {
-  const float* d_x;            /* [R_total, d_in] fp32 */
+  const float* d_x;            /* [R_total, d_in] fp32 (or fp16, see x_f16) */
   const int64_t* row_offsets;  /* HOST [n_slides + 1], row_offsets[0] == 0 */
   int32_t n_slides;
   int32_t n_masked;            /* n_masked_patch requested (0 = eval / no masking) */
@@ -119,6 +119,12 @@ typedef struct acmil_gp_batch {
   const int64_t* shard_row_begin;  /* HOST [n_slides] or NULL */
   float* d_a_out;              /* [n_branch, a_ld] raw scores of the local rows (may be NULL) */
   int64_t a_ld;                /* leading dimension of d_a_out (>= R_total) */
+  /* 1: d_x points to IEEE fp16 rows ([R_total, d_in] halves) -- the dtype the reference stores features in
+   * (Step2_feature_extract.py:165) and widens before the model (Step3_WSI_classification_ACMIL.py:193).  fp16 -> fp32 is
+   * exact, so results equal those of the widened input; the kernels read half the bytes and the tcgen05 kernel skips
+   * the x_lo products (x_lo == 0). */
+  int32_t x_f16;
+  int32_t reserved;
 } acmil_gp_batch;
 
 /* Classifier heads applied by acmil_gp_finish (Classifier_1fc: nn.Linear [C, L]). */

@@ -652,3 +652,34 @@ def test_diversity_loss_matches_the_training_script(K, n):
     assert err < 1e-3, err
     assert float(a2.grad[0, :, 5].abs().max()) == 0.0
     assert float(diversity_loss(a[:, :1])) == 0.0      # one branch: the reference's double loop is empty
+
+
+@pytest.mark.parametrize("impl_name", ["umma", "ffma"])
+@pytest.mark.parametrize("train", [False, True])
+def test_fp16_rows_equal_widened_rows(impl_name, train):
+    """x_f16: the kernels read fp16 features (the reference's H5 storage dtype, Step2_feature_extract.py:165) directly.
+    Widening fp16 -> fp32 is exact, so every output must equal the one computed from the widened rows: masks identical,
+    scores / logits to rounding (the tcgen05 kernel sums hi products only: same values, other order)."""
+    import acmil_b200._lib as L
+    m = _random_acmil(41).cuda()
+    m._op.impl = L.IMPL_UMMA if impl_name == "umma" else L.IMPL_FFMA
+    g = torch.Generator().manual_seed(6)
+    sizes = [3000, 1, 4097]
+    x16 = torch.randn(sum(sizes), 384, generator=g).half().cuda()
+    off = [0, 3000, 3001, 3001 + 4097]
+    rand = torch.rand(3, 5, 10, generator=g).cuda()
+    m.train(train)
+    with torch.no_grad():
+        a = m.forward_bags(x16, off, rand=rand if train else None)
+        b = m.forward_bags(x16.float(), off, rand=rand if train else None)
+    for u, v in zip(a, b):
+        assert np.array_equal((u == -1e9).cpu().numpy(), (v == -1e9).cpu().numpy())
+        close(u, v.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    # through the single-bag module call too (autograd path in train mode is covered by the backward tests)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        s16 = m(x16[None, :3000])
+        torch.manual_seed(3)
+        s32 = m(x16[None, :3000].float())
+    for u, v in zip(s16, s32):
+        close(u, v.cpu().numpy(), rtol=1e-5, atol=2e-6)
