@@ -108,6 +108,19 @@ class NystromWeights(C.Structure):
                 ("d_wqkv", C.c_void_p), ("d_wout", C.c_void_p), ("d_bout", C.c_void_p), ("d_wconv", C.c_void_p)]
 
 
+class NystromShard(C.Structure):
+    """acmil_nystrom_shard (include/acmil_transmil.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_loc", "lead_zero", "dim", "heads", "dim_head", "num_landmarks", "m_loc", "group_len", "pinv_iterations", "residual",
+        "conv_kernel", "precise", "n_out", "head_first", "head_count", "halo")]
+
+
+class NystromShardBufs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_x", "d_residual", "d_out", "d_ql_loc", "d_kl_loc", "d_ql", "d_kl", "d_z", "d_kv_part", "d_st_m", "d_st_l", "d_kv",
+        "d_vt_ext", "d_workspace")] + [("workspace_bytes", C.c_size_t)]
+
+
 class VitShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "img", "patch", "in_ch", "dim", "depth", "heads", "mlp_dim", "n_class",
                                          "precise")] + [("ln_eps", C.c_float), ("reserved", C.c_int32 * 5)]
@@ -171,6 +184,13 @@ SYMBOLS = {
     "acmil_nystrom_attn_fwd": (C.c_int, [C.POINTER(NystromShape), C.POINTER(NystromWeights), C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "acmil_softmax_rows_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "acmil_nystrom_shard_workspace_bytes": (C.c_int, [C.POINTER(NystromShard), _SIZE_P]),
+    "acmil_nystrom_shard_phase": (C.c_int, [C.POINTER(NystromShard), C.POINTER(NystromWeights), C.POINTER(NystromShardBufs),
+                                            C.c_int32, C.c_void_p]),
+    "acmil_lse_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p]),
+    "acmil_ppeg_fwd_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "acmil_vit_workspace_bytes": (C.c_int, [C.POINTER(VitShape), _SIZE_P]),
     "acmil_vit_fwd": (C.c_int, [C.POINTER(VitShape), C.POINTER(VitWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),

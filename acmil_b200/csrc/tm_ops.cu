@@ -214,6 +214,34 @@ __global__ void __launch_bounds__(256) tm_resconv_kernel(const float* __restrict
   }
 }
 
+// same, for a sequence shard: v^T lives in a halo-extended buffer (column i) while merged holds the local rows only (row
+// i - shift); the halo columns carry the neighbours' values (zeros at the ends of the whole sequence)
+__global__ void __launch_bounds__(256) tm_resconv_shard_kernel(const float* __restrict__ vt, const float* __restrict__ w,
+                                                               float* __restrict__ merged, int n_ext, int inner, int d, int ks,
+                                                               int col0, int nrows, int shift) {
+  extern __shared__ float tile[];
+  const int half = ks / 2;
+  const int span = (CONV_TP + ks - 1) | 1;
+  const int i0 = col0 + blockIdx.x * CONV_TP, c0 = blockIdx.y * 32;
+  const float* vb = vt + (size_t)c0 * n_ext;
+  for (int e = threadIdx.x; e < 32 * (CONV_TP + ks - 1); e += 256) {
+    const int c = e / (CONV_TP + ks - 1), o = e % (CONV_TP + ks - 1);
+    const int i = i0 + o - half;
+    tile[c * span + o] = (c0 + c < inner && i >= 0 && i < n_ext) ? vb[(size_t)c * n_ext + i] : 0.f;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  if (c0 + cx >= inner) return;
+  const float* wh = w + (size_t)((c0 + cx) / d) * ks;
+  for (int o = py; o < CONV_TP; o += 8) {
+    const int i = i0 + o;
+    if (i >= col0 + nrows) break;
+    float acc = 0.f;
+    for (int t = 0; t < ks; ++t) acc = fmaf(__ldg(wh + t), tile[cx * span + o + t], acc);
+    merged[(size_t)(i - shift) * inner + c0 + cx] += acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // PPEG (transMIL.py:38-45): out = feat + conv7(feat) + conv5(feat) + conv3(feat) on the [gh, gw] token grid,
 // channels last.  The three depth-wise kernels and the identity are summed into one 7x7 stencil per channel
@@ -224,16 +252,17 @@ constexpr int PPEG_TX = 16, PPEG_TY = 8;
 __global__ void __launch_bounds__(256) tm_ppeg_kernel(const float* __restrict__ x, int gh, int gw, int C, const float* __restrict__ w7,
                                                       const float* __restrict__ b7, const float* __restrict__ w5,
                                                       const float* __restrict__ b5, const float* __restrict__ w3,
-                                                      const float* __restrict__ b3, float* __restrict__ out, int cblocks) {
+                                                      const float* __restrict__ b3, float* __restrict__ out, int cblocks,
+                                                      int y_first, int y_end) {      // grid rows [y_first, y_end) are produced
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.z % cblocks) * 32 + cx, bz = blockIdx.z / cblocks;
   const size_t tok = (size_t)gh * gw + 1;
   const float* xb = x + (size_t)bz * tok * C;
   float* ob = out + (size_t)bz * tok * C;
   if (c >= C) return;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && ty == 0) ob[c] = xb[c];      // class token passes through
-  const int y = blockIdx.y * PPEG_TY + ty, x0 = blockIdx.x * PPEG_TX;
-  if (y >= gh) return;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && ty == 0 && y_first == 0 && y_end == gh) ob[c] = xb[c];      // class token passes through
+  const int y = y_first + blockIdx.y * PPEG_TY + ty, x0 = blockIdx.x * PPEG_TX;
+  if (y >= y_end) return;
   float wk[49];
 #pragma unroll
   for (int dy = 0; dy < 7; ++dy)
@@ -355,7 +384,26 @@ extern "C" int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32
   const int cblocks = (c + 31) / 32;
   ACMIL_REQUIRE((long long)cblocks * batch <= 65535 && (gh + PPEG_TY - 1) / PPEG_TY <= 65535, ACMIL_E_INVALID, "ppeg: grid too large");
   dim3 grid((gw + PPEG_TX - 1) / PPEG_TX, (gh + PPEG_TY - 1) / PPEG_TY, cblocks * batch);
-  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, cblocks);
+  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, cblocks, 0, gh);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+// grid rows [y_first, y_first + ny) of ONE sequence only (the class token row is not touched): the sharded TransMIL keeps a
+// full-size token buffer per rank in which only its own rows and a 3-grid-row halo are valid
+extern "C" int acmil_ppeg_fwd_rows(const float* d_x, int32_t gh, int32_t gw, int32_t c, const float* d_w7, const float* d_b7,
+                                   const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3, float* d_out,
+                                   int32_t y_first, int32_t ny, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_x && d_out && d_w7 && d_b7 && d_w5 && d_b5 && d_w3 && d_b3, ACMIL_E_INVALID, "ppeg: null pointer");
+  ACMIL_REQUIRE(gh >= 1 && gw >= 1 && c >= 1 && y_first >= 0 && ny >= 0 && y_first + ny <= gh, ACMIL_E_INVALID, "ppeg rows: bad shape");
+  if (ny == 0) return ACMIL_OK;
+  const int cblocks = (c + 31) / 32;
+  ACMIL_REQUIRE(cblocks <= 65535 && (ny + PPEG_TY - 1) / PPEG_TY <= 65535, ACMIL_E_INVALID, "ppeg: grid too large");
+  dim3 grid((gw + PPEG_TX - 1) / PPEG_TX, (ny + PPEG_TY - 1) / PPEG_TY, cblocks);
+  tm_ppeg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, gh, gw, c, d_w7, d_b7, d_w5, d_b5, d_w3, d_b3, d_out, cblocks, y_first,
+                                                         y_first + ny);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
@@ -532,6 +580,288 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     if (d_residual && !s.padded_out) {
       g.addend = d_residual + (size_t)b * s.n * dim; g.ld_addend = dim; g.beta = 1.f;
     }
+    TM_RUN(tm_gemm(g, st));
+  }
+  return ACMIL_OK;
+}
+
+// ==========================================================================================
+// Sequence-parallel NystromAttention (BASELINE.json configs[2]: "bag sharded 1 -> 8 B200").
+// The padded sequence is cut at landmark-group boundaries: rank p owns groups [p m / P, (p + 1) m / P) = n_loc = m_loc l
+// consecutive rows (rank 0's begin with the front zero padding).  Everything proportional to the sequence length is local;
+// what crosses ranks is small and goes through the caller (torch.distributed / peer copies) BETWEEN the phases below:
+//   phase A  LN, q / k / v of the local rows, local landmark means        -> all-gather q_l, k_l   [H, m, d]  (1 MB)
+//   phase B  attn2 = softmax(q_l k_l^T) of all heads (the start value of the pseudo-inverse needs the maxima over every
+//            head), Moore-Penrose iterations for heads [head_first, +count) -> all-gather pinv       [H, m, m]  (2 MB)
+//   phase C  local scores q_l k_loc^T, exp against the LOCAL row maximum, (exp v) partial sums + (max, sum) per row
+//                                                                          -> all-gather partials   [H, m, d + 2]
+//            acmil_lse_merge: kv = sum_p e^(m_p - M) part_p / sum_p e^(m_p - M) l_p  (= attn3 v of the whole sequence)
+//   phase D  W = pinv kv, attn1 of the local rows, out = attn1 W + depth-wise conv of v (16-row halo of v from both
+//            neighbours, exchanged by the caller into vt_ext) -> to_out (+ bias, + residual) for the local rows
+namespace {
+
+struct ShardLayout {
+  size_t xn, q, k, a2, y, yt, t1t, t2t, za, zta, zb, ztb, sbuf, wt, merged, split, scal, total;
+  int inner, ksplit, n_ext;
+};
+
+ShardLayout shard_layout(const acmil_nystrom_shard& s) {
+  ShardLayout L{};
+  L.inner = s.heads * s.dim_head;
+  L.n_ext = s.n_loc + 2 * s.halo;
+  const size_t H = s.heads, d = s.dim_head, m = s.num_landmarks, nl = s.n_loc;
+  L.ksplit = (int)std::max<size_t>(1, std::min<size_t>(64, (nl / 32) / 48));
+  size_t o = 0;
+  auto take = [&](size_t n) { const size_t r = o; o += align64(n); return r; };
+  L.xn = take(nl * s.dim);
+  L.q = take(H * nl * d);
+  L.k = take(H * nl * d);
+  const size_t mm = H * m * m;
+  L.a2 = take(mm); L.y = take(mm); L.yt = take(mm); L.t1t = take(mm); L.t2t = take(mm);
+  L.za = take(mm); L.zta = take(mm); L.zb = take(mm); L.ztb = take(mm);
+  L.sbuf = take(H * nl * m);
+  L.wt = take(H * d * m);
+  L.merged = take(nl * (size_t)L.inner);
+  L.split = take((size_t)L.ksplit * H * d * m);
+  L.scal = take(64);
+  L.total = o;
+  return L;
+}
+
+int shard_check(const acmil_nystrom_shard& s) {
+  ACMIL_REQUIRE(s.n_loc >= 1 && s.dim >= 4 && s.dim % 4 == 0 && s.heads >= 1 && s.dim_head >= 4 && s.dim_head % 4 == 0, ACMIL_E_INVALID,
+                "nystrom shard: bad shape");
+  ACMIL_REQUIRE(s.num_landmarks >= 4 && s.num_landmarks % 4 == 0 && s.num_landmarks <= 1024 && s.m_loc >= 1 &&
+                    s.group_len >= 1 && s.n_loc == s.m_loc * s.group_len && s.n_loc % 4 == 0,
+                ACMIL_E_INVALID, "nystrom shard: n_loc must be m_loc * group_len and a multiple of 4");
+  ACMIL_REQUIRE(s.lead_zero >= 0 && s.lead_zero < s.n_loc && s.n_out >= 0 && s.n_out <= s.n_loc - s.lead_zero, ACMIL_E_INVALID,
+                "nystrom shard: bad lead_zero / n_out");
+  ACMIL_REQUIRE(s.head_first >= 0 && s.head_count >= 0 && s.head_first + s.head_count <= s.heads, ACMIL_E_INVALID, "nystrom shard: bad head range");
+  ACMIL_REQUIRE(!s.residual || (s.conv_kernel % 2 == 1 && s.halo == s.conv_kernel / 2 && s.halo % 4 == 0), ACMIL_E_INVALID,
+                "nystrom shard: halo must be conv_kernel / 2 and a multiple of 4");
+  return ACMIL_OK;
+}
+
+// exp(a - rowmax) in place + (rowmax, rowsum): the local part of a softmax over a sequence that is spread over ranks
+__global__ void __launch_bounds__(1024) tm_softmax_partial_kernel(float* __restrict__ a, long long len, float* __restrict__ st_m,
+                                                                  float* __restrict__ st_l) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  float* r = a + (size_t)blockIdx.x * len;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (long long j = tid; j < len; j += 1024) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_max(red[lane]);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  mx = bc;
+  float s = 0.f;
+  for (long long j = tid; j < len; j += 1024) {
+    const float e = expf(r[j] - mx);
+    r[j] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_sum(red[lane]);
+    if (lane == 0) { st_m[blockIdx.x] = mx; st_l[blockIdx.x] = t; }
+  }
+}
+
+// kv[h][c][j] = sum_p e^(m_p[h][j] - M) part_p[h][c][j] / sum_p e^(m_p[h][j] - M) l_p[h][j]
+__global__ void __launch_bounds__(256) tm_lse_merge_kernel(const float* __restrict__ parts, const float* __restrict__ st_m,
+                                                           const float* __restrict__ st_l, int P, int H, int d, int m,
+                                                           float* __restrict__ kv) {
+  const size_t total = (size_t)H * d * m;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int j = (int)(e % m), h = (int)(e / ((size_t)d * m));
+    const size_t row = (size_t)h * m + j;
+    float M = -INFINITY;
+    for (int p = 0; p < P; ++p) M = fmaxf(M, st_m[(size_t)p * H * m + row]);
+    float num = 0.f, den = 0.f;
+    for (int p = 0; p < P; ++p) {
+      const float w = expf(st_m[(size_t)p * H * m + row] - M);
+      num = fmaf(w, parts[(size_t)p * total + e], num);
+      den = fmaf(w, st_l[(size_t)p * H * m + row], den);
+    }
+    kv[e] = num / den;
+  }
+}
+
+}  // namespace
+
+extern "C" int acmil_nystrom_shard_workspace_bytes(const acmil_nystrom_shard* shard, size_t* bytes) {
+  ACMIL_REQUIRE(shard && bytes, ACMIL_E_INVALID, "nystrom shard: null argument");
+  const int rc = shard_check(*shard);
+  if (rc) return rc;
+  *bytes = shard_layout(*shard).total * sizeof(float);
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_lse_merge(const float* d_parts, const float* d_st_m, const float* d_st_l, int32_t n_ranks, int32_t heads,
+                               int32_t dim_head, int32_t num_landmarks, float* d_kv, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_parts && d_st_m && d_st_l && d_kv && n_ranks >= 1 && heads >= 1 && dim_head >= 1 && num_landmarks >= 1, ACMIL_E_INVALID,
+                "lse_merge: bad argument");
+  const size_t total = (size_t)heads * dim_head * num_landmarks;
+  tm_lse_merge_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 1184), 256, 0, (cudaStream_t)stream>>>(
+      d_parts, d_st_m, d_st_l, n_ranks, heads, dim_head, num_landmarks, d_kv);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_nystrom_shard_phase(const acmil_nystrom_shard* shard, const acmil_nystrom_weights* w,
+                                         const acmil_nystrom_shard_bufs* bufs, int32_t phase, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(shard && w && bufs && bufs->d_workspace, ACMIL_E_INVALID, "nystrom shard: null argument");
+  const acmil_nystrom_shard& s = *shard;
+  const acmil_nystrom_shard_bufs& b = *bufs;
+  TM_RUN(shard_check(s));
+  const ShardLayout L = shard_layout(s);
+  ACMIL_REQUIRE(b.workspace_bytes >= L.total * sizeof(float), ACMIL_E_WORKSPACE, "nystrom shard: workspace %zu < %zu bytes",
+                b.workspace_bytes, L.total * sizeof(float));
+  ACMIL_REQUIRE(((uintptr_t)b.d_workspace & 255) == 0, ACMIL_E_INVALID, "nystrom shard: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(b.d_workspace);
+  const int m = s.num_landmarks, d = s.dim_head, H = s.heads, nl = s.n_loc, inner = L.inner, dim = s.dim, P = s.precise;
+  const int n_real = nl - s.lead_zero, n_ext = L.n_ext;
+  float *xn = ws + L.xn, *q = ws + L.q, *k = ws + L.k, *sbuf = ws + L.sbuf, *a2 = ws + L.a2;
+  const int64_t mm = (int64_t)m * m;
+  if (phase == 0) {
+    ACMIL_REQUIRE(b.d_x && b.d_ql_loc && b.d_kl_loc && b.d_vt_ext && w->d_wqkv, ACMIL_E_INVALID, "nystrom shard phase A: null buffer");
+    if (s.lead_zero) ACMIL_CHECK_CUDA(cudaMemsetAsync(xn, 0, (size_t)s.lead_zero * dim * sizeof(float), st));
+    TM_RUN(acmil_layernorm_rows(b.d_x, dim, n_real, dim, w->d_ln_w, w->d_ln_b, w->ln_eps, xn + (size_t)s.lead_zero * dim, dim, stream));
+    acmil_gemm_desc g = gemm0(P);
+    g.a = xn; g.lda = dim; g.m = nl; g.k = dim; g.batch = 1;
+    g.b = w->d_wqkv; g.ldb = dim; g.n = inner;
+    g.c = q; g.ldc = d; g.col_block_width = d; g.col_block_stride = (int64_t)nl * d;
+    g.alpha = 1.f / sqrtf((float)d);
+    TM_RUN(tm_gemm(g, st));
+    g.b = w->d_wqkv + (size_t)inner * dim; g.c = k; g.alpha = 1.f;
+    TM_RUN(tm_gemm(g, st));
+    acmil_gemm_desc gv = gemm0(P);      // v^T straight into the halo-extended buffer
+    gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
+    gv.b = xn; gv.ldb = dim; gv.n = nl;
+    gv.c = b.d_vt_ext + s.halo; gv.ldc = n_ext;
+    TM_RUN(tm_gemm(gv, st));
+    dim3 grid(s.m_loc, H);
+    tm_landmark_kernel<<<grid, 256, 0, st>>>(q, b.d_ql_loc, nl, s.m_loc, s.group_len, d);
+    tm_landmark_kernel<<<grid, 256, 0, st>>>(k, b.d_kl_loc, nl, s.m_loc, s.group_len, d);
+    g_acmil_launches += 2;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    return ACMIL_OK;
+  }
+  if (phase == 1) {
+    ACMIL_REQUIRE(b.d_ql && b.d_kl && b.d_z, ACMIL_E_INVALID, "nystrom shard phase B: null buffer");
+    acmil_gemm_desc g = gemm0(P);
+    g.a = b.d_ql; g.lda = d; g.a_batch_stride = (int64_t)m * d; g.m = m; g.k = d; g.batch = H;
+    g.b = b.d_kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
+    g.c = a2; g.ldc = m; g.c_batch_stride = mm;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_small_launch(a2, (long long)H * m, m, m, st);
+    ++g_acmil_launches;
+    if (s.head_count == 0) return ACMIL_OK;
+    float *z = ws + L.za, *zt = ws + L.zta, *z2 = ws + L.zb, *zt2 = ws + L.ztb;
+    int* scal = reinterpret_cast<int*>(ws + L.scal);
+    ACMIL_CHECK_CUDA(cudaMemsetAsync(scal, 0, 8, st));
+    tm_pinv_sums_kernel<<<dim3(H, 2), 256, 0, st>>>(a2, m, scal);      // maxima over ALL heads (torch.max of the tensor)
+    const int hc = s.head_count;
+    const float* a2h = a2 + (size_t)s.head_first * mm;
+    tm_pinv_init_kernel<<<dim3((m + 31) / 32, (m + 31) / 32, hc), 256, 0, st>>>(a2h, m, scal, z, zt);
+    g_acmil_launches += 2;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    float *y = ws + L.y, *yt = ws + L.yt, *t1t = ws + L.t1t, *t2t = ws + L.t2t;
+    auto sq = [&](const float* A, const float* Bt, float* C, float* Ct, float alpha, const float* add, float beta) {
+      acmil_gemm_desc g2 = gemm0(P);
+      g2.a = A; g2.lda = m; g2.a_batch_stride = mm; g2.m = m; g2.k = m; g2.batch = hc;
+      g2.b = Bt; g2.ldb = m; g2.b_batch_stride = mm; g2.n = m;
+      g2.c = C; g2.ldc = m; g2.c_batch_stride = mm;
+      g2.ct = Ct; g2.ldct = m; g2.ct_batch_stride = mm;
+      g2.alpha = alpha; g2.addend = add; g2.ld_addend = m; g2.addend_batch_stride = mm; g2.beta = beta;
+      return tm_gemm(g2, st);
+    };
+    for (int it = 0; it < s.pinv_iterations; ++it) {
+      TM_RUN(sq(a2h, zt, y, yt, 1.f, nullptr, 0.f));
+      TM_RUN(sq(y, yt, nullptr, t1t, -1.f, y, 7.f));
+      TM_RUN(sq(y, t1t, nullptr, t2t, -1.f, y, 15.f));
+      TM_RUN(sq(z, t2t, z2, zt2, -0.25f, z, 3.25f));
+      std::swap(z, z2);
+      std::swap(zt, zt2);
+    }
+    ACMIL_CHECK_CUDA(cudaMemcpyAsync(b.d_z + (size_t)s.head_first * mm, z, (size_t)hc * mm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return ACMIL_OK;
+  }
+  if (phase == 2) {
+    ACMIL_REQUIRE(b.d_ql && b.d_kv_part && b.d_st_m && b.d_st_l && b.d_vt_ext, ACMIL_E_INVALID, "nystrom shard phase C: null buffer");
+    acmil_gemm_desc g = gemm0(P);
+    g.a = b.d_ql; g.lda = d; g.a_batch_stride = (int64_t)m * d; g.m = m; g.k = d; g.batch = H;
+    g.b = k; g.ldb = d; g.b_batch_stride = (int64_t)nl * d; g.n = nl;
+    g.c = sbuf; g.ldc = nl; g.c_batch_stride = (int64_t)m * nl;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_partial_kernel<<<(unsigned)((size_t)H * m), 1024, 0, st>>>(sbuf, nl, b.d_st_m, b.d_st_l);
+    ++g_acmil_launches;
+    acmil_gemm_desc g2 = gemm0(P);
+    g2.a = b.d_vt_ext + s.halo; g2.lda = n_ext; g2.a_batch_stride = (int64_t)d * n_ext; g2.m = d; g2.k = nl; g2.batch = H;
+    g2.b = sbuf; g2.ldb = nl; g2.b_batch_stride = (int64_t)m * nl; g2.n = m;
+    g2.c = b.d_kv_part; g2.ldc = m; g2.c_batch_stride = (int64_t)d * m;
+    g2.k_split = L.ksplit; g2.split_ws = ws + L.split;
+    TM_RUN(tm_gemm(g2, st));
+    return ACMIL_OK;
+  }
+  ACMIL_REQUIRE(phase == 3, ACMIL_E_INVALID, "nystrom shard: phase must be 0..3");
+  ACMIL_REQUIRE(b.d_kl && b.d_z && b.d_kv && b.d_vt_ext && b.d_out && w->d_wout && w->d_bout && (!s.residual || w->d_wconv),
+                ACMIL_E_INVALID, "nystrom shard phase D: null buffer");
+  {
+    acmil_gemm_desc g = gemm0(P);      // W^T = (attn3 v)^T pinv^T
+    g.a = b.d_kv; g.lda = m; g.a_batch_stride = (int64_t)d * m; g.m = d; g.k = m; g.batch = H;
+    g.b = b.d_z; g.ldb = m; g.b_batch_stride = mm; g.n = m;
+    g.c = ws + L.wt; g.ldc = m; g.c_batch_stride = (int64_t)d * m;
+    TM_RUN(tm_gemm(g, st));
+  }
+  const int r0 = s.lead_zero;
+  const int nr = s.n_out > 0 ? s.n_out : n_real;
+  float* merged = ws + L.merged;
+  {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = q + (size_t)r0 * d; g.lda = d; g.a_batch_stride = (int64_t)nl * d; g.m = nr; g.k = d; g.batch = H;
+    g.b = b.d_kl; g.ldb = d; g.b_batch_stride = (int64_t)m * d; g.n = m;
+    g.c = sbuf; g.ldc = m; g.c_batch_stride = (int64_t)nr * m;
+    TM_RUN(tm_gemm(g, st));
+    tm_softmax_small_launch(sbuf, (long long)H * nr, m, m, st);
+    ++g_acmil_launches;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+    acmil_gemm_desc g2 = gemm0(P);
+    g2.a = sbuf; g2.lda = m; g2.a_batch_stride = (int64_t)nr * m; g2.m = nr; g2.k = m; g2.batch = H;
+    g2.b = ws + L.wt; g2.ldb = m; g2.b_batch_stride = (int64_t)d * m; g2.n = d;
+    g2.c = merged + (size_t)r0 * inner; g2.ldc = inner; g2.c_batch_stride = d;
+    TM_RUN(tm_gemm(g2, st));
+  }
+  if (s.residual) {
+    // the conv kernel indexes merged rows and vt columns with the same i: view merged as starting `halo` rows earlier so
+    // that row (halo + r) of the view = local row r = column (halo + r) of vt_ext (the first `halo` view rows are never touched)
+    const int ks = s.conv_kernel;
+    const size_t smem = (size_t)32 * ((CONV_TP + ks - 1) | 1) * sizeof(float);
+    dim3 grid((nr + CONV_TP - 1) / CONV_TP, (inner + 31) / 32, 1);
+    tm_resconv_shard_kernel<<<grid, 256, smem, st>>>(b.d_vt_ext, w->d_wconv, merged, n_ext, inner, d, ks, s.halo + r0, nr, s.halo);
+    ++g_acmil_launches;
+    ACMIL_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    acmil_gemm_desc g = gemm0(P);
+    g.a = merged + (size_t)r0 * inner; g.lda = inner; g.m = nr; g.k = inner; g.batch = 1;
+    g.b = w->d_wout; g.ldb = inner; g.n = dim;
+    g.bias = w->d_bout;
+    g.c = b.d_out; g.ldc = dim;
+    if (b.d_residual) { g.addend = b.d_residual; g.ld_addend = dim; g.beta = 1.f; }
     TM_RUN(tm_gemm(g, st));
   }
   return ACMIL_OK;

@@ -108,6 +108,51 @@ ACMIL_API int acmil_ppeg_fwd(const float* d_x, int32_t batch, int32_t gh, int32_
                              const float* d_b7, const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3,
                              float* d_out, void* stream);
 
+/* ---- sequence-parallel NystromAttention: one rank's share of a padded sequence cut at landmark-group boundaries
+ * (csrc/tm_ops.cu has the phase list; acmil_b200/transmil_sharded.py drives it and does the exchanges).  batch = 1. */
+typedef struct acmil_nystrom_shard {
+  int32_t n_loc;            /* rows of the padded sequence on this rank = m_loc * group_len (multiple of 4) */
+  int32_t lead_zero;        /* leading all-zero rows (the front padding of nystrom_attention.py:72-80: rank 0 only) */
+  int32_t dim, heads, dim_head;
+  int32_t num_landmarks;    /* m of the whole sequence */
+  int32_t m_loc;            /* landmark groups on this rank */
+  int32_t group_len;        /* l = n_pad / m */
+  int32_t pinv_iterations, residual, conv_kernel, precise;
+  int32_t n_out;            /* phase D produces the first n_out real rows (0 = all n_loc - lead_zero) */
+  int32_t head_first, head_count;   /* heads whose pseudo-inverse this rank iterates in phase B */
+  int32_t halo;             /* conv_kernel / 2 columns on both sides of d_vt_ext */
+} acmil_nystrom_shard;
+
+typedef struct acmil_nystrom_shard_bufs {
+  const float* d_x;         /* [n_loc - lead_zero, dim] local real rows */
+  const float* d_residual;  /* [rows produced, dim] or NULL */
+  float* d_out;             /* [rows produced, dim] */
+  float* d_ql_loc;          /* phase A out: [heads, m_loc, dim_head] local landmark means of q (scaled) */
+  float* d_kl_loc;          /* ... and of k */
+  const float* d_ql;        /* [heads, m, dim_head] landmarks of the whole sequence (phases B, C) */
+  const float* d_kl;        /* (phases B, D) */
+  float* d_z;               /* [heads, m, m] pseudo-inverse: phase B writes its heads, phase D reads all */
+  float* d_kv_part;         /* phase C out: [heads, dim_head, m] sum_n exp(s - max_loc) v */
+  float* d_st_m;            /* phase C out: [heads * m] local row maxima */
+  float* d_st_l;            /* phase C out: [heads * m] local row sums of exp */
+  const float* d_kv;        /* phase D in: [heads, dim_head, m] = (attn3 v)^T of the whole sequence (acmil_lse_merge) */
+  float* d_vt_ext;          /* [heads * dim_head, n_loc + 2 * halo]: phase A writes the middle, the caller the halos */
+  void* d_workspace;
+  size_t workspace_bytes;
+} acmil_nystrom_shard_bufs;
+
+ACMIL_API int acmil_nystrom_shard_workspace_bytes(const acmil_nystrom_shard* shard, size_t* bytes);
+/* phase 0..3 = A..D */
+ACMIL_API int acmil_nystrom_shard_phase(const acmil_nystrom_shard* shard, const acmil_nystrom_weights* w,
+                                        const acmil_nystrom_shard_bufs* bufs, int32_t phase, void* stream);
+/* kv = sum_p e^(m_p - M) parts_p / sum_p e^(m_p - M) l_p with parts [n_ranks][heads, dim_head, m], st_m / st_l [n_ranks][heads * m] */
+ACMIL_API int acmil_lse_merge(const float* d_parts, const float* d_st_m, const float* d_st_l, int32_t n_ranks, int32_t heads,
+                              int32_t dim_head, int32_t num_landmarks, float* d_kv, void* stream);
+/* acmil_ppeg_fwd restricted to grid rows [y_first, y_first + ny) of one sequence; the class-token row is left alone. */
+ACMIL_API int acmil_ppeg_fwd_rows(const float* d_x, int32_t gh, int32_t gw, int32_t c, const float* d_w7, const float* d_b7,
+                                  const float* d_w5, const float* d_b5, const float* d_w3, const float* d_b3, float* d_out,
+                                  int32_t y_first, int32_t ny, void* stream);
+
 /* in-place softmax over `rows` rows of length len <= 1024 stored with leading dimension ld. */
 ACMIL_API int acmil_softmax_rows_inplace(float* d_a, int64_t ld, int64_t rows, int32_t len, void* stream);
 

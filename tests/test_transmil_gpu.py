@@ -212,3 +212,43 @@ def test_forward_only_and_cuda_only_errors():
     att = NystromAttention(64, dim_head=8, heads=8, num_landmarks=32).to(dev())
     with pytest.raises(NotImplementedError), torch.no_grad():
         att(torch.randn(1, 40, 64, device=dev()), mask=torch.ones(1, 40, dtype=torch.bool, device=dev()))
+
+
+def _sharded_logits(mod, x, world):
+    """TransMIL over `world` ranks played by threads on this GPU (ThreadComm): the per-rank code of the multi-GPU path."""
+    from acmil_b200.transmil_sharded import ShardPlan, run_threads, transmil_forward_sharded
+    n = x.shape[1]
+    plan = ShardPlan(n, world, mod.layer1.attn.num_landmarks)
+
+    def rank_fn(rank, comm):
+        rows = torch.from_numpy(plan.patch_rows(rank)).to(x.device)
+        return transmil_forward_sharded(mod, x[0].index_select(0, rows), n, rank, comm)
+
+    return run_threads(world, rank_fn)
+
+
+@pytest.mark.parametrize("d_inner,n,world", [(64, 300, 2), (64, 1000, 4), (128, 1000, 8), (64, 50, 1)])
+def test_transmil_sharded_equals_unsharded(d_inner, n, world):
+    """Sequence-parallel TransMIL (landmark-aligned shards, log-sum-exp merge of attn3 v, pinv heads split over the ranks,
+    conv / PPEG halos) against the single-GPU forward of the same module: every rank returns the same logits."""
+    from acmil_b200 import Struct
+    from acmil_b200.transmil import TransMIL
+    torch.manual_seed(17)
+    mod = TransMIL(Struct(D_feat=48, D_inner=d_inner, n_class=3)).to(dev()).eval()
+    x = torch.randn(1, n, 48, generator=torch.Generator().manual_seed(n)).to(dev())
+    with torch.no_grad():
+        ref = mod(x)
+    outs = _sharded_logits(mod, x, world)
+    for y in outs:
+        np.testing.assert_allclose(y.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_transmil_sharded_c3_full_size_against_the_reference():
+    """BASELINE.json configs[2] as written: N = 50 000, dim 512, 256 landmarks, the bag sharded over 8 ranks -- against the
+    logits of the reference itself (tests/golden/seeded_transmil_c3_n50000.npz)."""
+    _, meta = load_golden("seeded_transmil_c3_n50000")
+    mod = _seeded_transmil(meta).to(dev())
+    x = golden_x(meta).to(dev())
+    outs = _sharded_logits(mod, x, 8)
+    for y in outs:
+        np.testing.assert_allclose(y.cpu().numpy(), meta["out"], rtol=1e-3, atol=1e-4)
