@@ -59,6 +59,7 @@ def parse():
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
     ap.add_argument("--stream-slides", type=int, default=398, help="stream: slides in the Camelyon16-shaped set")
     ap.add_argument("--stream-scale", type=float, default=1 / 64, help="stream: patch-count scale (1 = 10k..100k patches per slide)")
+    ap.add_argument("--transmil-replicas", action="store_true", help="transmil at N > 1: independent replicas instead of one sharded bag")
     ap.add_argument("--dim", type=int, default=512, help="transmil: D_inner")
     ap.add_argument("--d-feat", type=int, default=512, help="transmil: D_feat")
     return ap.parse_args()

@@ -6,7 +6,11 @@ resident in HBM (one slide per step, rotating bags larger than L2 in total), `ro
 `achieved` = useful FLOPs of the formulation that runs (2 M N K per product, the 3xTF32 split NOT counted) over the
 CUDA-event time, `peak` = MEASURED_PEAKS.json bf16 sustained TFLOP/s, `e2e` = TransMIL.forward from pinned host
 memory with the logits read back, `cpu_baseline` = oracle/torch_port.transmil_forward on the host cores.
-N > 1: independent replicas (one slide per rank per step; the sequence-parallel sharding of SURVEY 8e is not built).
+N > 1: the bag is SHARDED over the ranks (acmil_b200/transmil_sharded.py: landmark-aligned sequence shards, all-gathers of the
+landmarks / pseudo-inverse heads / attn3 v partial sums over NCCL, conv and PPEG halos between neighbours): one slide per step
+on all GPUs together, so the total work per step is fixed ("scaling": "strong"); `--transmil-replicas` runs N independent
+replicas instead (one slide per rank per step, "weak").  Every sharded run first checks its logits against the unsharded
+forward of the same bag on rank 0 (`parity`).
 """
 import json
 import math
@@ -93,8 +97,34 @@ def run_ours(a, ClockSampler):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = TransMIL(Struct(D_feat=a.d_feat, D_inner=a.dim, n_class=2)).to(dev).eval()
-    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    sharded = world > 1 and not getattr(a, "transmil_replicas", False)
+    gen = torch.Generator(device=dev).manual_seed(99 + (0 if sharded else rank))
     bags = [torch.randn(1, a.rows, a.d_feat, device=dev, generator=gen) for _ in range(3)]
+    parity = None
+    if sharded:
+        from acmil_b200.transmil_sharded import DistComm, ShardPlan, transmil_forward_sharded
+        comm = DistComm()
+        plan = ShardPlan(a.rows, world, model.layer1.attn.num_landmarks)
+        rows = torch.from_numpy(plan.patch_rows(rank)).to(dev)
+        whole = bags                      # every rank drew the same bags (same seed): rank-local rows are a slice of them
+        bags = [b[0].index_select(0, rows) for b in whole]
+        full_forward = model.forward
+
+        def sharded_forward(x_rows):
+            return transmil_forward_sharded(model, x_rows, a.rows, rank, comm)
+
+        with torch.no_grad():
+            y_sh = sharded_forward(bags[0])
+            y_ref = full_forward(whole[0])
+            err = float(((y_sh - y_ref).abs() / (y_ref.abs() + 1e-4)).max())
+        t = torch.tensor([err], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = {"parity_ok": bool(t.item() < 1e-3), "logits_max_rel_err": float(t.item()),
+                  "what": "bag sharded over the ranks versus the whole bag on one GPU, same weights and rows"}
+        del whole
+        model_call = sharded_forward
+    else:
+        model_call = model
 
     def barrier():
         if world > 1:
@@ -103,10 +133,10 @@ def run_ours(a, ClockSampler):
 
     with torch.no_grad():
         for i in range(max(a.warmup, 3)):
-            y = model(bags[i % 3])
+            y = model_call(bags[i % 3])
         barrier()
         l0 = _lib.launch_count()
-        model(bags[0])
+        model_call(bags[0])
         torch.cuda.synchronize()
         launches = _lib.launch_count() - l0
         sampler = ClockSampler(local)
@@ -117,7 +147,7 @@ def run_ours(a, ClockSampler):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(a.steps):
-            y = model(bags[i % 3])
+            y = model_call(bags[i % 3])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -127,12 +157,16 @@ def run_ours(a, ClockSampler):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         checksum = float(y.sum().item())
-        host = [torch.randn(1, a.rows, a.d_feat).pin_memory() for _ in range(2)]
-        xdev = torch.empty(1, a.rows, a.d_feat, device=dev)
+        if sharded:      # every rank feeds its own rows of the bag from pinned host memory
+            host = [torch.randn(bags[0].shape).pin_memory() for _ in range(2)]
+            xdev = torch.empty(bags[0].shape, device=dev)
+        else:
+            host = [torch.randn(1, a.rows, a.d_feat).pin_memory() for _ in range(2)]
+            xdev = torch.empty(1, a.rows, a.d_feat, device=dev)
 
         def user_call(i):
             xdev.copy_(host[i % 2], non_blocking=True)
-            return model(xdev).cpu()
+            return model_call(xdev).cpu()
 
         user_call(0)
         barrier()
@@ -158,12 +192,13 @@ def run_ours(a, ClockSampler):
     peak = float(peaks.get("bf16_tflops_sustained", 1345.7))
     flops = transmil_flops(a.rows, a.d_feat, a.dim)
     sec = ms * 1e-3 / a.steps
-    achieved = flops / sec / 1e12
+    achieved = flops / sec / 1e12 / (world if sharded else 1)      # per GPU
     line = {
-        "metric": "slides/sec (TransMIL, N=50k, D=512)", "value": world * a.steps / (ms * 1e-3), "unit": "slides/s",
+        "metric": "slides/sec (TransMIL, N=50k, D=512)", "value": (1 if sharded else world) * a.steps / (ms * 1e-3), "unit": "slides/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products)", "data": "synthetic",
-        "config": config(a, world),
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products)", "data": "synthetic",
+        "config": dict(config(a, world), parallelism=(f"one bag sharded over {world} GPUs (sequence-parallel Nystrom, NCCL exchanges)"
+                                                       if sharded else config(a, world).get("parallelism"))),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "whole forward (tm_gemm_kernel dominates)",
                      "algorithmic_flops_per_slide": flops,
@@ -172,11 +207,13 @@ def run_ours(a, ClockSampler):
                                     "; the fp32-faithful 3xTF32 split costs 6 bf16-equivalent MMAs per product, so 1/6 of"
                                     " this peak is the ceiling of the formulation"},
         "clocks": clocks,
-        "e2e": {"value": world * n_e2e / dt, "unit": "slides/s", "h2d_bytes_per_step": world * a.rows * a.d_feat * 4,
+        "e2e": {"value": (1 if sharded else world) * n_e2e / dt, "unit": "slides/s", "h2d_bytes_per_step": (1 if sharded else world) * a.rows * a.d_feat * 4,
                 "d2h_bytes_per_step": world * 2 * 4, "api": "TransMIL.forward(x[1,N,D]) from pinned host memory, logits .cpu()",
                 "bags": n_e2e},
         "gpu_launches": int(launches * a.steps), "checksum": checksum,
     }
+    if parity is not None:
+        line["parity"] = parity
     if not a.no_cpu_baseline:
         rate, s1 = cpu_rate(a.rows, a.d_feat, a.dim, 2, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "slides/s", "cores": torch.get_num_threads(), "kind": "port",
