@@ -1,6 +1,7 @@
 // C-ABI entry points (include/acmil_b200.h).  No torch types, no exceptions, caller-owned memory.
 #include <stdarg.h>
 
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -14,7 +15,7 @@ int gp_umma_pack(const acmil_gp_shape& s, const acmil_gp_weights& w, unsigned ch
 int gp_umma_build_plan(const acmil_gp_batch& b, int sm_count, GpSegTable* t);
 
 static thread_local char g_err[512] = "";
-int64_t g_acmil_launches = 0;
+std::atomic<int64_t> g_acmil_launches{0};
 
 void acmil_set_error(const char* fmt, ...) {
   va_list ap;
@@ -27,18 +28,24 @@ void acmil_set_error(const char* fmt, ...) {
 
 namespace {
 
+// row-pass timing for bench.py (acmil_prof_enable / acmil_prof_collect): a diagnostic, guarded by a mutex so that host
+// threads driving different streams cannot corrupt the event pool
 struct ProfState {
+  std::mutex mu;
   bool on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
   size_t used = 0;
 } g_prof;
 
+// SM count of the CURRENT device (cached per device ordinal: a process may drive several GPUs)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -131,9 +138,10 @@ int acmil_device_count(void) {
   }
   return n;
 }
-int64_t acmil_launch_count(void) { return g_acmil_launches; }
+int64_t acmil_launch_count(void) { return g_acmil_launches.load(); }
 
 int acmil_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.on = on != 0;
   if (!on) g_prof.used = 0;
   return ACMIL_OK;
@@ -141,6 +149,7 @@ int acmil_prof_enable(int on) {
 
 int acmil_prof_collect(double* main_ms_sum, int64_t* n_launches) {
   double sum = 0.0;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   for (size_t i = 0; i < g_prof.used; ++i) {
     ACMIL_CHECK_CUDA(cudaEventSynchronize(g_prof.pool[i].second));
     float ms = 0.f;
@@ -266,6 +275,7 @@ static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, 
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
     if (g_prof.used == g_prof.pool.size()) {
       ACMIL_CHECK_CUDA(cudaEventCreate(&e0));
       ACMIL_CHECK_CUDA(cudaEventCreate(&e1));

@@ -16,7 +16,8 @@
 
 // ----------------------------------------------------------------------------- errors
 void acmil_set_error(const char* fmt, ...);
-extern int64_t g_acmil_launches;
+#include <atomic>
+extern std::atomic<int64_t> g_acmil_launches;      // kernels launched by this process (any host thread)
 
 #define ACMIL_CHECK_CUDA(expr)                                                          \
   do {                                                                                  \

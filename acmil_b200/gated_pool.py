@@ -98,6 +98,12 @@ class GatedPool:
         self._keepalive = keep
         return packed
 
+    def invalidate(self) -> None:
+        """Forget the packed weights.  The cache key is (storage pointer, in-place version, shape) of every weight tensor:
+        optimizer steps, ``load_state_dict`` and ``copy_`` bump the version, but writes through ``param.data`` (EMA / manual
+        weight surgery, as in the reference's attmil initialiser) do not -- call this after such a write."""
+        self._packed = self._packed_key = None
+
     def _buf(self, name: str, nbytes: int, dev) -> torch.Tensor:
         b = self._bufs.get((name, dev))
         if b is None or b.numel() < nbytes:

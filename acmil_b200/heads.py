@@ -152,6 +152,11 @@ class _GatedPoolModule(nn.Module):
     def _weights(self):  # -> ordered dict name -> tensor or None (nn.Linear layout)
         raise NotImplementedError
 
+    def invalidate_packed_weights(self) -> None:
+        """Call after writing weights through ``param.data`` (which does not bump the tensor version the packed-weight cache
+        keys on); optimizer steps, ``load_state_dict`` and in-place ops on the parameter itself are picked up automatically."""
+        self._op.invalidate()
+
     def _pool(self, x2d: torch.Tensor, *, n_masked=0, keep=0, rsel=None, branch=None, head=None,
               slide_head=False, shared_head=False, rand=None):
         """x2d [N, d_in] -> GatedPoolResult for one bag, differentiable w.r.t. params (and x)."""
