@@ -1,7 +1,8 @@
 """Feature-extraction loop of the reference (Step2_feature_extract.py:35-71, 164-167) on the GPU:
 uint8 RGB patches -> Resize(224) + ToTensor + Normalize (one kernel, byte-exact with Pillow) -> encoder -> features,
-stored as fp16 like the reference's H5 writer.  Slide reading (openslide) and the H5 container (h5py) are outside the
-hot path and absent from this image: ``extract_feature`` takes the decoded patches; ``store_features`` needs h5py.
+stored as fp16 like the reference's H5 writer.  Slide reading (openslide) is outside the hot path and absent from this image:
+``extract_feature`` takes the decoded patches.  The H5 container: ``store_features`` mirrors the reference's h5py calls (for
+an open h5py file); ``acmil_b200.h5bag.write_bags`` / ``H5BagFile`` write and read the same layout without h5py.
 """
 from __future__ import annotations
 
