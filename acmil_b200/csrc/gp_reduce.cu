@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float red[RR / 32];
   __shared__ int sel_pos[NMAX];
-  __shared__ int s_nsel;
+  __shared__ int s_nsel, s_nlive;
+  __shared__ float r_s[RR / 32];
+  __shared__ int r_i[RR / 32], r_p[RR / 32];
 
   const int L = p.sh.d_inner, K = p.sh.n_branch;
   const int k = blockIdx.x % K, s = blockIdx.x / K;
@@ -139,14 +141,14 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   const int hoff = k * p.seg.h_branch_stride;      // first h slot of this branch inside a holder
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cb0 = seg0 / cdiv, ncb = nseg / cdiv;      // candidate holders of this bag
-  const int ncand = ncb * nm;
+  const int ncap = ncb * nm;                           // candidate slots of this (bag, branch); the live ones are compacted below
   const int nq = L / 4;                                // float4 groups per row (<= 128 for L <= 512)
 
   float* c_score = reinterpret_cast<float*>(dsm);
-  int* c_idx = reinterpret_cast<int*>(c_score + ncand);
-  int* c_slot = c_idx + ncand;
-  int* c_sel = c_slot + ncand;
-  float4* wacc = reinterpret_cast<float4*>(dsm + (((size_t)ncand * 16 + 15) / 16) * 16);   // [32 warps][nq]
+  int* c_idx = reinterpret_cast<int*>(c_score + ncap);
+  int* c_slot = c_idx + ncap;
+  int* c_sel = c_slot + ncap;                          // holder index << 1 | selected
+  float4* wacc = reinterpret_cast<float4*>(dsm + (((size_t)ncap * 16 + 15) / 16) * 16);   // [32 warps][nq]
 
   const float* part = reinterpret_cast<const float*>(p.ws + p.wl.part);
   const int* g_cnt = reinterpret_cast<const int*>(p.ws + p.wl.cand_cnt);
@@ -155,54 +157,39 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   const int* g_slot = reinterpret_cast<const int*>(p.ws + p.wl.cand_slot);
   const float* g_h = reinterpret_cast<const float*>(p.ws + p.wl.cand_h);
 
-  // ---- 1. candidates of this (bag, branch) -> smem; reference point m* = max over everything ----
+  // ---- 1. live candidates of this (bag, branch) -> smem, compacted (most holder slots are empty: the row pass keeps
+  // only what can still be in the bag's top n); reference point m* = max over everything ----
+  if (tid == 0) s_nlive = 0;
+  __syncthreads();
   float mx = -INFINITY;
-  for (int c = tid; c < ncand; c += RR) {
+  for (int c = tid; c < ncap; c += RR) {
     const int sg = c / nm, i = c % nm;
     const size_t g = ((size_t)(cb0 + sg) * K + k) * cap + i;
-    const bool live = i < g_cnt[(size_t)(cb0 + sg) * K + k];
-    const float sc = live ? g_score[g] : -INFINITY;
-    c_score[c] = sc;
-    c_idx[c] = live ? g_idx[g] : 0x7fffffff;
-    c_slot[c] = live ? g_slot[g] : -1;
-    c_sel[c] = 0;
-    mx = fmaxf(mx, sc);
+    if (i < g_cnt[(size_t)(cb0 + sg) * K + k]) {
+      const float sc = g_score[g];
+      const int pos = atomicAdd(&s_nlive, 1);
+      c_score[pos] = sc;
+      c_idx[pos] = g_idx[g];
+      c_slot[pos] = g_slot[g];
+      c_sel[pos] = sg << 1;
+      mx = fmaxf(mx, sc);
+    }
   }
   for (int sg = tid; sg < nseg; sg += RR) mx = fmaxf(mx, part[((size_t)(seg0 + sg) * K + k) * (L + 2)]);
   const float mstar = block_max(mx, red);      // (contains a __syncthreads: the smem lists are visible)
+  const int ncand = s_nlive;
 
   float4 a4[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   float ls = 0.f;
-  int nsel = 0;
-  if (warp == 0) {
-    // ---- 2a. this rank's top-n (sorted: score desc, index asc), warp-level only ----
-    int live = 0;
-    for (int c = lane; c < ncand; c += 32) live += c_slot[c] >= 0 ? 1 : 0;
-    live = (int)(warp_sum((float)live) + 0.5f);
-    nsel = min(nm, live);
-    for (int round = 0; round < nsel; ++round) {
-      float bs = -INFINITY;
-      int bi = 0x7fffffff, bp = -1;
-      for (int c = lane; c < ncand; c += 32) {
-        if (c_slot[c] >= 0 && !c_sel[c] && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
-          bs = c_score[c]; bi = c_idx[c]; bp = c;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-        if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
-      }
-      if (lane == 0) { sel_pos[round] = bp; c_sel[bp] = 1; }
-      __syncwarp();
-    }
-  } else {
-    // ---- 2b. segment partials (independent loads, 4 in flight per lane) ----
-    for (int sg = warp - 1; sg < nseg; sg += RR / 32 - 1) {
+  // ---- 2. segment partials + this rank's top-n (sorted: score desc, index asc) ----
+  // Few candidates (batches of bags, row-sharded bags): warp 0 selects alone while warps 1.. merge the partials.  Many (a
+  // whole 50k-row bag on one GPU brings ~1500 per branch: the lone warp was 60 % of the kernel): all warps merge, then
+  // every thread scans its own candidates and the CTA agrees on the best one per round.
+  const bool wide_select = ncand > 384;
+  auto merge_partials = [&](int first, int step) {
+    for (int sg = first; sg < nseg; sg += step) {
       const float* pr = part + ((size_t)(seg0 + sg) * K + k) * (L + 2);
       const float m = pr[0];
       const float w = m == -INFINITY ? 0.f : expf(m - mstar);
@@ -218,10 +205,56 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
         }
       }
     }
+  };
+  int nsel = 0;
+  if (wide_select) {
+    merge_partials(warp, RR / 32);
+    int live = 0;
+    for (int c = tid; c < ncand; c += RR) live += 1;
+    nsel = min(nm, (int)(block_sum((float)live, red) + 0.5f));
+    for (int round = 0; round < nsel; ++round) {
+      float bs = -INFINITY;
+      int bi = 0x7fffffff, bp = -1;
+      for (int c = tid; c < ncand; c += RR) {
+        if (!(c_sel[c] & 1) && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
+          bs = c_score[c]; bi = c_idx[c]; bp = c;
+        }
+      }
+      bp = block_argbest(bs, bi, bp, r_s, r_i, r_p);
+      if (tid == 0) { sel_pos[round] = bp; c_sel[bp] |= 1; }
+      __syncthreads();
+    }
+  } else {
+    if (warp == 0) {
+      int live = 0;
+      for (int c = lane; c < ncand; c += 32) live += 1;
+      live = (int)(warp_sum((float)live) + 0.5f);
+      nsel = min(nm, live);
+      for (int round = 0; round < nsel; ++round) {
+        float bs = -INFINITY;
+        int bi = 0x7fffffff, bp = -1;
+        for (int c = lane; c < ncand; c += 32) {
+          if (!(c_sel[c] & 1) && (bp < 0 || cand_better(c_score[c], c_idx[c], bs, bi))) {
+            bs = c_score[c]; bi = c_idx[c]; bp = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+          const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+          if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
+        }
+        if (lane == 0) { sel_pos[round] = bp; c_sel[bp] |= 1; }
+        __syncwarp();
+      }
+    } else {
+      merge_partials(warp - 1, RR / 32 - 1);
+    }
+    if (tid == 0) s_nsel = nsel;      // known to warp 0 only
+    __syncthreads();
+    nsel = s_nsel;
   }
-  if (tid == 0) s_nsel = nsel;      // known to warp 0 only
-  __syncthreads();
-  nsel = s_nsel;
 
   // ---- 3. candidates that were not selected rejoin the sums ----
   // (two candidates per round with all their loads in flight together: the rows sit in L2 at best)
@@ -231,9 +264,9 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int c = c0 + t * (RR / 32);
-      const bool on = c < ncand && c_slot[c] >= 0 && !c_sel[c];
+      const bool on = c < ncand && !(c_sel[c] & 1);
       wv[t] = on ? expf(c_score[c] - mstar) : 0.f;
-      const float* hr = g_h + ((size_t)(cb0 + (on ? c / nm : 0)) * rowcap + hoff + (on ? c_slot[c] : 0)) * L;
+      const float* hr = g_h + ((size_t)(cb0 + (on ? (c_sel[c] >> 1) : 0)) * rowcap + hoff + (on ? c_slot[c] : 0)) * L;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int qd = lane + 32 * j;
@@ -275,7 +308,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   for (int i = warp; i < nmc; i += RR / 32) {
     const bool on = i < nsel;
     const int c = on ? sel_pos[i] : 0;
-    const float* hr = on ? g_h + ((size_t)(cb0 + c / nm) * rowcap + hoff + c_slot[c]) * L : nullptr;
+    const float* hr = on ? g_h + ((size_t)(cb0 + (c_sel[c] >> 1)) * rowcap + hoff + c_slot[c]) * L : nullptr;
     for (int jf = lane; jf < L; jf += 32) rec[p.rec.h() + ((size_t)k * nmc + i) * L + jf] = on ? hr[jf] : 0.f;
     if (lane == 0) {
       rec[p.rec.score() + (size_t)k * nmc + i] = on ? c_score[c] : -INFINITY;

@@ -562,23 +562,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1) gp_main_umma_
         if (e_idx < K) {     // warp k publishes which records are still in list k and hands the list to the reduce kernel
           const int k = e_idx;
           const float mg_s = cs->ls[k][lane];
-          const int mg_rec = cs->lrec[k][lane], mg_cnt = cs->cnt[k], mg_app = min(cs->app[k], rcap);
+          const int mg_rec = cs->lrec[k][lane], mg_cnt = cs->cnt[k];
+          // Entries below the bag-wide threshold (a lower bound of the bag's final n-th best, from warp 3) cannot be in the
+          // global top n: they rejoin the sums HERE, on this CTA, instead of travelling to the reduce kernel, where the
+          // add-back of ~10 candidates per CTA and branch ran on one CTA per (bag, branch)
+          const unsigned long long gq = *reinterpret_cast<volatile unsigned long long*>(&cs->gtau[k]);
+          const float gt = (unsigned)(gq >> 32) == (unsigned)s_cur ? __uint_as_float((unsigned)gq) : -INFINITY;
+          const bool keepf = lane < mg_cnt && !(mg_s < gt);
+          const unsigned kbal = __ballot_sync(0xffffffffu, keepf);
+          const int pos = __popc(kbal & ((1u << lane) - 1u)), nkeep = __popc(kbal);
 #pragma unroll
           for (int w = 0; w < REC_CAP / 32; ++w) {
-            const unsigned m = __reduce_or_sync(0xffffffffu, (lane < mg_cnt && (mg_rec >> 5) == w) ? (1u << (mg_rec & 31)) : 0u);
+            const unsigned m = __reduce_or_sync(0xffffffffu, (keepf && (mg_rec >> 5) == w) ? (1u << (mg_rec & 31)) : 0u);
             if (lane == 0) cs->active[k][w] = m;
           }
-          (void)mg_app;
           int* g_cnt = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_cnt) + (size_t)cb * K;
           float* g_score = reinterpret_cast<float*>(p.mp.ws + p.mp.wl.cand_score) + (size_t)cb * K * cap;
           int* g_idx = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_idx) + (size_t)cb * K * cap;
           int* g_slot = reinterpret_cast<int*>(p.mp.ws + p.mp.wl.cand_slot) + (size_t)cb * K * cap;
-          if (lane == 0) g_cnt[k] = mg_cnt;
-          if (lane < cap) {
-            const bool live = lane < mg_cnt;
-            g_score[k * cap + lane] = live ? mg_s : -INFINITY;
-            g_idx[k * cap + lane] = live ? rix[(size_t)k * rcap + mg_rec] : 0x7fffffff;
-            g_slot[k * cap + lane] = live ? rsl[(size_t)k * rcap + mg_rec] : 0;
+          if (lane == 0) g_cnt[k] = nkeep;
+          if (keepf) {      // compacted: the reduce kernel reads the first g_cnt entries
+            g_score[k * cap + pos] = mg_s;
+            g_idx[k * cap + pos] = rix[(size_t)k * rcap + mg_rec];
+            g_slot[k * cap + pos] = rsl[(size_t)k * rcap + mg_rec];
+          }
+          if (lane < cap && lane >= nkeep) {
+            g_score[k * cap + lane] = -INFINITY;
+            g_idx[k * cap + lane] = 0x7fffffff;
+            g_slot[k * cap + lane] = 0;
           }
         }
         __threadfence_block();
