@@ -72,6 +72,8 @@ class GatedPool:
         self._shape = spec.c_struct()
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._w1 = None           # (w1, b1, (wv, bv, wu, bu, ww, bw)) fp32 copies of the last pack()
+        self._tail: Optional["GatedPool"] = None
         self._bufs: dict = {}
 
     # ------------------------------------------------------------------ weights
@@ -96,7 +98,30 @@ class GatedPool:
             L.check(lib.acmil_gp_pack(C.byref(self._shape), C.byref(w), _ptr(packed), nbytes.value, None, C.c_void_p(st)))
         self._packed, self._packed_key = packed, key
         self._keepalive = keep
+        self._w1 = None if keep[0] is None else (keep[0], keep[1], tuple(keep[2:]))      # for _split_front
         return packed
+
+    # ------------------------------------------------------------------ front projection on the GEMM engine
+    def _split_front(self, x, n_masked, impl):
+        """-> (tail GatedPool, its packed weights, h) when this call should run as  h = act(x W1^T + b1)  on the tcgen05 GEMM
+        engine (3xTF32, fp32-faithful) followed by the pool kernels on h; None = run fused as is.  Only without masking: the
+        mask indices are promised bit-exact against the fp32 reference, which the exact FFMA kernel guarantees and a
+        2^-21-accurate GEMM in front of it would not in near-ties; eval-mode outputs have the 1e-3 bar."""
+        sp = self.spec
+        impl = self.impl if impl is None else impl
+        if (not sp.front or n_masked > 0 or impl != L.IMPL_AUTO or self._w1 is None or x.shape[0] < 4096
+                or L.load().acmil_gp_umma_supported(C.byref(self._shape))):
+            return None
+        from .transmil import gemm_nt
+        if self._tail is None:
+            tail_spec = GatedPoolSpec(d_in=sp.d_inner, d_inner=sp.d_inner, n_branch=sp.n_branch, d_attn=sp.d_attn, front=False,
+                                      act_a=sp.act_a, gated=sp.gated, gate_bias=sp.gate_bias, score_bias=sp.score_bias)
+            self._tail = GatedPool(tail_spec, L.IMPL_FFMA)
+        w1, b1, rest = self._w1
+        packed2 = self._tail.pack(None, None, *rest)
+        xf = x if x.dtype == torch.float32 else x.float()
+        h = gemm_nt(xf, w1, bias=b1, relu=sp.front_act == "relu", gelu=sp.front_act == "gelu")
+        return self._tail, packed2, h
 
     def invalidate(self) -> None:
         """Forget the packed weights.  The cache key is (storage pointer, in-place version, shape) of every weight tensor:
@@ -241,6 +266,14 @@ class GatedPool:
         ``shard_begin`` (global index of its first row per bag); the per-bag partial records (a few KB)
         are all-gathered over NCCL and every rank finishes redundantly -- no other exchange.
         """
+        split = self._split_front(x, n_masked, impl)
+        if split is not None:
+            # shapes outside the fused tcgen05 kernel (D_inner 256 / 384 / 512, front-layer bias, GELU front): the front
+            # projection -- most of the FLOPs -- runs on the tcgen05 GEMM engine and the exact FFMA kernel does the rest
+            op2, packed2, h = split
+            return op2.run(packed2, h, row_offsets, n_masked=0, keep=keep, branch_w=branch_w, branch_b=branch_b, head_w=head_w,
+                           head_b=head_b, slide_head=slide_head, shared_head=shared_head, want_scores=want_scores,
+                           shard_begin=shard_begin, group=group, exchange=exchange)
         if exchange is not None:
             # records travel inside the kernels (NVLink stores + flags): no collective, graph-capturable
             _, ctx = self.partial(packed, x, row_offsets, n_masked=n_masked, want_scores=want_scores,

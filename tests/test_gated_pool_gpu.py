@@ -683,3 +683,40 @@ def test_fp16_rows_equal_widened_rows(impl_name, train):
         s32 = m(x16[None, :3000].float())
     for u, v in zip(s16, s32):
         close(u, v.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("case", [
+    dict(d_in=512, d_inner=256, K=3),                                                  # ResNet18 / CLIP features (Step3 table)
+    dict(d_in=1024, d_inner=512, K=1, front_bias=True, front_act="gelu", gated=False),   # attmil.DAttention
+    dict(d_in=768, d_inner=384, K=5),
+])
+def test_front_projection_on_the_gemm_engine_matches_the_fused_fp32_kernel(case):
+    """Shapes outside the fused tcgen05 kernel: in eval mode the front projection runs on the tcgen05 GEMM engine (3xTF32)
+    and the exact FFMA kernel pools h; the result must match the all-FFMA (exact fp32) run of the same head."""
+    import acmil_b200._lib as L
+    from acmil_b200.gated_pool import GatedPool, GatedPoolSpec
+    if case["d_inner"] % 128:
+        pytest.skip("d_inner must be a multiple of 128 for the pool kernels")
+    d_in, Li, K = case["d_in"], case["d_inner"], case["K"]
+    gated, fb, fa = case.get("gated", True), case.get("front_bias", False), case.get("front_act", "relu")
+    spec = GatedPoolSpec(d_in=d_in, d_inner=Li, n_branch=K, front_bias=fb, front_act=fa, gated=gated)
+    g = torch.Generator().manual_seed(d_in)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).cuda()      # noqa: E731
+    w = (rnd(Li, d_in, scale=d_in ** -0.5), rnd(Li, scale=0.1) if fb else None, rnd(128, Li, scale=Li ** -0.5), rnd(128, scale=0.1),
+         rnd(128, Li, scale=Li ** -0.5) if gated else None, rnd(128, scale=0.1) if gated else None, rnd(K, 128, scale=0.3),
+         rnd(K, scale=0.1))
+    n = [5000, 4500]
+    x = rnd(sum(n), d_in)
+    off = [0, n[0], sum(n)]
+    auto, exact = GatedPool(spec, L.IMPL_AUTO), GatedPool(spec, L.IMPL_FFMA)
+    ra = auto.run(auto.pack(*w), x, off)
+    assert auto._tail is not None                       # the composed path was taken
+    re = exact.run(exact.pack(*w), x, off)
+    # (3xTF32 front projection over K up to 1024 + the A&S erf of its GELU epilogue: a few 1e-5 absolute on scores of O(0.1))
+    close(ra.scores, re.scores.cpu().numpy(), rtol=1e-3, atol=5e-5)
+    close(ra.afeat, re.afeat.cpu().numpy(), rtol=1e-3, atol=5e-5)
+    close(ra.bag_feat, re.bag_feat.cpu().numpy(), rtol=1e-3, atol=5e-5)
+    # masking keeps the exact kernel end to end (mask indices are promised bit-exact)
+    rm = auto.run(auto.pack(*w), x, off, n_masked=10, keep=[6, 6], rand=torch.rand(2, K, 10, generator=g).cuda())
+    rx = exact.run(exact.pack(*w), x, off, n_masked=10, keep=[6, 6], rand=torch.rand(2, K, 10, generator=torch.Generator().manual_seed(1)).cuda())
+    assert torch.equal(rm.topk_idx, rx.topk_idx)
