@@ -52,7 +52,7 @@ class GpConsts(C.Structure):
 class GpBatch(C.Structure):
     _fields_ = [("d_x", C.c_void_p), ("row_offsets", C.POINTER(C.c_int64)), ("n_slides", C.c_int32),
                 ("n_masked", C.c_int32), ("shard_row_begin", C.POINTER(C.c_int64)), ("d_a_out", C.c_void_p),
-                ("a_ld", C.c_int64), ("x_f16", C.c_int32), ("reserved", C.c_int32)]
+                ("a_ld", C.c_int64), ("x_f16", C.c_int32), ("reserved", C.c_int32), ("d_z", C.c_void_p)]
 
 
 class GpHeads(C.Structure):

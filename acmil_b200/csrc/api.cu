@@ -249,6 +249,9 @@ static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, 
     use = ACMIL_IMPL_FFMA;   // masking with > 6 branches: stay on the general kernel
   ACMIL_REQUIRE(use != ACMIL_IMPL_UMMA || gp_umma_supported(*shape), ACMIL_E_UNSUPPORTED,
                 "tcgen05 kernel does not support this shape");
+  ACMIL_REQUIRE(batch->d_z == nullptr || (shape->front == 0 && batch->x_f16 == 0 && use == ACMIL_IMPL_FFMA &&
+                                          ((uintptr_t)batch->d_z & 15) == 0),
+                ACMIL_E_INVALID, "d_z needs front == 0, fp32 rows, the FFMA kernel and a 16-byte aligned pointer");
   GpMainParams p;
   memset(&p, 0, sizeof(p));
   p.sh = *shape;
@@ -267,6 +270,7 @@ static int gp_partial_common(const acmil_gp_shape* shape, const void* d_packed, 
   const GpExchange* gxp = x ? &gx : nullptr;
   p.x = batch->d_x;
   p.x_f16 = batch->x_f16 != 0;
+  p.z = batch->d_z;
   p.a_out = batch->d_a_out;
   p.a_ld = batch->a_ld;
   p.pack = reinterpret_cast<const float*>(d_packed);

@@ -222,6 +222,7 @@ struct GpMainParams {
   // FFMA kernel as the rescue pass of the tcgen05 kernel: only the bags with rescue_flags[s] == 1 are processed
   const int* rescue_flags;
   int x_f16;              // x holds fp16 rows (acmil_gp_batch.x_f16)
+  const float* z;         // optional gate pre-activations without biases (acmil_gp_batch.d_z), FFMA kernel only
 };
 
 // which bags a reduce launch handles, by the tcgen05 kernel's per-bag overflow flag

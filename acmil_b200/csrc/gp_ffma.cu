@@ -226,6 +226,25 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int c = 0; c < 8; ++c) accv[i][c] = accu[i][c] = 0.f;
+      if (p.z != nullptr) {
+        // the caller computed h Wv^T (and h Wu^T) on the tensor cores: this thread's 4 rows x 8 units come from there
+        const int zc = p.sh.gated ? 2 * GP_DATTN : GP_DATTN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ty * 4 + i;
+          if (r < valid) {
+            const float* zr = p.z + (size_t)(row0_bag + trow + r) * zc + tx * 8;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(zr)), a1 = __ldg(reinterpret_cast<const float4*>(zr + 4));
+            accv[i][0] = a0.x; accv[i][1] = a0.y; accv[i][2] = a0.z; accv[i][3] = a0.w;
+            accv[i][4] = a1.x; accv[i][5] = a1.y; accv[i][6] = a1.z; accv[i][7] = a1.w;
+            if (p.sh.gated) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(zr + GP_DATTN)), b1 = __ldg(reinterpret_cast<const float4*>(zr + GP_DATTN + 4));
+              accu[i][0] = b0.x; accu[i][1] = b0.y; accu[i][2] = b0.z; accu[i][3] = b0.w;
+              accu[i][4] = b1.x; accu[i][5] = b1.y; accu[i][6] = b1.z; accu[i][7] = b1.w;
+            }
+          }
+        }
+      } else {
       for (int kc = 0; kc < L / FKC; ++kc) {
         load_w_chunk(sm.ws, wvt, GP_DATTN, kc * FKC, 0, tid);
         __syncthreads();
@@ -239,6 +258,7 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
           chunk_fma(accu, sm.hs + (ty * 4) * ldh + kc * FKC, ldh, sm.ws, tx);
           __syncthreads();
         }
+      }
       }
       float part[4][KMAX];
 #pragma unroll

@@ -74,6 +74,7 @@ class GatedPool:
         self._packed_key = None
         self._w1 = None           # (w1, b1, (wv, bv, wu, bu, ww, bw)) fp32 copies of the last pack()
         self._tail: Optional["GatedPool"] = None
+        self._wcat = self._wcat_key = None
         self._bufs: dict = {}
 
     # ------------------------------------------------------------------ weights
@@ -99,6 +100,7 @@ class GatedPool:
         self._packed, self._packed_key = packed, key
         self._keepalive = keep
         self._w1 = None if keep[0] is None else (keep[0], keep[1], tuple(keep[2:]))      # for _split_front
+        self._wcat = self._wcat_key = None
         return packed
 
     # ------------------------------------------------------------------ front projection on the GEMM engine
@@ -121,7 +123,13 @@ class GatedPool:
         packed2 = self._tail.pack(None, None, *rest)
         xf = x if x.dtype == torch.float32 else x.float()
         h = gemm_nt(xf, w1, bias=b1, relu=sp.front_act == "relu", gelu=sp.front_act == "gelu")
-        return self._tail, packed2, h
+        # ... and the gate products h Wv^T | h Wu^T too (the kernel adds the biases, applies the gate and pools)
+        wv, _bv, wu, _bu = rest[0], rest[1], rest[2], rest[3]
+        if self._wcat is None or self._wcat_key != (wv.data_ptr(), None if wu is None else wu.data_ptr()):
+            self._wcat = (torch.cat([wv, wu], 0) if sp.gated else wv).contiguous()
+            self._wcat_key = (wv.data_ptr(), None if wu is None else wu.data_ptr())
+        zz = gemm_nt(h, self._wcat)
+        return self._tail, packed2, h, zz
 
     def invalidate(self) -> None:
         """Forget the packed weights.  The cache key is (storage pointer, in-place version, shape) of every weight tensor:
@@ -139,7 +147,7 @@ class GatedPool:
     # ------------------------------------------------------------------ forward
     def partial(self, packed: torch.Tensor, x: torch.Tensor, row_offsets: Sequence[int], *, n_masked: int = 0,
                 want_scores: bool = True, shard_begin: Optional[Sequence[int]] = None, impl: Optional[int] = None,
-                exchange=None):
+                exchange=None, z: Optional[torch.Tensor] = None):
         """Row pass over this device's rows.  Returns (record, ctx): ``record`` is the flat fp32 partial
         record (what sharded ranks all-gather), ``ctx`` carries the batch description for finish().
         With ``exchange`` (a sharding.PeerExchange) the reduce kernel stores the records into every peer's gather buffer
@@ -159,7 +167,7 @@ class GatedPool:
         off = (C.c_int64 * (S + 1))(*[int(v) for v in row_offsets])
         sb = (C.c_int64 * max(S, 1))(*[int(v) for v in shard_begin]) if shard_begin is not None else None
         scores = torch.empty((sp.n_branch, max(R, 1)), dtype=torch.float32, device=dev) if want_scores else None
-        batch = L.GpBatch(_ptr(x), off, S, int(n_masked), sb, _ptr(scores), max(R, 1), int(x.dtype == torch.float16), 0)
+        batch = L.GpBatch(_ptr(x), off, S, int(n_masked), sb, _ptr(scores), max(R, 1), int(x.dtype == torch.float16), 0, _ptr(z))
         ws_b, part_b = C.c_size_t(0), C.c_size_t(0)
         L.check(lib.acmil_gp_sizes(C.byref(self._shape), C.byref(batch), impl, C.byref(ws_b), C.byref(part_b)))
         ws = self._buf("ws", ws_b.value, dev)
@@ -174,7 +182,7 @@ class GatedPool:
             else:
                 L.check(lib.acmil_gp_partial(C.byref(self._shape), _ptr(packed), consts, C.byref(batch), impl, _ptr(ws),
                                              ws.numel(), _ptr(part), part.numel() * 4, st))
-        ctx = dict(batch=batch, keepalive=(off, sb, x), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
+        ctx = dict(batch=batch, keepalive=(off, sb, x, z), scores=scores, S=S, R=R, dev=dev, n_masked=int(n_masked),
                    row_offsets=list(row_offsets), ws=ws, impl=impl,
                    exchange=exchange, partial_bytes=part_b.value)
         return part, ctx
@@ -259,29 +267,29 @@ class GatedPool:
             head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
             slide_head: bool = False, shared_head: bool = False, want_scores: bool = True,
             shard_begin: Optional[Sequence[int]] = None, group=None, impl: Optional[int] = None,
-            rand: Optional[torch.Tensor] = None, exchange=None) -> GatedPoolResult:
+            rand: Optional[torch.Tensor] = None, exchange=None, z: Optional[torch.Tensor] = None) -> GatedPoolResult:
         """x: [R, d_in] fp32 CUDA, rows of S bags concatenated; row_offsets: S+1 host ints.
 
         With ``group`` (a torch.distributed process group) every rank passes its row shard of each bag and
         ``shard_begin`` (global index of its first row per bag); the per-bag partial records (a few KB)
         are all-gathered over NCCL and every rank finishes redundantly -- no other exchange.
         """
-        split = self._split_front(x, n_masked, impl)
+        split = self._split_front(x, n_masked, impl) if z is None else None
         if split is not None:
             # shapes outside the fused tcgen05 kernel (D_inner 256 / 384 / 512, front-layer bias, GELU front): the front
             # projection -- most of the FLOPs -- runs on the tcgen05 GEMM engine and the exact FFMA kernel does the rest
-            op2, packed2, h = split
+            op2, packed2, h, zz = split
             return op2.run(packed2, h, row_offsets, n_masked=0, keep=keep, branch_w=branch_w, branch_b=branch_b, head_w=head_w,
                            head_b=head_b, slide_head=slide_head, shared_head=shared_head, want_scores=want_scores,
-                           shard_begin=shard_begin, group=group, exchange=exchange)
+                           shard_begin=shard_begin, group=group, exchange=exchange, z=zz)
         if exchange is not None:
             # records travel inside the kernels (NVLink stores + flags): no collective, graph-capturable
             _, ctx = self.partial(packed, x, row_offsets, n_masked=n_masked, want_scores=want_scores,
-                                  shard_begin=shard_begin, impl=impl, exchange=exchange)
+                                  shard_begin=shard_begin, impl=impl, exchange=exchange, z=z)
             return self.finish(ctx, None, exchange.world, keep=keep, rsel=rsel, branch_w=branch_w, branch_b=branch_b,
                                head_w=head_w, head_b=head_b, slide_head=slide_head, shared_head=shared_head, rand=rand)
         part, ctx = self.partial(packed, x, row_offsets, n_masked=n_masked, want_scores=want_scores,
-                                 shard_begin=shard_begin, impl=impl)
+                                 shard_begin=shard_begin, impl=impl, z=z)
         from .sharding import gather_records
         world = torch.distributed.get_world_size(group) if (group is not None or (
             shard_begin is not None and torch.distributed.is_available() and torch.distributed.is_initialized())) else 1

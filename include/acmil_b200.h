@@ -125,6 +125,10 @@ typedef struct acmil_gp_batch {
    * the x_lo products (x_lo == 0). */
   int32_t x_f16;
   int32_t reserved;
+  /* optional: the gate pre-activations of the rows in d_x WITHOUT their biases, [R_total, d_attn * (1 + gated)] fp32 (V units,
+   * then U units), computed by the caller (acmil_gemm_nt on the tensor cores); the FFMA kernel then skips its own gate
+   * products.  Needs front == 0 (d_x holds h) and fp32 rows; ignored by the tcgen05 kernel (ACMIL_IMPL_FFMA is forced). */
+  const float* d_z;
 } acmil_gp_batch;
 
 /* Classifier heads applied by acmil_gp_finish (Classifier_1fc: nn.Linear [C, L]). */

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header_layout():
     import acmil_b200._lib as L
     assert C.sizeof(L.GpShape) == 48
     assert C.sizeof(L.GpWeights) == 64
-    assert C.sizeof(L.GpBatch) == 56
+    assert C.sizeof(L.GpBatch) == 64
     assert C.sizeof(L.GpHeads) == 48
     assert C.sizeof(L.GpOutputs) == 64
     assert C.sizeof(L.GpConsts) == (3 * 128 + 8 * 128 + 8 + 4) * 4 + 16
