@@ -116,8 +116,10 @@ __device__ float block_sum(float v, float* red) {
 // add the unselected candidates back; each warp covers the 128 features with one float4 per lane.
 // RR = threads per CTA: 1024 for the long segment / candidate lists of a whole 50k-row bag on one GPU, 256 when a bag
 // has few segments (row-sharded bags, small bags), where 8 CTAs per SM finish the whole batch in one wave.
-template <int RR>
-__global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
+// NJ = float4 groups of a feature row per lane (1 for L <= 128): sizes the register tiles.  The 256-thread variant is
+// compiled for 5 CTAs per SM so that the 640 CTAs of an 8-rank step (128 bag shards x 5 branches) fit ONE wave.
+template <int RR, int NJ>
+__global__ void __launch_bounds__(RR, RR == 256 ? (NJ == 1 ? 5 : 3) : 1) gp_reduce_kernel(const __grid_constant__ GpReduceParams p) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float red[RR / 32];
   __shared__ int sel_pos[NMAX];
@@ -179,9 +181,9 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   const float mstar = block_max(mx, red);      // (contains a __syncthreads: the smem lists are visible)
   const int ncand = s_nlive;
 
-  float4 a4[4];
+  float4 a4[NJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NJ; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   float ls = 0.f;
   // ---- 2. segment partials + this rank's top-n (sorted: score desc, index asc) ----
   // Few candidates (batches of bags, row-sharded bags): warp 0 selects alone while warps 1.. merge the partials.  Many (a
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
       const float w = m == -INFINITY ? 0.f : expf(m - mstar);
       if (lane == 0) ls += w * pr[1];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int qd = lane + 32 * j;
         if (qd < nq) {
           const float2 u0 = *reinterpret_cast<const float2*>(pr + 2 + qd * 4);      // rows are 8-byte aligned (L + 2 floats)
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
   // (two candidates per round with all their loads in flight together: the rows sit in L2 at best)
   for (int c0 = warp; c0 < ncand; c0 += 2 * (RR / 32)) {
     float wv[2];
-    float4 uv[2][4];
+    float4 uv[2][NJ];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int c = c0 + t * (RR / 32);
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
       wv[t] = on ? expf(c_score[c] - mstar) : 0.f;
       const float* hr = g_h + ((size_t)(cb0 + (on ? (c_sel[c] >> 1) : 0)) * rowcap + hoff + (on ? c_slot[c] : 0)) * L;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int qd = lane + 32 * j;
         uv[t][j] = (on && qd < nq) ? __ldcg(reinterpret_cast<const float4*>(hr + qd * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -277,14 +279,14 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
     for (int t = 0; t < 2; ++t) {
       if (lane == 0) ls += wv[t];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         a4[j].x = fmaf(wv[t], uv[t][j].x, a4[j].x); a4[j].y = fmaf(wv[t], uv[t][j].y, a4[j].y);
         a4[j].z = fmaf(wv[t], uv[t][j].z, a4[j].z); a4[j].w = fmaf(wv[t], uv[t][j].w, a4[j].w);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int qd = lane + 32 * j;
     if (qd < nq) wacc[warp * nq + qd] = a4[j];
   }
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(RR) gp_reduce_kernel(const __grid_constant__ G
 // serial), then all 8 warps stream the rank partials and the candidate rows (the bulk of the bytes: n_ranks * n_masked
 // rows of d_inner floats per branch) in a fixed assignment, so the result does not depend on timing.  The bag feature and
 // the slide head need all branches: gp_heads_kernel, launched right behind.
-__global__ void __launch_bounds__(RT) gp_finish_kernel(const __grid_constant__ GpFinishParams p) {
+__global__ void __launch_bounds__(RT, 5) gp_finish_kernel(const __grid_constant__ GpFinishParams p) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float s_m, s_l;
 
@@ -710,13 +712,23 @@ int gp_launch_reduce(const GpMainParams& mp, const GpRecord& rec, float* d_recor
   const int rr = small ? 256 : 1024;
   const size_t smem = (((size_t)max_cand * 16 + 15) / 16) * 16 + (size_t)(rr / 32) * mp.sh.d_inner * 4 + 32;
   ACMIL_REQUIRE(smem <= 220 * 1024, ACMIL_E_INVALID, "reduce: too many candidates per bag (%d)", max_cand);
-  static size_t configured = 48 * 1024;
-  if (!small && smem > configured) {
-    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  const int nj = (mp.sh.d_inner / 4 + 31) / 32;      // float4 groups of a feature row per lane
+#define REDUCE_CASE(RRV, NJV)                                                                                              \
+  {                                                                                                                        \
+    static size_t configured = 48 * 1024;                                                                                  \
+    if (smem > configured) {                                                                                               \
+      ACMIL_CHECK_CUDA(cudaFuncSetAttribute(gp_reduce_kernel<RRV, NJV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                            (int)smem));                                                                   \
+      configured = smem;                                                                                                   \
+    }                                                                                                                      \
+    gp_reduce_kernel<RRV, NJV><<<S * K, RRV, smem, st>>>(p);                                                               \
   }
-  if (small) gp_reduce_kernel<256><<<S * K, 256, smem, st>>>(p);
-  else gp_reduce_kernel<1024><<<S * K, 1024, smem, st>>>(p);
+  if (small) {
+    if (nj <= 1) REDUCE_CASE(256, 1) else if (nj <= 2) REDUCE_CASE(256, 2) else REDUCE_CASE(256, 4)
+  } else {
+    if (nj <= 1) REDUCE_CASE(1024, 1) else if (nj <= 2) REDUCE_CASE(1024, 2) else REDUCE_CASE(1024, 4)
+  }
+#undef REDUCE_CASE
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+export ACMIL_B200_NO_REBUILD=1
+timeout 120 python tests/cuda/shard_time.py 8
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/s40_launches.csv python tests/cuda/shard_time.py 8 > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows = [r for r in csv.reader(open('gpurun_out/s40_launches.csv')) if len(r) > 10]
+hdr = rows[0]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+agg = collections.defaultdict(list)
+for r in rows[1:]:
+    agg[r[ki][:70]].append(float(r[vi].replace(',', '')))
+for k, v in agg.items():
+    if 'gp_' in k or 'memset' in k.lower(): print(f"{k:70s} n={len(v):3d} mean {sum(v) / len(v) / 1e3:8.1f} us  min {min(v)/1e3:8.1f}")
+PY

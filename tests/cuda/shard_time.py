@@ -1,4 +1,4 @@
-"""Times the pieces of a bag-sharded step at the shape one rank sees at N ranks (S = 8 N bags of 50000 / N rows), with the
+"""Times the pieces of a bag-sharded step at the shape one rank sees at N ranks (S = 16 N bags of 50000 / N rows), with the
 peers' gather buffers on the same GPU: python tests/cuda/shard_time.py [ranks]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 from acmil_b200 import ACMIL_GA, Struct, _lib as L
 ranks = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-S, n = 8 * ranks, 50000 // ranks
+S, n = 16 * ranks, 50000 // ranks
 torch.manual_seed(0)
 m = ACMIL_GA(Struct(D_feat=384, D_inner=128, n_class=2, n_token=5), n_token=5, n_masked_patch=10, mask_drop=0.6).cuda().train()
 op = m._op
