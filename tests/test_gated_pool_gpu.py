@@ -720,3 +720,37 @@ def test_front_projection_on_the_gemm_engine_matches_the_fused_fp32_kernel(case)
     rm = auto.run(auto.pack(*w), x, off, n_masked=10, keep=[6, 6], rand=torch.rand(2, K, 10, generator=g).cuda())
     rx = exact.run(exact.pack(*w), x, off, n_masked=10, keep=[6, 6], rand=torch.rand(2, K, 10, generator=torch.Generator().manual_seed(1)).cuda())
     assert torch.equal(rm.topk_idx, rx.topk_idx)
+
+
+@pytest.mark.parametrize("name", ["acmil_ga_k5_n1024", "acmil_ga_k3_d512_n2000", "acmil_ga_k8_n4099"])
+def test_public_train_forward_and_masked_forward_feature_golden(name, monkeypatch):
+    """The PUBLIC calls -- ``forward`` in train mode and ``forward_feature(x, use_attention_mask=True)`` (transformer.py:305-352)
+    -- with the reference's own uniform draw replayed through torch.rand: masked positions bit-exact, outputs within 1e-3."""
+    import acmil_b200.heads as Hd
+    w, g = load_golden(name)
+    x = golden_x(g).cuda()
+    m = make_acmil(w, g, 0)
+    draw = torch.from_numpy(g["train_rand"]).cuda()
+    calls = []
+
+    def fake_rand(*shape, **kw):
+        assert tuple(shape) == tuple(draw.shape), (shape, draw.shape)      # the reference's call shape (transformer.py:316)
+        calls.append(1)
+        return draw
+
+    monkeypatch.setattr(Hd.torch, "rand", fake_rand)
+    m.train()
+    with torch.no_grad():
+        sub, slide, a = m(x)
+        m.eval()                                                            # forward_feature masks by its argument, not by mode
+        feat = m.forward_feature(x, use_attention_mask=True)
+        feat_plain = m.forward_feature(x)
+    monkeypatch.undo()
+    assert len(calls) == 2
+    a = a.cpu().numpy()
+    assert np.array_equal(a == -1e9, g["train_A"] == -1e9)
+    both(a, g["train_A"])
+    both(sub, g["train_sub"])
+    both(slide, g["train_slide"])
+    both(feat, g["train_feat"])
+    both(feat_plain, g["eval_feat"])
