@@ -530,14 +530,16 @@ def test_in_kernel_exchange_matches_unsharded(ranks, impl):
         assert all(int(xc.state[0]) == step + 1 for xc in xch)      # every rank's epoch advanced once per step
 
 
-def _grad_close(name, got, ref, strict=True):
+def _grad_close(name, got, ref, strict=True, floor=0.0):
     """strict: every entry within 2e-3 of the tensor's largest entry.  Not strict (the two sides computed the front layer
     independently): a pre-activation within rounding distance of the ReLU's kink (|z| ~ 1e-5) may fall on the other side,
     which moves single entries of dz1 by their whole value and with them one row of dx / dW1 -- both answers are valid
     subgradients -- so only the tensor-level l2 error is bounded (5e-3)."""
     d = (got - ref).abs()
     if strict:
-        err = float(d.max()) / (float(ref.abs().max()) + 1e-30)
+        # (floor: tensors whose true gradient nearly cancels -- the score bias under a softmax, everything softmax-related in a
+        # one-row bag -- are measured against the largest gradient of the step instead of their own rounding noise)
+        err = float(d.max()) / max(float(ref.abs().max()), floor, 1e-30)
         assert err < 2e-3, (name, err)
     else:
         l2 = float(d.norm()) / (float(ref.norm()) + 1e-30)
@@ -551,6 +553,8 @@ def _grad_close(name, got, ref, strict=True):
     dict(d_in=512, d_inner=256, K=1, n=801, front_bias=True, gated=False),                   # CLAM_SB(gate=False)
     dict(d_in=1024, d_inner=512, K=1, n=700, front_bias=True, act_a="gelu", biases=False),   # attmil.AttentionGated
     dict(d_in=1024, d_inner=512, K=2, n=640, act_a="relu"),
+    dict(d_in=384, d_inner=128, K=5, n=7, masked=True),                                      # fewer rows than n_masked_patch
+    dict(d_in=384, d_inner=128, K=3, n=1),                                                   # a one-patch bag
 ])
 def test_pool_backward_kernels_match_autograd(case):
     """acmil_b200.gp_backward (tcgen05 GEMMs + csrc/gp_bwd.cu) against torch autograd of the same graph written with
@@ -573,7 +577,7 @@ def test_pool_backward_kernels_match_autograd(case):
     x = rnd(n, d_in)
     op = GatedPool(spec)
     packed = op.pack(w["w1"], w["b1"], w["wv"], w["bv"], w["wu"], w["bu"], w["ww"], w["bw"])
-    n_masked, keep, rand = (10, [6], torch.rand(1, K, 10, generator=g).cuda()) if case.get("masked") else (0, [0], None)
+    n_masked, keep, rand = (10, [int(min(10, n) * 0.6)], torch.rand(1, K, 10, generator=g).cuda()) if case.get("masked") else (0, [0], None)
     res = op.run(packed, x, [0, n], n_masked=n_masked, keep=keep, rand=rand)
     g_afeat, g_bag, g_scores = rnd(K, Li), rnd(1, Li), rnd(K, n, scale=1e-3)
     dbg = {}
@@ -599,9 +603,10 @@ def test_pool_backward_kernels_match_autograd(case):
     outs = [af, af.mean(0, keepdim=True), s]
     names = list(leaves)
     ref = torch.autograd.grad(outs, [xr] + [leaves[k] for k in names], [g_afeat, g_bag, g_scores])
+    floor = 1e-2 * max(float(r.abs().max()) for r in ref[1:])
     for k, r in zip(["x"] + names, ref):
         assert got[k].shape == r.shape, k
-        _grad_close(k, got[k], r)
+        _grad_close(k, got[k], r, floor=floor if k != "x" else 0.0)
 
 
 def test_acmil_training_step_kernel_vs_torch_backward(monkeypatch):
