@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(FT) gp_main_ffma_kernel(const __grid_constant_
 
   // ---- which segments: blockIdx.x, blockIdx.x + gridDim.x, ... (one each unless this is a rescue pass, which is launched
   // with a small grid because it normally has nothing to do) ----
+  if (p.rescue_flags != nullptr) {
+    // rescue pass: normally no bag is flagged -- find that out with one look at the flags instead of walking the segments
+    int any = 0;
+    for (int b = tid; b < p.seg.n_slides; b += FT) any |= p.rescue_flags[b] == 1;
+    if (!__syncthreads_or(any)) return;
+  }
   int s = 0;
   for (int seg = blockIdx.x; seg < p.seg.n_seg; seg += gridDim.x) {
   while (seg >= p.seg.seg_begin[s + 1]) ++s;

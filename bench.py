@@ -488,61 +488,65 @@ def run_ours(a):
         # is exact, the kernels read the halves directly): reported next to the fp32 headline, with its own roofline
         fp16_line = None
         if world == 1 and not a.no_fp16:
-            g16 = [g.half() for g in groups]
-            def step16(i):
-                r = torch.rand(S, K_BRANCH, nm, device=dev) if masking else None
-                return op.run(packed, g16[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
-                              keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
-                              head_w=head_w, head_b=head_b, slide_head=True)
-            for i in range(max(a.warmup, 3)):
-                step16(i)
-            torch.cuda.synchronize()
-            launch16, g16 = "eager launches", None
-            if graphs is not None:      # same launch mode as the headline: one captured graph per bag group, replayed
-                try:
-                    g16 = []
-                    for gi in range(a.groups):
-                        gg = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(gg):
-                            rr = step16(gi)
-                        g16.append((gg, rr))
-                    launch16 = "cuda graph (one per bag group), replayed"
-                except Exception:      # noqa: BLE001
-                    g16 = None
-                    torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for i in range(a.steps):
-                if g16 is None:
-                    r16 = step16(i)
-                else:
-                    g16[i % a.groups][0].replay()
-                    r16 = g16[i % a.groups][1]
-            f1.record()
-            torch.cuda.synchronize()
-            lib.acmil_prof_enable(1)      # the row-pass kernel alone: CUDA events around its launch in an eager pass
-            for i in range(a.steps):
-                step16(i)
-            torch.cuda.synchronize()
-            k_ms, k_n = C.c_double(0), C.c_int64(0)
-            lib.acmil_prof_collect(C.byref(k_ms), C.byref(k_n))
-            lib.acmil_prof_enable(0)
-            ms16 = f0.elapsed_time(f1) / a.steps
-            kms16 = k_ms.value / max(k_n.value, 1)
-            bytes16 = (ALGO_BYTES_PER_SLIDE - N_ROWS * D_FEAT * 2) * (a.rows / N_ROWS) * a.slides
             try:
-                peak16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
-            except Exception:
-                peak16 = 6650.0
-            fp16_line = {"value": S / (ms16 * 1e-3), "unit": "slides/s", "ms_per_step": ms16, "launch": launch16,
-                         "roofline": {"bound": "hbm", "achieved": bytes16 / (kms16 * 1e-3) / 1e9, "peak": peak16, "unit": "GB/s",
-                                      "frac": bytes16 / (kms16 * 1e-3) / 1e9 / peak16, "kernel_ms": kms16,
-                                      "algorithmic_bytes_per_launch": bytes16},
-                         "max_abs_logit_diff_vs_fp32_of_same_values": float((r16.slide - op.run(
-                             packed, g16[(a.steps - 1) % a.groups].float(), offsets, n_masked=0, keep=[0] * S, branch_w=branch_w,
-                             branch_b=branch_b, head_w=head_w, head_b=head_b, slide_head=True).slide).abs().max()) if not masking else None,
-                         "note": "x_f16 = 1: fp16 rows read by TMA as the hi operand, no x_lo products, half the HBM bytes"}
-            del g16
+                g16 = [g.half() for g in groups]
+                def step16(i):
+                    r = torch.rand(S, K_BRANCH, nm, device=dev) if masking else None
+                    return op.run(packed, g16[i % a.groups], offsets, n_masked=N_MASKED if masking else 0,
+                                  keep=[keep if masking else 0] * S, rand=r, branch_w=branch_w, branch_b=branch_b,
+                                  head_w=head_w, head_b=head_b, slide_head=True)
+                for i in range(max(a.warmup, 3)):
+                    step16(i)
+                torch.cuda.synchronize()
+                launch16, g16 = "eager launches", None
+                if graphs is not None:      # same launch mode as the headline: one captured graph per bag group, replayed
+                    try:
+                        g16 = []
+                        for gi in range(a.groups):
+                            gg = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(gg):
+                                rr = step16(gi)
+                            g16.append((gg, rr))
+                        launch16 = "cuda graph (one per bag group), replayed"
+                    except Exception:      # noqa: BLE001
+                        g16 = None
+                        torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(a.steps):
+                    if g16 is None:
+                        r16 = step16(i)
+                    else:
+                        g16[i % a.groups][0].replay()
+                        r16 = g16[i % a.groups][1]
+                f1.record()
+                torch.cuda.synchronize()
+                lib.acmil_prof_enable(1)      # the row-pass kernel alone: CUDA events around its launch in an eager pass
+                for i in range(a.steps):
+                    step16(i)
+                torch.cuda.synchronize()
+                k_ms, k_n = C.c_double(0), C.c_int64(0)
+                lib.acmil_prof_collect(C.byref(k_ms), C.byref(k_n))
+                lib.acmil_prof_enable(0)
+                ms16 = f0.elapsed_time(f1) / a.steps
+                kms16 = k_ms.value / max(k_n.value, 1)
+                bytes16 = (ALGO_BYTES_PER_SLIDE - N_ROWS * D_FEAT * 2) * (a.rows / N_ROWS) * a.slides
+                try:
+                    peak16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                except Exception:
+                    peak16 = 6650.0
+                fp16_line = {"value": S / (ms16 * 1e-3), "unit": "slides/s", "ms_per_step": ms16, "launch": launch16,
+                             "roofline": {"bound": "hbm", "achieved": bytes16 / (kms16 * 1e-3) / 1e9, "peak": peak16, "unit": "GB/s",
+                                          "frac": bytes16 / (kms16 * 1e-3) / 1e9 / peak16, "kernel_ms": kms16,
+                                          "algorithmic_bytes_per_launch": bytes16},
+                             "max_abs_logit_diff_vs_fp32_of_same_values": float((r16.slide - op.run(
+                                 packed, g16[(a.steps - 1) % a.groups].float(), offsets, n_masked=0, keep=[0] * S, branch_w=branch_w,
+                                 branch_b=branch_b, head_w=head_w, head_b=head_b, slide_head=True).slide).abs().max()) if not masking else None,
+                             "note": "x_f16 = 1: fp16 rows read by TMA as the hi operand, no x_lo products, half the HBM bytes"}
+                del g16
+            except Exception as exc:      # noqa: BLE001  (an extra: never take the headline line down with it)
+                fp16_line = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.synchronize()
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
