@@ -498,27 +498,27 @@ def run_ours(a):
                 for i in range(max(a.warmup, 3)):
                     step16(i)
                 torch.cuda.synchronize()
-                launch16, g16 = "eager launches", None
+                launch16, gr16 = "eager launches", None
                 if graphs is not None:      # same launch mode as the headline: one captured graph per bag group, replayed
                     try:
-                        g16 = []
+                        gr16 = []
                         for gi in range(a.groups):
                             gg = torch.cuda.CUDAGraph()
                             with torch.cuda.graph(gg):
                                 rr = step16(gi)
-                            g16.append((gg, rr))
+                            gr16.append((gg, rr))
                         launch16 = "cuda graph (one per bag group), replayed"
                     except Exception:      # noqa: BLE001
-                        g16 = None
+                        gr16 = None
                         torch.cuda.synchronize()
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
                 for i in range(a.steps):
-                    if g16 is None:
+                    if gr16 is None:
                         r16 = step16(i)
                     else:
-                        g16[i % a.groups][0].replay()
-                        r16 = g16[i % a.groups][1]
+                        gr16[i % a.groups][0].replay()
+                        r16 = gr16[i % a.groups][1]
                 f1.record()
                 torch.cuda.synchronize()
                 lib.acmil_prof_enable(1)      # the row-pass kernel alone: CUDA events around its launch in an eager pass
