@@ -5,7 +5,7 @@ import torch
 from acmil_b200 import ACMIL_GA, Struct, _lib as L
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 nmask = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-n = 50000
+n = int(os.environ.get('UMMA_PROF_ROWS', '50000'))
 torch.manual_seed(0)
 m = ACMIL_GA(Struct(D_feat=384, D_inner=128, n_class=2, n_token=5), n_token=5, n_masked_patch=10, mask_drop=0.6).cuda().eval()
 x = torch.randn(S * n, 384, device="cuda")
@@ -28,7 +28,7 @@ names = {0: "TMA wait_empty_x", 8: "MMA wait_w_ready", 9: "MMA idle: G1 blk d1_e
          29: "EPI pool", 30: "EPI flush (bag ends)", 31: "EPI total"}
 for cta in (0, 1):
     sel = a[cta::2]
-    print(f"--- cta rank {cta} (mean over {len(sel)} CTAs; tiles per CTA ~{S * 196 / 74:.1f})")
+    print(f"--- cta rank {cta} (mean over {len(sel)} CTAs; tiles per CTA ~{S * ((n + 255) // 256) / 74:.1f})")
     for k, v in names.items():
         print(f"{v:28s} mean {sel[:, k].mean():12.0f}  max {sel[:, k].max():12.0f}")
 
