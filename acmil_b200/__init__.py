@@ -9,6 +9,8 @@ from .heads import (ABMIL, ACMIL_GA, Attention2, Attention_Gated, Attention_with
                     AttentionGated, Classifier_1fc, DAttention, DimReduction)
 from .mha import ACMIL_MHA, MHA, MutiHeadAttention, MutiHeadAttention_modify  # noqa: F401
 from .transmil import PPEG, NystromAttention, TransLayer, TransMIL  # noqa: F401
+from .consumers import CLAM_MB, CLAM_SB, IBMIL, Attn_Net, Attn_Net_Gated  # noqa: F401
+from .losses import diversity_loss  # noqa: F401
 from .utils import Struct, set_seed  # noqa: F401
 
 __version__ = "0.1.0"
