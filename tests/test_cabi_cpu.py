@@ -141,3 +141,36 @@ def test_attention_py_and_attmil_parameter_names():
         assert list(sd.keys()) == list(ATTMIL_AG_SHAPES(bias).keys())
     sd = DAttention(3, False, "relu").state_dict()
     assert {k: tuple(v.shape) for k, v in sd.items()} == ATTMIL_DA_SHAPES
+
+
+def test_round2_entry_points_validate_and_refuse_without_a_gpu():
+    """The entry points added in round 2 (backward row kernels, diversity loss, sharded Nystrom phases, log-sum-exp merge,
+    PPEG rows): host-side validation gives codes + messages, and with no CUDA device every compute call returns
+    ACMIL_E_CUDA -- there is no CPU path."""
+    import acmil_b200._lib as L
+    lib = L.load()
+    gate_f, relu_f = C.c_int64(0), C.c_int64(0)
+    assert lib.acmil_gp_bwd_workspace_floats(128, C.byref(gate_f), C.byref(relu_f)) == 0
+    assert gate_f.value % (8 * 128 + 8 + 256) == 0 and relu_f.value % 128 == 0 and gate_f.value > 0
+    shard = L.NystromShard(6304, 255, 512, 8, 64, 256, 32, 197, 6, 1, 33, 1, 0, 0, 1, 16)
+    n = C.c_size_t(0)
+    assert lib.acmil_nystrom_shard_workspace_bytes(C.byref(shard), C.byref(n)) == 0
+    assert n.value >= (6304 * 512 + 2 * 8 * 6304 * 64 + 8 * 6304 * 256) * 4            # xn, q, k, one similarity
+    bad = L.NystromShard(6300, 255, 512, 8, 64, 256, 32, 197, 6, 1, 33, 1, 0, 0, 1, 16)   # n_loc != m_loc * group_len
+    assert lib.acmil_nystrom_shard_workspace_bytes(C.byref(bad), C.byref(n)) == -1
+    assert b"n_loc" in lib.acmil_last_error()
+    if torch.cuda.is_available():
+        return
+    p = C.c_void_p(256)
+    args = L.GpBwdGateArgs(p, p, p, p, p, p, None, None, None, p, 8, 8, 0, 8, 128, 128, 5, 0, 1, 0, p, p, p, p, p)
+    assert lib.acmil_gp_bwd_gate(C.byref(args), None) == -2
+    assert lib.acmil_gp_bwd_relu_mask(p, p, 8, 128, None, p, 8, p, p, None) == -2
+    assert lib.acmil_transpose_f32(p, 8, 8, 8, p, 8, None) == -2
+    assert lib.acmil_div_loss_fwd(p, 8, 5, 8, p, p, p, None) == -2
+    assert lib.acmil_div_loss_bwd(p, 8, 5, 8, p, p, p, p, 8, None) == -2
+    assert lib.acmil_lse_merge(p, p, p, 2, 8, 64, 256, p, None) == -2
+    assert lib.acmil_ppeg_fwd_rows(p, 4, 4, 32, p, p, p, p, p, p, p, 0, 4, None) == -2
+    bufs = L.NystromShardBufs(p, None, p, p, p, p, p, p, p, p, p, p, p, p, 1 << 40)
+    w = L.NystromWeights()
+    assert lib.acmil_nystrom_shard_phase(C.byref(shard), C.byref(w), C.byref(bufs), 0, None) == -2
+    assert b"no CUDA device" in lib.acmil_last_error()
