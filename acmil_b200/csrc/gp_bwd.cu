@@ -48,7 +48,7 @@ __device__ __forceinline__ float gelu_grad(float z) {
 // transposed through shared memory.  Shared memory is sized by the actual shape so that 4 CTAs (32 warps) fit an SM:
 // the per-row chain (loads -> K warp reductions -> exp -> gate) is latency-bound and needs the warps.
 template <int NF, int KB>
-__global__ void __launch_bounds__(BT, NF <= 8 ? 3 : 2) gp_bwd_gate_kernel(const GateArgs a) {
+__global__ void __launch_bounds__(BT, 2) gp_bwd_gate_kernel(const GateArgs a) {
   extern __shared__ float sm[];
   constexpr int L = NF * 32;
   const int K = a.K, zc = a.zc;
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(BT, NF <= 8 ? 3 : 2) gp_bwd_gate_kernel(const 
 
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
     const long long n0 = (long long)t * TR;
-#pragma unroll 1
-    for (int rr = 0; rr < TR / 8; ++rr) {
+#pragma unroll 2
+    for (int rr = 0; rr < TR / 8; ++rr) {      // two rows in flight per warp: their loads overlap
       const int r = warp * (TR / 8) + rr;
       const long long n = n0 + r;
       if (n < a.n) {
