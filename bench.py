@@ -57,6 +57,7 @@ def parse():
                     help="N > 1: how the per-bag partial records travel: inside the kernels over peer memory, or NCCL")
     ap.add_argument("--workload", default="acmil", choices=["acmil", "transmil", "vit", "resnet", "stream"],
                     help="acmil = the headline metric (BASELINE.json configs[1]); transmil = configs[2], see bench_transmil.py")
+    ap.add_argument("--patch-batch", type=int, default=256, help="vit / resnet: patches per step per GPU")
     ap.add_argument("--stream-slides", type=int, default=398, help="stream: slides in the Camelyon16-shaped set")
     ap.add_argument("--stream-scale", type=float, default=1 / 64, help="stream: patch-count scale (1 = 10k..100k patches per slide)")
     ap.add_argument("--transmil-replicas", action="store_true", help="transmil at N > 1: independent replicas instead of one sharded bag")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Secondary bench: ViT-S/16 patch-feature extraction (BASELINE.json configs[3]: 256x256 RGB uint8 patches -> Resize(224)
 + normalise -> ViT-S/16 -> fp16 features).  Same JSON contract as bench.py (`--workload vit` dispatches here).
-A step = one batch of `--slides`*32 patches (default 256, the reference's batch size) per GPU; `value` = patches/s over
+A step = one batch of `--patch-batch` patches (default 256, the reference's batch size) per GPU; `value` = patches/s over
 all GPUs with the uint8 patches resident in HBM; `e2e` = extract_feature() from pinned host memory (H2D of the uint8
 patches, features read back); roofline bound "tensor": useful FLOPs (2 M N K, split not counted) / time against the
 measured bf16 peak.  Patches are independent: N GPUs = N data-parallel replicas, no collective.
@@ -121,7 +121,7 @@ def run_ours(a, ClockSampler):
         enc = vit_small(False, False, None)
     model = CustomModel(Struct(n_class=2), enc).to(dev).eval()
     enc_name, flops, feat_dim = names(a)
-    batch = a.slides * 32
+    batch = getattr(a, "patch_batch", 256)      # the reference's extraction batch size (Step2_feature_extract.py:25)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     bags = [torch.randint(0, 256, (batch, 256, 256, 3), device=dev, dtype=torch.uint8, generator=gen) for _ in range(3)]
 
