@@ -82,12 +82,21 @@ __device__ int block_argbest(float s, int i, int pos, float* r_s, int* r_i, int*
   __syncthreads();
   if (lane == 0) { r_s[warp] = s; r_i[warp] = i; r_p[warp] = pos; }
   __syncthreads();
-  float bs = r_s[0];
-  int bi = r_i[0], bp = r_p[0];
-  for (int w = 1; w < nw; ++w) {
-    if (r_p[w] >= 0 && (bp < 0 || cand_better(r_s[w], r_i[w], bs, bi))) { bs = r_s[w]; bi = r_i[w]; bp = r_p[w]; }
+  if (warp == 0) {      // the warps' winners are reduced by one warp (not scanned by every thread) and handed out through r_p[0]
+    float bs = lane < nw ? r_s[lane] : -INFINITY;
+    int bi = lane < nw ? r_i[lane] : 0x7fffffff, bp = lane < nw ? r_p[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (p2 >= 0 && (bp < 0 || cand_better(s2, i2, bs, bi))) { bs = s2; bi = i2; bp = p2; }
+    }
+    __syncwarp();
+    if (lane == 0) r_p[0] = bp;
   }
-  return bp;
+  __syncthreads();
+  return r_p[0];
 }
 
 __device__ float block_max(float v, float* red) {
@@ -259,12 +268,13 @@ __global__ void __launch_bounds__(RR, RR == 256 ? (NJ == 1 ? 5 : 3) : 1) gp_redu
   }
 
   // ---- 3. candidates that were not selected rejoin the sums ----
-  // (two candidates per round with all their loads in flight together: the rows sit in L2 at best)
-  for (int c0 = warp; c0 < ncand; c0 += 2 * (RR / 32)) {
-    float wv[2];
-    float4 uv[2][NJ];
+  // (CPR candidates per round with all their loads in flight together: the rows sit in L2 at best)
+  constexpr int CPR = NJ == 1 ? 4 : 2;
+  for (int c0 = warp; c0 < ncand; c0 += CPR * (RR / 32)) {
+    float wv[CPR];
+    float4 uv[CPR][NJ];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < CPR; ++t) {
       const int c = c0 + t * (RR / 32);
       const bool on = c < ncand && !(c_sel[c] & 1);
       wv[t] = on ? expf(c_score[c] - mstar) : 0.f;
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(RR, RR == 256 ? (NJ == 1 ? 5 : 3) : 1) gp_redu
       }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < CPR; ++t) {
       if (lane == 0) ls += wv[t];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
