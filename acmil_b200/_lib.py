@@ -94,7 +94,8 @@ class GemmDesc(C.Structure):
                    ("alpha", C.c_float), ("beta", C.c_float), ("diag", C.c_float), ("act", C.c_int32),
                    ("precise", C.c_int32), ("batch_inner", C.c_int32), ("bias_per_row", C.c_int32), ("reserved", C.c_int32)]
                 + [(n, C.c_int64) for n in ("a_batch_stride2", "b_batch_stride2", "c_batch_stride2", "ct_batch_stride2",
-                                            "addend_batch_stride2")])
+                                            "addend_batch_stride2")]
+                + [("b_split", C.c_void_p), ("b_split_rows", C.c_int32), ("b_split_row0", C.c_int32)])
 
 
 class NystromShape(C.Structure):
@@ -105,7 +106,8 @@ class NystromShape(C.Structure):
 
 class NystromWeights(C.Structure):
     _fields_ = [("d_ln_w", C.c_void_p), ("d_ln_b", C.c_void_p), ("ln_eps", C.c_float), ("reserved", C.c_int32),
-                ("d_wqkv", C.c_void_p), ("d_wout", C.c_void_p), ("d_bout", C.c_void_p), ("d_wconv", C.c_void_p)]
+                ("d_wqkv", C.c_void_p), ("d_wout", C.c_void_p), ("d_bout", C.c_void_p), ("d_wconv", C.c_void_p),
+                ("d_split_qkv", C.c_void_p), ("d_split_out", C.c_void_p)]
 
 
 class NystromShard(C.Structure):
@@ -128,12 +130,14 @@ class VitShape(C.Structure):
 
 class VitBlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_ln1_w", "d_ln1_b", "d_qkv_w", "d_qkv_b", "d_proj_w", "d_proj_b", "d_ln2_w",
-                                          "d_ln2_b", "d_fc1_w", "d_fc1_b", "d_fc2_w", "d_fc2_b")]
+                                          "d_ln2_b", "d_fc1_w", "d_fc1_b", "d_fc2_w", "d_fc2_b", "d_split_qkv",
+                                          "d_split_proj", "d_split_fc1", "d_split_fc2")]
 
 
 class VitWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_cls_token", "d_pos_embed", "d_patch_w", "d_patch_b", "d_norm_w", "d_norm_b",
-                                          "d_head_w", "d_head_b")] + [("blocks", C.POINTER(VitBlockWeights))]
+                                          "d_head_w", "d_head_b")] + [("blocks", C.POINTER(VitBlockWeights)),
+                                                                     ("d_split_patch", C.c_void_p)]
 
 
 # every symbol include/*.h declares: (restype, argtypes)
@@ -178,6 +182,8 @@ SYMBOLS = {
                                      C.c_int64, C.c_void_p]),
     # include/acmil_transmil.h
     "acmil_gemm_nt": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "acmil_gemm_split_bytes": (C.c_int, [C.c_int32, C.c_int32, _SIZE_P]),
+    "acmil_gemm_split_b": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "acmil_layernorm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "acmil_nystrom_workspace_bytes": (C.c_int, [C.POINTER(NystromShape), _SIZE_P]),

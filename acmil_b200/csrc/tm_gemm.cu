@@ -46,6 +46,8 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
 
 struct GemmParams {
   CUtensorMap ta, tb;            // (K, rows, batch_lo, batch_hi) fp32
+  CUtensorMap tbh, tbl;          // fp16-split mode: (K, rows) fp16 hi / lo sections of a pre-split B image
+  const float* bscale;           // fp16-split mode: 1 / (power-of-two scale the image was made with), on the device
   float* c;
   float* ct;                     // optional transposed copy: ct[b] + col * ldct + row
   const float* bias;             // [N] or null
@@ -163,6 +165,118 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile, i
   t.bz = p.ksplit > 1 ? z / p.ksplit : z;
   t.split = p.ksplit > 1 ? z % p.ksplit : 0;
   return t;
+}
+
+// Epilogue of one 128 x BN tile for one warp: TMEM lanes 32 q .. 32 q + 31 (thread = row), the 32-column chunks `half`,
+// `half` + 2, ...; scale / diagonal / bias / addend / activation on registers, float4 global traffic where the layout allows.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& t, int nchunk, uint32_t tacc, int q, int half,
+                                              int lane, float alpha) {
+  const int zlo = t.bz % p.zdiv, zhi = t.bz / p.zdiv;
+  const int row = t.m0 + q * 32 + lane;
+  const bool row_ok = row < p.M;
+  float* crow = p.c ? p.c + (size_t)zlo * p.c_batch_stride + (size_t)zhi * p.c_bs2 + (size_t)row * p.ldc : nullptr;
+  const float* arow =
+      p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
+  float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
+  const int zsplit = p.ksplit > 1 ? t.bz * p.ksplit + t.split : 0;
+  const float rbias = (p.bias && p.bias_row && row_ok) ? p.bias[row] : 0.f;
+#pragma unroll 1
+  for (int c0 = half * 32; c0 < BN; c0 += 64) {
+    const int col0 = t.n0 + c0;
+    if (col0 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + c0, v);
+    tmem_wait_ld();
+    const bool full = col0 + 32 <= p.N;      // warp-uniform
+    if (p.ksplit > 1) {
+      if (row_ok) {
+        float* dst = p.split_ws + ((size_t)zsplit * p.M + row) * p.N + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
+      }
+      continue;
+    }
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = alpha * __uint_as_float(v[j]);
+    if (p.diag != 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j == row) r[j] += p.diag;
+    }
+    if (p.bias) {
+      if (p.bias_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] += rbias;
+      } else if (full && p.bias_vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);      // same address in every lane: broadcast
+          r[j] += b4.x; r[j + 1] += b4.y; r[j + 2] += b4.z; r[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) r[j] += p.bias[col0 + j];
+      }
+    }
+    if (row_ok) {
+      if (arow) {
+        if (full && p.add_vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(arow + col0 + j);
+            r[j] = fmaf(p.beta, a4.x, r[j]); r[j + 1] = fmaf(p.beta, a4.y, r[j + 1]);
+            r[j + 2] = fmaf(p.beta, a4.z, r[j + 2]); r[j + 3] = fmaf(p.beta, a4.w, r[j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) r[j] = fmaf(p.beta, arow[col0 + j], r[j]);
+        }
+      }
+      if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const uint64_t g = gelu2(pack2(r[j], r[j + 1]));
+          r[j] = lo2(g);
+          r[j + 1] = hi2(g);
+        }
+      } else if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
+      }
+      if (crow) {
+        // column blocks: the chunk sits inside one block whenever its first and last column do
+        const int blk0 = col0 / p.cbw, off0 = col0 - blk0 * p.cbw;
+        const bool one_blk = off0 + 32 <= p.cbw;
+        float* dst = crow + (size_t)blk0 * p.cbs + off0;
+        if (full && one_blk && p.vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else if (one_blk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = r[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
+          }
+        }
+      }
+      if (ctb) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
+        }
+      }
+    }
+  }
 }
 
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and the two TMEM
@@ -344,114 +458,10 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
       const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
       int kbeg, nchunk;
       k_range(t, kbeg, nchunk);
-      const int zlo = t.bz % p.zdiv, zhi = t.bz / p.zdiv;
       const uint32_t buf = it & 1u;
-      const int row = t.m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
       mbar_wait(&bars->acc_full[buf], (it >> 1) & 1u);
       tc_fence_after();
-      float* crow = p.c ? p.c + (size_t)zlo * p.c_batch_stride + (size_t)zhi * p.c_bs2 + (size_t)row * p.ldc : nullptr;
-      const float* arow =
-          p.addend ? p.addend + (size_t)zlo * p.add_batch_stride + (size_t)zhi * p.add_bs2 + (size_t)row * p.ld_add : nullptr;
-      float* ctb = p.ct ? p.ct + (size_t)zlo * p.ct_batch_stride + (size_t)zhi * p.ct_bs2 + row : nullptr;
-      const int zsplit = p.ksplit > 1 ? t.bz * p.ksplit + t.split : 0;
-      const float rbias = (p.bias && p.bias_row && row_ok) ? p.bias[row] : 0.f;
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        const int col0 = t.n0 + c0;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(tm + buf * (ACC_COLS / 2) + ((uint32_t)(q * 32) << 16) + c0, v);
-        tmem_wait_ld();
-        const bool full = col0 + 32 <= p.N;      // warp-uniform
-        if (p.ksplit > 1) {
-          if (row_ok) {
-            float* dst = p.split_ws + ((size_t)zsplit * p.M + row) * p.N + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = nchunk > 0 ? __uint_as_float(v[j]) : 0.f;
-          }
-          continue;
-        }
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = p.alpha * __uint_as_float(v[j]);
-        if (p.diag != 0.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j == row) r[j] += p.diag;
-        }
-        if (p.bias) {
-          if (p.bias_row) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] += rbias;
-          } else if (full && p.bias_vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);      // same address in every lane: broadcast
-              r[j] += b4.x; r[j + 1] += b4.y; r[j + 2] += b4.z; r[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) r[j] += p.bias[col0 + j];
-          }
-        }
-        if (row_ok) {
-          if (arow) {
-            if (full && p.add_vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 a4 = *reinterpret_cast<const float4*>(arow + col0 + j);
-                r[j] = fmaf(p.beta, a4.x, r[j]); r[j + 1] = fmaf(p.beta, a4.y, r[j + 1]);
-                r[j + 2] = fmaf(p.beta, a4.z, r[j + 2]); r[j + 3] = fmaf(p.beta, a4.w, r[j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) r[j] = fmaf(p.beta, arow[col0 + j], r[j]);
-            }
-          }
-          if (p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const uint64_t g = gelu2(pack2(r[j], r[j + 1]));
-              r[j] = lo2(g);
-              r[j + 1] = hi2(g);
-            }
-          } else if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = act_apply_tm(r[j], p.act);
-          }
-          if (crow) {
-            // column blocks: the chunk sits inside one block whenever its first and last column do
-            const int blk0 = col0 / p.cbw, off0 = col0 - blk0 * p.cbw;
-            const bool one_blk = off0 + 32 <= p.cbw;
-            float* dst = crow + (size_t)blk0 * p.cbs + off0;
-            if (full && one_blk && p.vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-            } else if (one_blk) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = r[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = col0 + j;
-                if (col < p.N) crow[(size_t)(col / p.cbw) * p.cbs + col % p.cbw] = r[j];
-              }
-            }
-          }
-          if (ctb) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (col < p.N) ctb[(size_t)col * p.ldct] = r[j];      // lanes = consecutive rows: coalesced
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, t, nchunk, tm + buf * (ACC_COLS / 2), q, half, lane, p.alpha);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);      // this warp's TMEM reads of the buffer are complete
@@ -460,6 +470,235 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<1>(tm, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fp16-split mode (precise = 2): the products whose B operand is a WEIGHT (nn.Linear / conv weights: static, so its split
+// is made once, acmil_gemm_split_b).  a b ~= a_hi b_hi + a_lo b_hi + a_hi b_lo with 11-bit hi parts and fp16 lo parts
+// (b pre-scaled by a power of two so that its lo parts stay in fp16's normal range): 3 kind::f16 MMAs of K = 16 where the
+// TF32 split needs 3 of K = 8 -- half the tensor-pipe time -- and per 64 columns of K a CTA moves 32 KB of A (TMA) +
+// 2 x BN x 128 B of B (TMA) into shared memory, reads A once (converter) and B three times (MMAs): 144 KB against
+// 256 KB for the same K in the TF32 engine, which is what bounds it (profiles/ncu_r1_gemm_summary.md).  Error: the a_lo b_lo
+// term (2^-22) and the fp16 rounding of the lo parts (2^-23 of |a|, absolute floor 2^-25): fp32-level for |a| < 65504.
+// Same roles as tm_gemm_kernel: warp 0 TMA, warp 1 MMA issue, warps 2-5 A converters (TMEM operand slots), warps 6-13 epilogue.
+constexpr int KCH = 64;                       // K columns per stage
+constexpr uint32_t H_A_SLOT = 64;             // TMEM columns per A operand slot: 32 packed hi + 32 packed lo
+template <int BN>
+__host__ __device__ constexpr uint32_t h_stage_bytes() {
+  return 2u * TILE_BYTES + 2u * (uint32_t)BN * 128u;      // two 128 x 32 fp32 A tiles, B hi, B lo (BN rows of 64 halves)
+}
+template <int BN>
+__host__ __device__ constexpr int h_stages() {
+  return BN <= 64 ? 4 : 3;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // low half = a
+  return r;
+}
+// two fp32 -> packed (hi, hi) and (lo, lo): hi = the top 11 significant bits (exact in fp16), lo = the rest rounded to fp16
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  hi = pack_h2(ah, bh);
+  lo = pack_h2(a - ah, b - bh);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(KC == 32, "the fp16-split kernel stages A as 128-byte fp32 rows");
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t BH_BYTES = (uint32_t)BN * 128u;
+  constexpr uint32_t STAGE = h_stage_bytes<BN>();
+  constexpr int NS = h_stages<BN>();
+  constexpr uint32_t ACC_COLS = 2 * BN;
+  constexpr uint32_t TM_A = ACC_COLS;
+  constexpr uint32_t TM_NEED = ACC_COLS + NS * H_A_SLOT;
+  constexpr uint32_t TM_COLS = TM_NEED <= 256 ? 256 : 512;
+  static_assert(TM_NEED <= 512 && BN >= 32, "TMEM budget");
+  Bars* bars = reinterpret_cast<Bars*>(smem + NS * STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM;
+  const int ntiles = p.ntiles;
+  const int nchunk = (p.K + KCH - 1) / KCH;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 4);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 8);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.ta);
+    tma_prefetch_desc(&p.tbh);
+    tma_prefetch_desc(&p.tbl);
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(&bars->tmem, TM_COLS);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = bars->tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ctr = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+        const int zlo = p.a_batched ? t.bz % p.zdiv : 0, zhi = p.a_batched ? t.bz / p.zdiv : 0;
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+          mbar_wait(&bars->empty[s], ph ^ 1u);
+          unsigned char* st = smem + s * STAGE;
+          const bool second = c * KCH + 32 < p.K;      // the K tail may end inside the first 32-column box of the chunk
+          mbar_expect_tx(&bars->full[s], (second ? 2u : 1u) * TILE_BYTES + 2u * BH_BYTES);
+          tma_load_4d(st, &p.ta, c * KCH, t.m0, zlo, zhi, &bars->full[s]);
+          if (second) tma_load_4d(st + TILE_BYTES, &p.ta, c * KCH + 32, t.m0, zlo, zhi, &bars->full[s]);
+          tma_load_2d(st + 2 * TILE_BYTES, &p.tbh, c * KCH, t.n0, &bars->full[s]);
+          tma_load_2d(st + 2 * TILE_BYTES + BH_BYTES, &p.tbl, c * KCH, t.n0, &bars->full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    uint32_t ctr = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tm + buf * (ACC_COLS / 2);
+      for (int c = 0; c < nchunk; ++c, ++ctr) {
+        const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+        mbar_wait(&bars->full[s], ph);       // B hi / lo have landed
+        mbar_wait(&bars->split[s], ph);      // A operands are in TMEM
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(smem + s * STAGE + 2 * TILE_BYTES), b_lo = b_hi + BH_BYTES;
+        const uint32_t ta_hi = tm + TM_A + s * H_A_SLOT, ta_lo = ta_hi + 32;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KCH / 16; ++k) {      // one MMA covers K = 16 halves = 32 bytes of the swizzle row = 8 TMEM columns
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_ts<1>(tacc, ta_lo + k * 8, umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+            umma_ts<1>(tacc, ta_hi + k * 8, umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
+            umma_ts<1>(tacc, ta_hi + k * 8, umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
+          }
+          umma_commit(&bars->empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bars->acc_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // converters: thread = row of the A tile; the two landed 32-column fp32 tiles are read once (de-swizzled LDS.128) and
+    // written to the stage's TMEM operand slot as packed fp16 pairs: columns [0, 32) hi, [32, 64) lo
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    uint32_t ctr = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < nchunk; ++c, ++ctr) {
+        const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+        mbar_wait(&bars->full[s], ph);
+        const uint32_t ta = tm + lane_addr + TM_A + s * H_A_SLOT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned char* rowp = smem + s * STAGE + h * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+          const bool landed = h == 0 || c * KCH + 32 < p.K;      // a second box wholly past K is not loaded: zeros
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = landed ? *reinterpret_cast<const float4*>(rowp + ((i ^ (r & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            split_h2(v.x, v.y, hi[2 * i], lo[2 * i]);
+            split_h2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
+          }
+          tmem_st16(ta + 16 * h, hi);
+          tmem_st16(ta + 32 + 16 * h, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->split[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 6) >> 2;
+    const float alpha = p.alpha * (p.bscale ? __ldg(p.bscale) : 1.f);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
+      const uint32_t buf = it & 1u;
+      mbar_wait(&bars->acc_full[buf], (it >> 1) & 1u);
+      tc_fence_after();
+      epilogue_tile<BN>(p, t, nchunk, tm + buf * (ACC_COLS / 2), q, half, lane, alpha);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tm, TM_COLS);
+}
+
+// ---- pre-split image of a B operand: [256-byte header][hi: rows x ld16 fp16][lo: rows x ld16 fp16], ld16 = K rounded up to 8
+struct SplitHeader {
+  float inv_scale, scale;
+  unsigned max_bits;             // bit pattern of max |b| (non-negative floats order like unsigned integers)
+  int rows, k;
+};
+constexpr size_t SPLIT_HDR = 256;
+inline int64_t split_ld(int k) { return ((int64_t)k + 7) / 8 * 8; }
+inline size_t split_section(int rows, int k) { return ((size_t)rows * (size_t)split_ld(k) * 2 + 255) / 256 * 256; }
+
+__global__ void __launch_bounds__(256) tm_split_max_kernel(const float* __restrict__ b, int rows, int k, long long ld, SplitHeader* h) {
+  float mx = 0.f;
+  const size_t total = (size_t)rows * k;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256)
+    mx = fmaxf(mx, fabsf(b[(e / k) * ld + e % k]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&h->max_bits, __float_as_uint(mx));
+}
+
+__global__ void __launch_bounds__(256) tm_split_write_kernel(const float* __restrict__ b, int rows, int k, long long ld, int ld16,
+                                                             SplitHeader* h, uint32_t* __restrict__ hi, uint32_t* __restrict__ lo) {
+  // power-of-two scale that puts max |b| into [2^13, 2^14): the lo parts (<= 2^-11 of their value) of every element within
+  // 2^-13 of the maximum stay normal fp16 numbers, and the scaling itself is exact
+  const float mx = __uint_as_float(h->max_bits);
+  float scale = 1.f;
+  if (mx > 0.f && mx < 3.0e38f) {
+    int e;
+    frexpf(mx, &e);
+    scale = ldexpf(1.f, max(-100, min(100, 14 - e)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    h->scale = scale;
+    h->inv_scale = 1.f / scale;
+    h->rows = rows;
+    h->k = k;
+  }
+  const int pr = ld16 / 2;
+  const size_t total = (size_t)rows * pr;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const size_t row = e / pr;
+    const int col = (int)(e % pr) * 2;
+    const float v0 = col < k ? b[row * ld + col] * scale : 0.f;
+    const float v1 = col + 1 < k ? b[row * ld + col + 1] * scale : 0.f;
+    uint32_t a, c;
+    split_h2(v0, v1, a, c);
+    hi[e] = a;
+    lo[e] = c;
+  }
 }
 
 // k-split: sum the partial tiles in a fixed order, then the same epilogue terms
@@ -547,13 +786,48 @@ int launch(const GemmParams& gp, int batch, cudaStream_t st) {
   return ACMIL_OK;
 }
 
+int make_map_h(CUtensorMap* m, const void* base, int rows, int k, int64_t ld16, int box_rows, const char* what) {
+  EncodeFn enc = tm_get_encode();
+  ACMIL_REQUIRE(enc != nullptr, ACMIL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  ACMIL_REQUIRE(((uintptr_t)base & 15) == 0 && ld16 % 8 == 0, ACMIL_E_INVALID, "gemm: split image section %s is not 16-byte aligned", what);
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld16 * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KCH, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACMIL_REQUIRE(r == CUDA_SUCCESS, ACMIL_E_CUDA, "cuTensorMapEncodeTiled failed for %s (%d)", what, (int)r);
+  return ACMIL_OK;
+}
+
+template <int BN>
+int launch_h(const GemmParams& gp, int batch, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = (size_t)h_stages<BN>() * h_stage_bytes<BN>() + sizeof(Bars) + 1024;
+  if (!configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_gemm_h_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int dev = 0, n_sm = 0;
+  ACMIL_CHECK_CUDA(cudaGetDevice(&dev));
+  ACMIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  GemmParams gq = gp;
+  const long long tiles = (long long)((gp.N + BN - 1) / BN) * ((gp.M + BM - 1) / BM) * batch;
+  ACMIL_REQUIRE(tiles < (1ll << 31), ACMIL_E_INVALID, "gemm: too many tiles");
+  gq.ntiles = (int)tiles;
+  tm_gemm_h_kernel<BN><<<(unsigned)std::min<long long>(tiles, n_sm), GT, smem, st>>>(gq);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
 }  // namespace
 
 int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
   ACMIL_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0 && d.batch > 0, ACMIL_E_INVALID, "gemm: empty problem (%d x %d x %d, batch %d)", d.m,
                 d.n, d.k, d.batch);
-  ACMIL_REQUIRE(d.a && d.b && (d.c || d.ct), ACMIL_E_INVALID, "gemm: null operand");
+  ACMIL_REQUIRE(d.a && (d.b || d.b_split) && (d.c || d.ct), ACMIL_E_INVALID, "gemm: null operand");
   const int ksplit = d.k_split > 1 ? d.k_split : 1;
   ACMIL_REQUIRE(ksplit == 1 || d.split_ws != nullptr, ACMIL_E_INVALID, "gemm: k_split needs split_ws");
   GemmParams gp{};
@@ -565,10 +839,30 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   ACMIL_REQUIRE((!a_b || ((zdiv == 1 || d.a_batch_stride) && (n_hi == 1 || d.a_batch_stride2))) &&
                     (!b_b || ((zdiv == 1 || d.b_batch_stride) && (n_hi == 1 || d.b_batch_stride2))),
                 ACMIL_E_INVALID, "gemm: a batched operand needs a non-zero stride on every batch level in use");
+  // precise = 2 with a pre-split image of B (acmil_gemm_split_b): the fp16-split kernel; without an image it means precise = 1
+  const bool hmode = d.precise == 2 && d.b_split != nullptr;
+  if (hmode) {
+    ACMIL_REQUIRE(!b_b && ksplit == 1, ACMIL_E_INVALID, "gemm: a pre-split B operand cannot be batched or k-split");
+    ACMIL_REQUIRE(d.b_split_rows >= 1 && d.b_split_row0 >= 0 && (int64_t)d.b_split_row0 + d.n <= d.b_split_rows, ACMIL_E_INVALID,
+                  "gemm: rows [%d, %d) are outside the split image (%d rows)", d.b_split_row0, d.b_split_row0 + d.n, d.b_split_rows);
+    ACMIL_REQUIRE(((uintptr_t)d.b_split & 255) == 0, ACMIL_E_INVALID, "gemm: the split image must be 256-byte aligned");
+  }
   int rc = make_map(&gp.ta, d.a, d.m, d.k, d.lda, a_b ? zdiv : 1, d.a_batch_stride, a_b ? n_hi : 1, d.a_batch_stride2, BM, "A");
   if (rc) return rc;
-  rc = make_map(&gp.tb, d.b, d.n, d.k, d.ldb, b_b ? zdiv : 1, d.b_batch_stride, b_b ? n_hi : 1, d.b_batch_stride2, bn, "B");
-  if (rc) return rc;
+  if (hmode) {
+    const int64_t ld16 = split_ld(d.k);
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(d.b_split);
+    const unsigned char* hi = img + SPLIT_HDR + (size_t)d.b_split_row0 * ld16 * 2;
+    rc = make_map_h(&gp.tbh, hi, d.n, d.k, ld16, bn, "B hi");
+    if (rc) return rc;
+    rc = make_map_h(&gp.tbl, hi + split_section(d.b_split_rows, d.k), d.n, d.k, ld16, bn, "B lo");
+    if (rc) return rc;
+    gp.bscale = reinterpret_cast<const float*>(img);      // SplitHeader::inv_scale
+  } else {
+    ACMIL_REQUIRE(d.b != nullptr, ACMIL_E_INVALID, "gemm: null operand");
+    rc = make_map(&gp.tb, d.b, d.n, d.k, d.ldb, b_b ? zdiv : 1, d.b_batch_stride, b_b ? n_hi : 1, d.b_batch_stride2, bn, "B");
+    if (rc) return rc;
+  }
   gp.zdiv = zdiv;
   gp.c_bs2 = d.c_batch_stride2; gp.ct_bs2 = d.ct_batch_stride2; gp.add_bs2 = d.addend_batch_stride2;
   gp.c = d.c; gp.ct = d.ct; gp.bias = d.bias; gp.addend = d.addend;
@@ -589,6 +883,7 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.add_vec_ok = d.addend != nullptr && ((uintptr_t)d.addend & 15) == 0 && d.ld_addend % 4 == 0 &&
                   d.addend_batch_stride % 4 == 0 && d.addend_batch_stride2 % 4 == 0;
   gp.bias_vec_ok = d.bias != nullptr && !d.bias_per_row && ((uintptr_t)d.bias & 15) == 0;
+  if (hmode) return bn == 64 ? launch_h<64>(gp, d.batch, st) : launch_h<128>(gp, d.batch, st);
   if (d.precise) return bn == 64 ? launch<64, true>(gp, d.batch, st) : launch<128, true>(gp, d.batch, st);
   return bn == 64 ? launch<64, false>(gp, d.batch, st) : launch<128, false>(gp, d.batch, st);
 }
@@ -596,4 +891,30 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
 extern "C" int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream) {
   ACMIL_REQUIRE(desc != nullptr, ACMIL_E_INVALID, "gemm: null descriptor");
   return tm_gemm(*desc, (cudaStream_t)stream);
+}
+
+extern "C" int acmil_gemm_split_bytes(int32_t rows, int32_t k, size_t* bytes) {
+  ACMIL_REQUIRE(bytes != nullptr && rows >= 1 && k >= 1, ACMIL_E_INVALID, "gemm split: bad shape [%d, %d]", rows, k);
+  *bytes = SPLIT_HDR + 2 * split_section(rows, k);
+  return ACMIL_OK;
+}
+
+extern "C" int acmil_gemm_split_b(const float* d_b, int32_t rows, int32_t k, int64_t ldb, void* d_image, size_t image_bytes, void* stream) {
+  ACMIL_REQUIRE(acmil_device_count() > 0, ACMIL_E_CUDA, "no CUDA device: acmil_b200 has no CPU path");
+  ACMIL_REQUIRE(d_b && d_image && rows >= 1 && k >= 1 && ldb >= k, ACMIL_E_INVALID, "gemm split: bad arguments");
+  ACMIL_REQUIRE(((uintptr_t)d_image & 255) == 0, ACMIL_E_INVALID, "gemm split: the image must be 256-byte aligned");
+  const size_t need = SPLIT_HDR + 2 * split_section(rows, k);
+  ACMIL_REQUIRE(image_bytes >= need, ACMIL_E_WORKSPACE, "gemm split: image %zu < %zu bytes", image_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* img = reinterpret_cast<unsigned char*>(d_image);
+  SplitHeader* h = reinterpret_cast<SplitHeader*>(img);
+  ACMIL_CHECK_CUDA(cudaMemsetAsync(img, 0, SPLIT_HDR, st));
+  const size_t total = (size_t)rows * k;
+  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+  tm_split_max_kernel<<<grid, 256, 0, st>>>(d_b, rows, k, ldb, h);
+  tm_split_write_kernel<<<grid, 256, 0, st>>>(d_b, rows, k, ldb, (int)split_ld(k), h, reinterpret_cast<uint32_t*>(img + SPLIT_HDR),
+                                              reinterpret_cast<uint32_t*>(img + SPLIT_HDR + split_section(rows, k)));
+  g_acmil_launches += 2;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
 }

@@ -362,6 +362,14 @@ acmil_gemm_desc gemm0(int precise) {
   return g;
 }
 
+// B = rows [row0, row0 + g.n) of a weight matrix with `rows` rows: use its pre-split image when there is one (precise = 2)
+void use_split(acmil_gemm_desc& g, const void* image, int rows, int row0) {
+  if (g.precise != 2 || image == nullptr) return;
+  g.b_split = image;
+  g.b_split_rows = rows;
+  g.b_split_row0 = row0;
+}
+
 }  // namespace
 
 extern "C" int acmil_layernorm_rows(const float* d_x, int64_t ldx, int64_t rows, int32_t dim, const float* d_w, const float* d_b,
@@ -454,13 +462,22 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = w->d_wqkv; g.ldb = dim; g.n = inner;
     g.c = q + (size_t)b * h * np * d; g.ldc = d; g.col_block_width = d; g.col_block_stride = (int64_t)np * d;
     g.alpha = 1.f / sqrtf((float)d);
+    use_split(g, w->d_split_qkv, 3 * inner, 0);
     TM_RUN(tm_gemm(g, st));
     g.b = w->d_wqkv + (size_t)inner * dim; g.c = k + (size_t)b * h * np * d; g.alpha = 1.f;
+    use_split(g, w->d_split_qkv, 3 * inner, inner);
     TM_RUN(tm_gemm(g, st));
     acmil_gemm_desc gv = gemm0(P);
-    gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
-    gv.b = xn + (size_t)b * np * dim; gv.ldb = dim; gv.n = np;
-    gv.c = vt + (size_t)b * inner * np; gv.ldc = np;
+    if (P == 2 && w->d_split_qkv) {      // v = xn Wv^T on the fp16-split kernel, stored transposed by the epilogue
+      gv.a = xn + (size_t)b * np * dim; gv.lda = dim; gv.m = np; gv.k = dim; gv.batch = 1;
+      gv.b = w->d_wqkv + (size_t)2 * inner * dim; gv.ldb = dim; gv.n = inner;
+      gv.ct = vt + (size_t)b * inner * np; gv.ldct = np;
+      use_split(gv, w->d_split_qkv, 3 * inner, 2 * inner);
+    } else {
+      gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
+      gv.b = xn + (size_t)b * np * dim; gv.ldb = dim; gv.n = np;
+      gv.c = vt + (size_t)b * inner * np; gv.ldc = np;
+    }
     TM_RUN(tm_gemm(gv, st));
   }
   // 3. landmarks = group means (:98-114)
@@ -580,6 +597,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     if (d_residual && !s.padded_out) {
       g.addend = d_residual + (size_t)b * s.n * dim; g.ld_addend = dim; g.beta = 1.f;
     }
+    use_split(g, w->d_split_out, dim, 0);
     TM_RUN(tm_gemm(g, st));
   }
   return ACMIL_OK;
@@ -745,13 +763,22 @@ extern "C" int acmil_nystrom_shard_phase(const acmil_nystrom_shard* shard, const
     g.b = w->d_wqkv; g.ldb = dim; g.n = inner;
     g.c = q; g.ldc = d; g.col_block_width = d; g.col_block_stride = (int64_t)nl * d;
     g.alpha = 1.f / sqrtf((float)d);
+    use_split(g, w->d_split_qkv, 3 * inner, 0);
     TM_RUN(tm_gemm(g, st));
     g.b = w->d_wqkv + (size_t)inner * dim; g.c = k; g.alpha = 1.f;
+    use_split(g, w->d_split_qkv, 3 * inner, inner);
     TM_RUN(tm_gemm(g, st));
     acmil_gemm_desc gv = gemm0(P);      // v^T straight into the halo-extended buffer
-    gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
-    gv.b = xn; gv.ldb = dim; gv.n = nl;
-    gv.c = b.d_vt_ext + s.halo; gv.ldc = n_ext;
+    if (P == 2 && w->d_split_qkv) {
+      gv.a = xn; gv.lda = dim; gv.m = nl; gv.k = dim; gv.batch = 1;
+      gv.b = w->d_wqkv + (size_t)2 * inner * dim; gv.ldb = dim; gv.n = inner;
+      gv.ct = b.d_vt_ext + s.halo; gv.ldct = n_ext;
+      use_split(gv, w->d_split_qkv, 3 * inner, 2 * inner);
+    } else {
+      gv.a = w->d_wqkv + (size_t)2 * inner * dim; gv.lda = dim; gv.m = inner; gv.k = dim; gv.batch = 1;
+      gv.b = xn; gv.ldb = dim; gv.n = nl;
+      gv.c = b.d_vt_ext + s.halo; gv.ldc = n_ext;
+    }
     TM_RUN(tm_gemm(gv, st));
     dim3 grid(s.m_loc, H);
     tm_landmark_kernel<<<grid, 256, 0, st>>>(q, b.d_ql_loc, nl, s.m_loc, s.group_len, d);
@@ -862,6 +889,7 @@ extern "C" int acmil_nystrom_shard_phase(const acmil_nystrom_shard* shard, const
     g.bias = w->d_bout;
     g.c = b.d_out; g.ldc = dim;
     if (b.d_residual) { g.addend = b.d_residual; g.ld_addend = dim; g.beta = 1.f; }
+    use_split(g, w->d_split_out, dim, 0);
     TM_RUN(tm_gemm(g, st));
   }
   return ACMIL_OK;
@@ -983,6 +1011,7 @@ extern "C" int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weigh
     g.bias = w->d_patch_b;
     g.addend = w->d_pos_embed + D; g.ld_addend = D; g.beta = 1.f;
     g.c = x + D; g.ldc = D; g.c_batch_stride = (int64_t)Tp * D;
+    use_split(g, w->d_split_patch, D, 0);
     TM_RUN(tm_gemm(g, st));
   }
   const int64_t head_sz = rows * dh;      // one head of q (or k): [B * Tp][dh]
@@ -998,12 +1027,21 @@ extern "C" int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weigh
       g.a = xn; g.lda = D; g.m = (int)rows; g.k = D; g.batch = 1;
       g.b = bw.d_qkv_w; g.ldb = D; g.n = 2 * D; g.bias = bw.d_qkv_b;
       g.c = qk; g.ldc = dh; g.col_block_width = dh; g.col_block_stride = head_sz;
+      use_split(g, bw.d_split_qkv, 3 * D, 0);
       TM_RUN(tm_gemm(g, st));
       acmil_gemm_desc gv = gemm0(P);     // v transposed: [dim][B * Tp]
-      gv.a = bw.d_qkv_w + (size_t)2 * D * D; gv.lda = D; gv.m = D; gv.k = D; gv.batch = 1;
-      gv.b = xn; gv.ldb = D; gv.n = (int)rows;
-      gv.bias = bw.d_qkv_b + 2 * D; gv.bias_per_row = 1;
-      gv.c = vt; gv.ldc = rows;
+      if (P == 2 && bw.d_split_qkv) {    // v = xn Wv^T + b on the fp16-split kernel, stored transposed by the epilogue
+        gv.a = xn; gv.lda = D; gv.m = (int)rows; gv.k = D; gv.batch = 1;
+        gv.b = bw.d_qkv_w + (size_t)2 * D * D; gv.ldb = D; gv.n = D;
+        gv.bias = bw.d_qkv_b + 2 * D;
+        gv.ct = vt; gv.ldct = rows;
+        use_split(gv, bw.d_split_qkv, 3 * D, 2 * D);
+      } else {
+        gv.a = bw.d_qkv_w + (size_t)2 * D * D; gv.lda = D; gv.m = D; gv.k = D; gv.batch = 1;
+        gv.b = xn; gv.ldb = D; gv.n = (int)rows;
+        gv.bias = bw.d_qkv_b + 2 * D; gv.bias_per_row = 1;
+        gv.c = vt; gv.ldc = rows;
+      }
       TM_RUN(tm_gemm(gv, st));
     }
     {
@@ -1026,6 +1064,7 @@ extern "C" int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weigh
       g3.b = bw.d_proj_w; g3.ldb = D; g3.n = D; g3.bias = bw.d_proj_b;
       g3.addend = x; g3.ld_addend = D; g3.beta = 1.f;
       g3.c = x; g3.ldc = D;
+      use_split(g3, bw.d_split_proj, D, 0);
       TM_RUN(tm_gemm(g3, st));
     }
     // x = x + fc2(gelu(fc1(LN(x))))
@@ -1035,12 +1074,14 @@ extern "C" int acmil_vit_fwd(const acmil_vit_shape* shape, const acmil_vit_weigh
       g.a = xn; g.lda = D; g.m = (int)rows; g.k = D; g.batch = 1;
       g.b = bw.d_fc1_w; g.ldb = D; g.n = s.mlp_dim; g.bias = bw.d_fc1_b; g.act = 2;
       g.c = hid; g.ldc = s.mlp_dim;
+      use_split(g, bw.d_split_fc1, s.mlp_dim, 0);
       TM_RUN(tm_gemm(g, st));
       acmil_gemm_desc g2 = gemm0(P);
       g2.a = hid; g2.lda = s.mlp_dim; g2.m = (int)rows; g2.k = s.mlp_dim; g2.batch = 1;
       g2.b = bw.d_fc2_w; g2.ldb = s.mlp_dim; g2.n = D; g2.bias = bw.d_fc2_b;
       g2.addend = x; g2.ld_addend = D; g2.beta = 1.f;
       g2.c = x; g2.ldc = D;
+      use_split(g2, bw.d_split_fc2, D, 0);
       TM_RUN(tm_gemm(g2, st));
     }
   }

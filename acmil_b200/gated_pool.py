@@ -75,6 +75,7 @@ class GatedPool:
         self._w1 = None           # (w1, b1, (wv, bv, wu, bu, ww, bw)) fp32 copies of the last pack()
         self._tail: Optional["GatedPool"] = None
         self._wcat = self._wcat_key = None
+        self._imgs: dict = {}     # fp16 hi / lo images of w1 and [wv; wu] for the fp16-split GEMM kernel
         self._bufs: dict = {}
 
     # ------------------------------------------------------------------ weights
@@ -101,6 +102,7 @@ class GatedPool:
         self._keepalive = keep
         self._w1 = None if keep[0] is None else (keep[0], keep[1], tuple(keep[2:]))      # for _split_front
         self._wcat = self._wcat_key = None
+        self._imgs = {}
         return packed
 
     # ------------------------------------------------------------------ front projection on the GEMM engine
@@ -114,7 +116,7 @@ class GatedPool:
         if (not sp.front or n_masked > 0 or impl != L.IMPL_AUTO or self._w1 is None or x.shape[0] < 4096
                 or L.load().acmil_gp_umma_supported(C.byref(self._shape))):
             return None
-        from .transmil import gemm_nt
+        from .transmil import SplitImage, gemm_mode, gemm_nt
         if self._tail is None:
             tail_spec = GatedPoolSpec(d_in=sp.d_inner, d_inner=sp.d_inner, n_branch=sp.n_branch, d_attn=sp.d_attn, front=False,
                                       act_a=sp.act_a, gated=sp.gated, gate_bias=sp.gate_bias, score_bias=sp.score_bias)
@@ -122,13 +124,21 @@ class GatedPool:
         w1, b1, rest = self._w1
         packed2 = self._tail.pack(None, None, *rest)
         xf = x if x.dtype == torch.float32 else x.float()
-        h = gemm_nt(xf, w1, bias=b1, relu=sp.front_act == "relu", gelu=sp.front_act == "gelu")
+        def image(name, w):      # the weights are the B operands: pre-split once per pack()
+            if gemm_mode() != 2:
+                return None
+            if name not in self._imgs:
+                self._imgs[name] = SplitImage(w)
+            return self._imgs[name]
+
+        h = gemm_nt(xf, w1, bias=b1, relu=sp.front_act == "relu", gelu=sp.front_act == "gelu", b_split=image("w1", w1))
         # ... and the gate products h Wv^T | h Wu^T too (the kernel adds the biases, applies the gate and pools)
         wv, _bv, wu, _bu = rest[0], rest[1], rest[2], rest[3]
         if self._wcat is None or self._wcat_key != (wv.data_ptr(), None if wu is None else wu.data_ptr()):
             self._wcat = (torch.cat([wv, wu], 0) if sp.gated else wv).contiguous()
             self._wcat_key = (wv.data_ptr(), None if wu is None else wu.data_ptr())
-        zz = gemm_nt(h, self._wcat)
+            self._imgs.pop("wcat", None)
+        zz = gemm_nt(h, self._wcat, b_split=image("wcat", self._wcat))
         return self._tail, packed2, h, zz
 
     def invalidate(self) -> None:

@@ -18,7 +18,7 @@ from torch import nn
 from torchvision.models.resnet import BasicBlock
 
 from . import _lib as L
-from .transmil import _need_cuda, _no_grad_path, _ptr, _stream, gemm_nt
+from .transmil import SplitImage, _need_cuda, _no_grad_path, _ptr, _stream, gemm_mode, gemm_nt
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
@@ -81,7 +81,7 @@ class ResNet(nn.Module):
     # ------------------------------------------------------------------ folded weights, rebuilt when a tensor changes
     def _weights(self):
         tensors = list(self.parameters()) + list(self.buffers())
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = tuple((t.data_ptr(), t._version) for t in tensors) + (gemm_mode(),)
         if self._packed is None or key != self._packed_key:
             with torch.no_grad():
                 pk = {"conv1": _fold(self.conv1, self.bn1)}
@@ -91,6 +91,9 @@ class ResNet(nn.Module):
                         pk[f"l{li}.{bi}.2"] = _fold(blk.conv2, blk.bn2)
                         if blk.downsample is not None:
                             pk[f"l{li}.{bi}.d"] = _fold(blk.downsample[0], blk.downsample[1])
+                # the folded weights are the B operands of every product: fp16 hi / lo images for the fp16-split kernel
+                split = gemm_mode() == 2 and pk["conv1"][0].is_cuda
+                pk = {name: (w, b, SplitImage(w) if split else None) for name, (w, b) in pk.items()}
             self._packed, self._packed_key = pk, key
         return self._packed
 
@@ -101,14 +104,14 @@ class ResNet(nn.Module):
         kh, kw = conv.kernel_size
         s, p = conv.stride[0], conv.padding[0]
         Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
-        w, bias = wb
+        w, bias, img = wb
         if kh == 1 and kw == 1 and s == 1 and p == 0 and not nchw:
             col = x
         else:
             col = torch.empty(B * Ho * Wo, w.shape[1], device=x.device, dtype=torch.float32)
             L.check(L.load().acmil_im2col(_ptr(x), _ptr(col), B, H, W, Cin, kh, kw, s, p, w.shape[1], int(nchw),
                                           _stream(x.device)))
-        out = gemm_nt(col, w, bias=bias, addend=addend, relu=relu)
+        out = gemm_nt(col, w, bias=bias, addend=addend, relu=relu, b_split=img)
         return out, (B, Ho, Wo, conv.out_channels)
 
     def _features(self, x):

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+import threading
 
 import numpy as np
 import torch
@@ -28,6 +30,71 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def gemm_mode():
+    """``precise`` value of the products: 2 = weight products on the fp16-split kernel (pre-split weight images, half the
+    tensor-pipe time), everything else 3xTF32; ``ACMIL_GEMM_SPLIT=tf32`` keeps 3xTF32 everywhere (1)."""
+    return 1 if os.environ.get("ACMIL_GEMM_SPLIT", "f16").lower() == "tf32" else 2
+
+
+class SplitImage:
+    """fp16 hi / lo image of a 2-D fp32 weight (``acmil_gemm_split_b``): the B operand of ``gemm_nt(..., precise=2)``."""
+
+    def __init__(self, w2d):
+        _need_cuda(w2d, "SplitImage")
+        w2d = w2d.detach()
+        if w2d.dim() != 2:
+            raise ValueError(f"SplitImage expects a 2-D weight, got {tuple(w2d.shape)}")
+        w2d = w2d if w2d.stride(1) == 1 else w2d.contiguous()
+        self.rows, self.k = w2d.shape
+        lib = L.load()
+        nbytes = C.c_size_t(0)
+        L.check(lib.acmil_gemm_split_bytes(self.rows, self.k, C.byref(nbytes)))
+        self.image = torch.empty(nbytes.value, dtype=torch.uint8, device=w2d.device)
+        L.check(lib.acmil_gemm_split_b(_ptr(w2d), self.rows, self.k, w2d.stride(0), _ptr(self.image), nbytes.value,
+                                       _stream(w2d.device)))
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.image.data_ptr())
+
+
+class SplitCache:
+    """Split images of a module's weights, rebuilt when a weight's storage or version counter changes (``clear()`` after
+    an update through ``.data``, which bumps neither).  A new image is complete before ``get`` returns (the build is
+    followed by a stream synchronize unless the stream is being captured), so other host threads / streams may use it."""
+
+    def __init__(self):
+        self._d = {}
+        self._lock = threading.Lock()
+
+    def clear(self):
+        self._d.clear()
+
+    def __deepcopy__(self, memo):      # copies and pickles of the owning module start with an empty cache
+        return SplitCache()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def get(self, name, w, view=None):
+        """image of ``w`` (``view(w)`` if given: e.g. a conv weight flattened to 2-D); None unless gemm_mode() == 2"""
+        if gemm_mode() != 2:
+            return None
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+        with self._lock:
+            hit = self._d.get(name)
+            if hit is None or hit[0] != key:
+                with torch.no_grad(), torch.cuda.device(w.device):
+                    hit = (key, SplitImage(view(w) if view is not None else w))
+                    if not torch.cuda.is_current_stream_capturing():
+                        torch.cuda.current_stream().synchronize()
+                self._d[name] = hit
+        return hit[1]
+
+
 def _need_cuda(x, what):
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise RuntimeError(f"{what}: acmil_b200 runs on CUDA tensors only (no CPU path)")
@@ -41,11 +108,12 @@ def _no_grad_path(what, *tensors):
 
 
 def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu=False, gelu=False, precise=True,
-            out=None, out_t=None, k_split=1):
+            out=None, out_t=None, k_split=1, b_split=None, b_split_row0=0):
     """out[..., m, n] = alpha * a[..., m, k] @ b[..., n, k]^T (+ diag I) (+ bias) (+ beta * addend) (relu).
 
     ``a`` / ``b`` are fp32 CUDA tensors, 2-D or 3-D (leading batch; a 2-D operand is shared by the batch).
-    ``out_t`` optionally receives the transposed result."""
+    ``out_t`` optionally receives the transposed result.  ``b_split``: a ``SplitImage`` of the 2-D weight whose rows
+    ``b_split_row0 .. + n`` are ``b`` -- the product then runs on the fp16-split kernel (precise = 2)."""
     _need_cuda(a, "gemm_nt")
     _need_cuda(b, "gemm_nt")
     a3 = a if a.dim() == 3 else a.unsqueeze(0)
@@ -80,6 +148,10 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
         g.addend, g.ld_addend, g.addend_batch_stride = _ptr(ad), ad.stride(1), ad.stride(0) if ad.shape[0] > 1 else 0
     g.alpha, g.beta, g.diag, g.precise = float(alpha), float(beta), float(diag), int(precise)
     g.act = 2 if gelu else int(relu)
+    if b_split is not None:
+        if b.dim() != 2 or b_split.k != k or b_split_row0 + n > b_split.rows:
+            raise ValueError("gemm_nt: b_split does not match b")
+        g.precise, g.b_split, g.b_split_rows, g.b_split_row0 = 2, b_split.ptr, b_split.rows, int(b_split_row0)
     ws = None
     if k_split > 1:
         ws = torch.empty(k_split * batch * m * n, device=a.device, dtype=torch.float32)
@@ -119,8 +191,20 @@ class NystromAttention(nn.Module):
         if residual:
             self.res_conv = nn.Conv2d(heads, heads, (residual_conv_kernel, 1), padding=(residual_conv_kernel // 2, 0),
                                       groups=heads, bias=False)
-        self.precise = True      # 3xTF32 (fp32-faithful); False = plain TF32
+        self.precise = True      # fp32-faithful products (gemm_mode(): fp16-split weights + 3xTF32); False = plain TF32
         self._ws = None
+        self._split = SplitCache()
+
+    def _mode(self):
+        return gemm_mode() if self.precise else 0
+
+    def _split_ptrs(self, w):
+        """fills the optional split-image pointers of an acmil_nystrom_weights; returns what must stay alive"""
+        if self._mode() != 2:
+            return ()
+        qkv, out = self._split.get("qkv", self.to_qkv.weight), self._split.get("out", self.to_out[0].weight)
+        w.d_split_qkv, w.d_split_out = qkv.ptr, out.ptr
+        return qkv, out
 
     def _run(self, x, *, ln=None, residual=None, n_out=0, padded_out=False):
         _need_cuda(x, "NystromAttention")
@@ -132,7 +216,7 @@ class NystromAttention(nn.Module):
         b, n, dim = x.shape
         shape = L.NystromShape(b, n, dim, self.heads, self.dim_head, self.num_landmarks, self.pinv_iterations,
                                int(self.residual), self.conv_kernel if self.residual else 1, int(n_out), int(padded_out),
-                               int(self.precise))
+                               self._mode())
         lib = L.load()
         nbytes = C.c_size_t(0)
         L.check(lib.acmil_nystrom_workspace_bytes(C.byref(shape), C.byref(nbytes)))
@@ -143,6 +227,7 @@ class NystromAttention(nn.Module):
             w.d_ln_w, w.d_ln_b, w.ln_eps = _ptr(ln[0].contiguous()), _ptr(ln[1].contiguous()), float(ln[2])
         keep = [self.to_qkv.weight.contiguous(), self.to_out[0].weight.contiguous(), self.to_out[0].bias.contiguous()]
         w.d_wqkv, w.d_wout, w.d_bout = _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2])
+        keep.extend(self._split_ptrs(w))
         if self.residual:
             keep.append(self.res_conv.weight.contiguous())
             w.d_wconv = _ptr(keep[-1])
@@ -224,6 +309,7 @@ class TransMIL(nn.Module):
         self.layer2 = TransLayer(dim=conf.D_inner)
         self.norm = nn.LayerNorm(conf.D_inner)
         self._fc2 = nn.Linear(conf.D_inner, conf.n_class)
+        self._split = SplitCache()
 
     def forward(self, input):
         _need_cuda(input, "TransMIL")
@@ -238,7 +324,8 @@ class TransMIL(nn.Module):
         _H = _W = int(np.ceil(np.sqrt(n)))
         add = _H * _W - n
         h = torch.empty(B, 1 + _H * _W, D, device=x.device, dtype=torch.float32)
-        gemm_nt(x, fc1.weight, bias=fc1.bias, relu=True, out=h[:, 1:1 + n])      # _fc1 (:61)
+        gemm_nt(x, fc1.weight, bias=fc1.bias, relu=True, out=h[:, 1:1 + n],      # _fc1 (:61)
+                b_split=self._split.get("fc1", fc1.weight))
         if add:
             h[:, 1 + n:] = h[:, 1:1 + add]
         h[:, 0] = self.cls_token[0, 0]

@@ -179,7 +179,7 @@ def nystrom_shard_forward(attn, x_loc, plan: ShardPlan, rank: int, comm, *, ln=N
     n_real = n_loc - lead
     rows = n_real if n_out is None else int(n_out)
     shard = L.NystromShard(n_loc, lead, dim, heads, d, m, plan.m_loc, plan.l, attn.pinv_iterations, int(attn.residual),
-                           attn.conv_kernel if attn.residual else 1, int(attn.precise), 0 if rows == n_real else max(rows, 1),
+                           attn.conv_kernel if attn.residual else 1, attn._mode(), 0 if rows == n_real else max(rows, 1),
                            hf, hc, halo)
     nbytes = C.c_size_t(0)
     L.check(lib.acmil_nystrom_shard_workspace_bytes(C.byref(shard), C.byref(nbytes)))
@@ -198,6 +198,7 @@ def nystrom_shard_forward(attn, x_loc, plan: ShardPlan, rank: int, comm, *, ln=N
         keep += [ln[0].contiguous(), ln[1].contiguous()]
         w.d_ln_w, w.d_ln_b, w.ln_eps = _ptr(keep[-2]), _ptr(keep[-1]), float(ln[2])
     w.d_wqkv, w.d_wout, w.d_bout = _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2])
+    keep.extend(attn._split_ptrs(w))
     if attn.residual:
         keep.append(attn.res_conv.weight.contiguous())
         w.d_wconv = _ptr(keep[-1])
@@ -279,7 +280,8 @@ def transmil_forward_sharded(model, x_rows, n: int, rank: int, comm):
     if x_rows.shape[0] != t1 - t0 - first:
         raise ValueError(f"rank {rank}: expected {t1 - t0 - first} patch rows, got {x_rows.shape[0]}")
     if x_rows.shape[0]:
-        gemm_nt(x_rows.contiguous(), fc1.weight, bias=fc1.bias, relu=True, out=h[first:])        # _fc1 (:61)
+        gemm_nt(x_rows.contiguous(), fc1.weight, bias=fc1.bias, relu=True, out=h[first:],        # _fc1 (:61)
+                b_split=model._split.get("fc1", fc1.weight))
     if t0 == 0:
         h[0] = model.cls_token[0, 0]
     l1, l2 = model.layer1, model.layer2

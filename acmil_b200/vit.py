@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .transmil import _need_cuda, _no_grad_path, _ptr, _stream
+from .transmil import SplitCache, _need_cuda, _no_grad_path, _ptr, _stream, gemm_mode
 
 
 class _PatchEmbed(nn.Module):
@@ -71,6 +71,7 @@ class VisionTransformer(nn.Module):
         self.head = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
         self.precise = True
         self._ws = None
+        self._split = SplitCache()
         self._init_weights()
 
     def _init_weights(self):      # timm: trunc_normal_(std=.02) for pos_embed / Linear weights, zero biases, cls ~ N(0, 1e-6)
@@ -93,7 +94,8 @@ class VisionTransformer(nn.Module):
         blk0 = self.blocks[0]
         n_class = head_w.shape[0] if head_w is not None else 0
         shape = L.VitShape(B, pe.img_size, pe.patch_size, pe.proj.in_channels, self.embed_dim, len(self.blocks),
-                           blk0.attn.num_heads, blk0.mlp.fc1.out_features, n_class, int(self.precise), float(self.norm.eps))
+                           blk0.attn.num_heads, blk0.mlp.fc1.out_features, n_class, gemm_mode() if self.precise else 0,
+                           float(self.norm.eps))
         lib = L.load()
         nbytes = C.c_size_t(0)
         L.check(lib.acmil_vit_workspace_bytes(C.byref(shape), C.byref(nbytes)))
@@ -106,14 +108,24 @@ class VisionTransformer(nn.Module):
             keep.append(t)
             return _ptr(t)
 
+        split = self._split.get if self.precise else (lambda *a, **k: None)      # weight images for the fp16-split products
+
+        def sp(name, t, view=None):
+            img = split(name, t, view)
+            keep.append(img)
+            return img.ptr if img is not None else None
+
         blocks = (L.VitBlockWeights * len(self.blocks))()
         for i, b in enumerate(self.blocks):
             blocks[i] = L.VitBlockWeights(p(b.norm1.weight), p(b.norm1.bias), p(b.attn.qkv.weight), p(b.attn.qkv.bias),
                                           p(b.attn.proj.weight), p(b.attn.proj.bias), p(b.norm2.weight), p(b.norm2.bias),
-                                          p(b.mlp.fc1.weight), p(b.mlp.fc1.bias), p(b.mlp.fc2.weight), p(b.mlp.fc2.bias))
+                                          p(b.mlp.fc1.weight), p(b.mlp.fc1.bias), p(b.mlp.fc2.weight), p(b.mlp.fc2.bias),
+                                          sp(f"{i}.qkv", b.attn.qkv.weight), sp(f"{i}.proj", b.attn.proj.weight),
+                                          sp(f"{i}.fc1", b.mlp.fc1.weight), sp(f"{i}.fc2", b.mlp.fc2.weight))
         w = L.VitWeights(p(self.cls_token), p(self.pos_embed), p(pe.proj.weight), p(pe.proj.bias), p(self.norm.weight),
                          p(self.norm.bias), p(head_w) if head_w is not None else None,
-                         p(head_b) if head_b is not None else None, blocks)
+                         p(head_b) if head_b is not None else None, blocks,
+                         sp("patch", pe.proj.weight, lambda t: t.reshape(t.shape[0], -1)))
         feats = torch.empty(B, self.embed_dim, device=x.device, dtype=torch.float32)
         logits = torch.empty(B, n_class, device=x.device, dtype=torch.float32) if n_class else None
         L.check(lib.acmil_vit_fwd(C.byref(shape), C.byref(w), _ptr(x), _ptr(feats), _ptr(logits), _ptr(self._ws),

@@ -171,7 +171,7 @@ def run_ours(a, ClockSampler):
     line = {
         "metric": "slides/sec (Camelyon16-shape stream, ViT-S/16 extract -> ACMIL head)", "value": value, "unit": "slides/s",
         "n_gpus": world, "steps": len(sizes), "warmup": 2, "ms_per_step": ms / max(len(sizes), 1), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u8 -> f32 (3xTF32 tensor-core products) -> f16 bag -> f32 head",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 -> f32 (tensor-core products: fp16 hi/lo split on weight GEMMs, 3xTF32 elsewhere; ACMIL_GEMM_SPLIT=tf32: 3xTF32 everywhere) -> f16 bag -> f32 head",
         "data": "synthetic", "config": config(a, world, sizes),
         "patches_per_sec": n_patches / (ms * 1e-3),
         "full_size_estimate": {"slides": N_SLIDES_C16, "patches": full_patches if len(sizes) == N_SLIDES_C16 else None,
@@ -180,7 +180,7 @@ def run_ours(a, ClockSampler):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "whole stream per GPU (tm_gemm_kernel of the encoder dominates)",
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1345.7") +
-                                    "; the fp32-faithful 3xTF32 split costs 6 bf16-equivalent MMAs per product"},
+                                    "; fp32-faithful products cost 3 fp16 MMAs (weight GEMMs, pre-split images) or 3 TF32 MMAs = 6 bf16-equivalent (the rest)"},
         "clocks": clocks,
         "e2e": {"value": len(sizes) / wall, "unit": "slides/s", "h2d_bytes_per_step": int(n_patches / len(sizes) * 256 * 256 * 3),
                 "d2h_bytes_per_step": 8,

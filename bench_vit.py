@@ -79,7 +79,7 @@ def cpu_rate(batch, reps, resnet=False):
 
 def config(a, world, batch, cpu=False):
     return {"workload": f"{names(a)[0]} patch-feature extraction: uint8 256x256 RGB patches -> Resize(224)+normalise -> encoder -> fp16 "
-                        "features (BASELINE.json configs[3]; 100k patches = one slide), 3xTF32",
+                        "features (BASELINE.json configs[3]; 100k patches = one slide), fp32-faithful split products",
             "patches_per_step": batch * (1 if cpu else world), "parallelism": "cpu" if cpu else f"{world} data-parallel replica(s)",
             "l2_policy": "rotating resident patch batches (50 MB uint8 each, 154 MB fp32 after resize); activations of a batch exceed L2"}
 
@@ -189,12 +189,12 @@ def run_ours(a, ClockSampler):
     line = {
         "metric": f"patches/sec ({enc_name} feature extraction)", "value": rate, "unit": "patches/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8 -> f32 (3xTF32 tensor-core products) -> f16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u8 -> f32 (tensor-core products: fp16 hi/lo split on weight GEMMs, 3xTF32 elsewhere; ACMIL_GEMM_SPLIT=tf32: 3xTF32 everywhere) -> f16", "data": "synthetic",
         "config": config(a, world, batch), "slides_per_sec_100k_patches": rate / 1e5,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "whole step (tm_gemm_kernel dominates)", "algorithmic_flops_per_patch": flops,
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1345.7") +
-                                    "; the fp32-faithful 3xTF32 split costs 6 bf16-equivalent MMAs per product"},
+                                    "; fp32-faithful products cost 3 fp16 MMAs (weight GEMMs, pre-split images) or 3 TF32 MMAs = 6 bf16-equivalent (the rest)"},
         "clocks": clocks,
         "e2e": {"value": world * n_e2e * 2 * batch / dt, "unit": "patches/s", "h2d_bytes_per_step": world * batch * 256 * 256 * 3,
                 "d2h_bytes_per_step": world * batch * feat_dim * 4,

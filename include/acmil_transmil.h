@@ -34,7 +34,13 @@ extern "C" {
  *   d_ct + b * ct_batch_stride + col * ldct + row.
  * A batch stride of 0 shares the operand between batch entries.  All strides in floats; operand
  * pointers 16-byte aligned, lda / ldb multiples of 4.  precise = 1: 3xTF32 split (fp32-faithful,
- * ~2^-21), precise = 0: plain TF32 (~2^-10).  k_split > 1 partitions K over that many CTAs per tile
+ * ~2^-21), precise = 0: plain TF32 (~2^-10).  precise = 2 with b_split != NULL: B is read from a
+ * pre-split fp16 hi / lo image of a weight matrix (acmil_gemm_split_b; rows b_split_row0 .. + n of an
+ * image of b_split_rows rows whose K equals k; `b` is ignored, B cannot be batched or k-split) and A
+ * is split to fp16 hi / lo inside the kernel: 3 kind::f16 MMAs per product, half the tensor-pipe time
+ * and 56 % of the shared-memory traffic of the TF32 split, fp32-level accuracy (~2^-22) for
+ * |a| < 65504 (larger values saturate; |a| below 2^-14 keep an absolute 2^-25).  precise = 2 without
+ * an image behaves like precise = 1.  k_split > 1 partitions K over that many CTAs per tile
  * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction).
  * Two-level batches: with batch_inner > 0, entry z uses offsets (z % batch_inner) * X_batch_stride +
  * (z / batch_inner) * X_batch_stride2 for every operand X (e.g. z = head * images + image).
@@ -60,9 +66,20 @@ typedef struct acmil_gemm_desc {
   int32_t bias_per_row;           /* 1: bias is indexed by the output row instead of the column */
   int32_t reserved;
   int64_t a_batch_stride2, b_batch_stride2, c_batch_stride2, ct_batch_stride2, addend_batch_stride2;
+  const void* b_split;            /* precise = 2: image made by acmil_gemm_split_b, or NULL */
+  int32_t b_split_rows;           /* rows of the whole image */
+  int32_t b_split_row0;           /* first image row of this product's B */
 } acmil_gemm_desc;
 
 ACMIL_API int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream);
+
+/* Pre-split image of a weight matrix b [rows, k] (row-major, leading dimension ldb) for precise = 2:
+ * a 256-byte header (the power-of-two scale, chosen on the device from max |b|: no host sync), then the
+ * fp16 hi and lo sections, rows padded to a multiple of 8 halves.  The image is a function of the
+ * weight values only: rebuild it when they change.  256-byte aligned, acmil_gemm_split_bytes long. */
+ACMIL_API int acmil_gemm_split_bytes(int32_t rows, int32_t k, size_t* bytes);
+ACMIL_API int acmil_gemm_split_b(const float* d_b, int32_t rows, int32_t k, int64_t ldb, void* d_image, size_t image_bytes,
+                                 void* stream);
 
 /* out[r, :] = (x[r, :] - mean) / sqrt(var + eps) * w + b  (biased variance, like nn.LayerNorm). */
 ACMIL_API int acmil_layernorm_rows(const float* d_x, int64_t ldx, int64_t rows, int32_t dim, const float* d_w,
@@ -92,6 +109,8 @@ typedef struct acmil_nystrom_weights {
   const float* d_wout;            /* to_out.0.weight [dim, inner] */
   const float* d_bout;            /* to_out.0.bias   [dim] */
   const float* d_wconv;           /* res_conv.weight [heads, 1, conv_kernel, 1] */
+  const void* d_split_qkv;        /* optional acmil_gemm_split_b images of to_qkv.weight (all 3 * inner rows) and */
+  const void* d_split_out;        /* to_out.0.weight: used by the q, k and to_out products when precise = 2 */
 } acmil_nystrom_weights;
 
 ACMIL_API int acmil_nystrom_workspace_bytes(const acmil_nystrom_shape* shape, size_t* bytes);
@@ -172,6 +191,8 @@ typedef struct acmil_vit_shape {
 typedef struct acmil_vit_block_weights {
   const float *d_ln1_w, *d_ln1_b, *d_qkv_w, *d_qkv_b, *d_proj_w, *d_proj_b;
   const float *d_ln2_w, *d_ln2_b, *d_fc1_w, *d_fc1_b, *d_fc2_w, *d_fc2_b;
+  /* optional acmil_gemm_split_b images of qkv.weight (all 3 * dim rows), proj / fc1 / fc2 .weight (precise = 2) */
+  const void *d_split_qkv, *d_split_proj, *d_split_fc1, *d_split_fc2;
 } acmil_vit_block_weights;
 
 typedef struct acmil_vit_weights {
@@ -180,6 +201,7 @@ typedef struct acmil_vit_weights {
   const float *d_norm_w, *d_norm_b;           /* final norm */
   const float *d_head_w, *d_head_b;           /* [n_class, dim], [n_class] or NULL */
   const acmil_vit_block_weights* blocks;      /* HOST array of `depth` entries */
+  const void* d_split_patch;                  /* optional split image of patch_embed.proj.weight as [dim, in_ch * patch^2] */
 } acmil_vit_weights;
 
 ACMIL_API int acmil_vit_workspace_bytes(const acmil_vit_shape* shape, size_t* bytes);

@@ -42,12 +42,12 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.GpOutputs) == 64
     assert C.sizeof(L.GpConsts) == (3 * 128 + 8 * 128 + 8 + 4) * 4 + 16
     # include/acmil_transmil.h
-    assert C.sizeof(L.GemmDesc) == 7 * 8 + 4 * 4 + 10 * 8 + 2 * 4 + 8 + 3 * 4 + 2 * 4 + 3 * 4 + 5 * 8
+    assert C.sizeof(L.GemmDesc) == 7 * 8 + 4 * 4 + 10 * 8 + 2 * 4 + 8 + 3 * 4 + 2 * 4 + 3 * 4 + 5 * 8 + 8 + 2 * 4
     assert C.sizeof(L.NystromShape) == 16 * 4
-    assert C.sizeof(L.NystromWeights) == 7 * 8
+    assert C.sizeof(L.NystromWeights) == 9 * 8
     assert C.sizeof(L.VitShape) == 16 * 4
-    assert C.sizeof(L.VitBlockWeights) == 12 * 8
-    assert C.sizeof(L.VitWeights) == 9 * 8
+    assert C.sizeof(L.VitBlockWeights) == 16 * 8
+    assert C.sizeof(L.VitWeights) == 10 * 8
 
 
 def test_transmil_host_entry_points_and_validation():
@@ -61,6 +61,10 @@ def test_transmil_host_entry_points_and_validation():
     bad = L.NystromShape(1, 100, 512, 8, 64, 254, 6, 1, 33, 0, 0, 1)
     assert lib.acmil_nystrom_workspace_bytes(C.byref(bad), C.byref(n)) == -1
     assert b"num_landmarks" in lib.acmil_last_error()
+    # pre-split weight image: 256-byte header + fp16 hi / lo sections, rows padded to 8 halves, sections to 256 bytes
+    assert lib.acmil_gemm_split_bytes(384, 1536, C.byref(n)) == 0 and n.value == 256 + 2 * 384 * 1536 * 2
+    assert lib.acmil_gemm_split_bytes(3, 13, C.byref(n)) == 0 and n.value == 256 + 2 * 256
+    assert lib.acmil_gemm_split_bytes(0, 13, C.byref(n)) == -1
     if not torch.cuda.is_available():      # no CPU path: compute entry points refuse loudly
         g = L.GemmDesc()
         g.a = g.b = g.c = 256
@@ -68,6 +72,7 @@ def test_transmil_host_entry_points_and_validation():
         g.batch = 1
         g.lda = g.ldb = g.ldc = 128
         assert lib.acmil_gemm_nt(C.byref(g), None) == -2
+        assert lib.acmil_gemm_split_b(C.c_void_p(256), 8, 8, 8, C.c_void_p(256), 1 << 20, None) == -2
         assert lib.acmil_layernorm_rows(C.c_void_p(256), 8, 1, 8, None, None, 1e-5, C.c_void_p(256), 8, None) == -2
 
 

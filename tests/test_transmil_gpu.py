@@ -61,6 +61,83 @@ def test_gemm_nt_epilogue_terms_and_layouts():
     assert float(buf[:, :5].abs().max()) == 0 and float(buf[:, 205:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("m,n,k,wscale", [(300, 200, 384, 0.02), (1000, 384, 1536, 0.02), (257, 70, 40, 1.0), (128, 64, 100, 50.0),
+                                           (513, 130, 64, 1e-4), (50, 8, 24, 0.3), (2000, 1536, 384, 0.02)])
+def test_gemm_fp16_split_weights_matches_fp64(m, n, k, wscale):
+    """precise = 2: B from a pre-split fp16 hi / lo image of the weight (acmil_gemm_split_b), A split in the kernel.  The
+    K tails (40, 100: the second 32-column A box of the last chunk is partly / wholly out of range), N / M tails and the
+    power-of-two weight scaling (weights of 1e-4 .. 50) all against fp64; accuracy must be that of the 3xTF32 mode."""
+    from acmil_b200.transmil import SplitImage, gemm_nt
+    g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
+    a = torch.randn(m, k, generator=g)
+    a[::7] *= 30.0                                   # rows of different magnitude: no per-row scaling is assumed
+    a[1::5] *= 1e-3
+    w = torch.randn(n, k, generator=g) * wscale
+    bias = torch.randn(n, generator=g)
+    ref = a.double() @ w.double().T
+    # error scale of each dot product: the fp16 lo part of a has an absolute floor of 2^-25 (elements below 0.25)
+    bound = ((a.double().abs() + 0.125) @ w.double().abs().T)
+    img = SplitImage(w.to(dev()))
+    out = gemm_nt(a.to(dev()), w.to(dev()), b_split=img).cpu().double()
+    err = float(((out - ref).abs() / bound.clamp(min=1e-30)).max())
+    out1 = gemm_nt(a.to(dev()), w.to(dev())).cpu().double()
+    err1 = float(((out1 - ref).abs() / bound.clamp(min=1e-30)).max())
+    # both splits are exact to ~2^-22 per product; what is left is the tensor core's truncating fp32 accumulation
+    # (measured on B200: 7.6e-7 .. 8.5e-7 of sum |a||w| for the fp16 split), the same for either kind
+    assert err < 3e-6 and err < 4 * err1 + 5e-7, (err, err1)
+    # epilogue terms ride on the same code as the TF32 kernels
+    add = torch.randn(m, n, generator=g)
+    out2 = gemm_nt(a.to(dev()), w.to(dev()), b_split=img, bias=bias.to(dev()), addend=add.to(dev()), alpha=0.5, beta=2.0,
+                   relu=True).cpu().double()
+    ref2 = torch.relu(0.5 * ref + bias.double() + 2.0 * add.double())
+    assert float(((out2 - ref2).abs() / (bound + 1.0)).max()) < 1e-6
+
+
+def test_gemm_fp16_split_row_ranges_batches_and_errors():
+    from acmil_b200 import _lib as L
+    from acmil_b200.transmil import SplitImage, gemm_nt
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(3 * 96, 128, generator=g) * 0.05                      # a to_qkv-like weight: three row blocks
+    a = torch.randn(4, 150, 128, generator=g)                             # batched A, shared weight
+    img = SplitImage(w.to(dev()))
+    for blk in range(3):
+        wb = w[blk * 96:(blk + 1) * 96]
+        out = gemm_nt(a.to(dev()), wb.to(dev()), b_split=img, b_split_row0=blk * 96).cpu().double()
+        ref = a.double() @ wb.double().T
+        assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    # an all-zero weight (scale falls back to 1) and a strided weight view
+    z = torch.zeros(16, 64)
+    assert float(gemm_nt(a[0, :, :64].contiguous().to(dev()), z.to(dev()), b_split=SplitImage(z.to(dev()))).abs().max()) == 0.0
+    wv = torch.randn(40, 200, generator=g).to(dev())[:, :128]
+    out = gemm_nt(a[0].to(dev()), wv, b_split=SplitImage(wv)).cpu().double()
+    ref = a[0].double() @ wv.cpu().double().T
+    assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    with pytest.raises(ValueError):
+        gemm_nt(a.to(dev()), w[:96].to(dev()), b_split=img, b_split_row0=250)
+    with pytest.raises(ValueError):
+        gemm_nt(a[..., :64].contiguous().to(dev()), w[:96, :64].contiguous().to(dev()), b_split=img)
+    with pytest.raises(L.AcmilError):      # a pre-split B cannot be k-split
+        gemm_nt(a.to(dev()), w[:96].to(dev()), b_split=img, k_split=2)
+
+
+def test_modules_agree_between_the_fp16_split_and_the_tf32_split(monkeypatch):
+    """The weight products of TransMIL run on the fp16-split kernel by default; ACMIL_GEMM_SPLIT=tf32 keeps every product
+    on 3xTF32.  Both are fp32-faithful: the logits agree to 1e-4 relative (and each is checked against the reference's
+    fixtures elsewhere in this file under the default)."""
+    from acmil_b200 import Struct, TransMIL
+    import acmil_b200.transmil as T
+    torch.manual_seed(3)
+    m = TransMIL(Struct(D_feat=384, D_inner=128, n_class=3)).to(dev()).eval()
+    x = torch.randn(1, 1500, 384, device=dev())
+    with torch.no_grad():
+        assert T.gemm_mode() == 2
+        y2 = m(x)
+        monkeypatch.setenv("ACMIL_GEMM_SPLIT", "tf32")
+        assert T.gemm_mode() == 1
+        y1 = m(x)
+    assert float((y1 - y2).abs().max()) <= 1e-4 * max(1.0, float(y1.abs().max()))
+
+
 def test_gemm_gelu_epilogue_is_the_exact_erf_gelu_within_6e7():
     """The fc1 epilogue of the ViT MLP evaluates nn.GELU (exact-erf, timm's default act_layer) with the
     Abramowitz-Stegun 7.1.26 erf on packed fp32 -- a deliberate deviation from libm's erff.  Bound it by itself, over
