@@ -95,7 +95,8 @@ class GemmDesc(C.Structure):
                    ("precise", C.c_int32), ("batch_inner", C.c_int32), ("bias_per_row", C.c_int32), ("reserved", C.c_int32)]
                 + [(n, C.c_int64) for n in ("a_batch_stride2", "b_batch_stride2", "c_batch_stride2", "ct_batch_stride2",
                                             "addend_batch_stride2")]
-                + [("b_split", C.c_void_p), ("b_split_rows", C.c_int32), ("b_split_row0", C.c_int32)])
+                + [("b_split", C.c_void_p), ("b_split_rows", C.c_int32), ("b_split_row0", C.c_int32),
+                   ("softmax_stats_out", C.c_void_p), ("softmax_stats_in", C.c_void_p)])
 
 
 class NystromShape(C.Structure):

@@ -48,6 +48,11 @@ struct GemmParams {
   CUtensorMap ta, tb;            // (K, rows, batch_lo, batch_hi) fp32
   CUtensorMap tbh, tbl;          // fp16-split mode: (K, rows) fp16 hi / lo sections of a pre-split B image
   const float* bscale;           // fp16-split mode: 1 / (power-of-two scale the image was made with), on the device
+  float2* stats_out;             // chunked softmax, producer side: the epilogue stores exp(c - chunk max) and (max, sum) per
+                                 //   (batch, row, 32-column chunk) at ((z * M + row) * nch_out + chunk)
+  const float2* stats_in;        // consumer side: A rows are such exponentials over K; the converter rescales chunk c of a row
+                                 //   by exp(max_c - row max) / row sum  (stats of nch_in = ceil(K / 32) chunks per row)
+  int nch_out, nch_in;
   float* c;
   float* ct;                     // optional transposed copy: ct[b] + col * ldct + row
   const float* bias;             // [N] or null
@@ -237,6 +242,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
             if (col0 + j < p.N) r[j] = fmaf(p.beta, arow[col0 + j], r[j]);
         }
       }
+      if (p.stats_out) {      // softmax numerators against the chunk's own maximum; the consumer GEMM finishes the softmax
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) mx = fmaxf(mx, r[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          r[j] = col0 + j < p.N ? __expf(r[j] - mx) : 0.f;
+          sum += r[j];
+        }
+        p.stats_out[((size_t)t.bz * p.M + row) * p.nch_out + (col0 >> 5)] = make_float2(mx, sum);
+      }
       if (p.act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -407,8 +425,20 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
         const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
         int kbeg, nchunk;
         k_range(t, kbeg, nchunk);
+        // chunked softmax, consumer side: this thread's A row holds exp(s - chunk max); finish the softmax on the way to TMEM
+        const float2* srow = nullptr;
+        float row_max = 0.f, row_inv = 0.f;
+        if (p.stats_in && t.m0 + r < p.M) {
+          srow = p.stats_in + ((size_t)t.bz * p.M + t.m0 + r) * p.nch_in;
+          row_max = -INFINITY;
+          for (int i = 0; i < p.nch_in; ++i) row_max = fmaxf(row_max, srow[i].x);
+          float l = 0.f;
+          for (int i = 0; i < p.nch_in; ++i) l += srow[i].y * __expf(srow[i].x - row_max);
+          row_inv = 1.f / l;
+        }
         for (int c = 0; c < nchunk; ++c, ++ctr) {
           const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+          const float f = srow ? __expf(srow[(kbeg >> 5) + c].x - row_max) * row_inv : (p.stats_in ? 0.f : 1.f);
           mbar_wait(&bars->full[s], ph);
           const unsigned char* rowp = smem + s * STAGE + (r >> 3) * 1024 + (r & 7) * 128;
           const uint32_t ta = tm + lane_addr + TM_A + s * A_SLOT_COLS;
@@ -417,7 +447,8 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 v = *reinterpret_cast<const float4*>(rowp + (((4 * h + i) ^ (r & 7)) << 4));
+              float4 v = *reinterpret_cast<const float4*>(rowp + (((4 * h + i) ^ (r & 7)) << 4));
+              if (p.stats_in) { v.x *= f; v.y *= f; v.z *= f; v.w *= f; }
               hi[4 * i] = __float_as_uint(v.x); hi[4 * i + 1] = __float_as_uint(v.y);
               hi[4 * i + 2] = __float_as_uint(v.z); hi[4 * i + 3] = __float_as_uint(v.w);
               lo[4 * i] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
@@ -831,7 +862,19 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   const int ksplit = d.k_split > 1 ? d.k_split : 1;
   ACMIL_REQUIRE(ksplit == 1 || d.split_ws != nullptr, ACMIL_E_INVALID, "gemm: k_split needs split_ws");
   GemmParams gp{};
-  const int bn = d.n <= 64 ? 64 : 128;
+  // 64-wide tiles when the problem is at most 64 columns wide, or when 128-wide tiles would leave more than half of the SMs
+  // idle (the 256^3 products of the pseudo-inverse iteration: 32 tiles -> 64)
+  int bn = d.n <= 64 ? 64 : 128;
+  if (bn == 128) {
+    static int n_sm_cached = 0;
+    if (n_sm_cached == 0) {
+      int dev = 0;
+      ACMIL_CHECK_CUDA(cudaGetDevice(&dev));
+      ACMIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_cached, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long t128 = (long long)((d.n + 127) / 128) * ((d.m + BM - 1) / BM) * d.batch * ksplit;
+    if (2 * t128 <= n_sm_cached) bn = 64;
+  }
   const int zdiv = d.batch_inner > 0 ? d.batch_inner : d.batch;
   ACMIL_REQUIRE(d.batch % zdiv == 0, ACMIL_E_INVALID, "gemm: batch %d is not a multiple of batch_inner %d", d.batch, zdiv);
   const int n_hi = d.batch / zdiv;
@@ -878,6 +921,18 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.k_per_split = ((((d.k + KC - 1) / KC) + ksplit - 1) / ksplit) * KC;
   gp.split_ws = d.split_ws;
 
+  if (d.softmax_stats_out) {
+    ACMIL_REQUIRE(ksplit == 1 && d.act == 0 && d.c != nullptr && d.ct == nullptr, ACMIL_E_INVALID,
+                  "gemm: softmax_stats_out needs a plain C output (no k_split, activation or transposed copy)");
+    gp.stats_out = reinterpret_cast<float2*>(d.softmax_stats_out);
+    gp.nch_out = (d.n + 31) / 32;
+  }
+  if (d.softmax_stats_in) {
+    ACMIL_REQUIRE(d.precise != 0 && !hmode && KC == 32, ACMIL_E_INVALID, "gemm: softmax_stats_in needs the 3xTF32 kernel (precise = 1)");
+    ACMIL_REQUIRE(((uintptr_t)d.softmax_stats_in & 7) == 0, ACMIL_E_INVALID, "gemm: softmax_stats_in must be 8-byte aligned");
+    gp.stats_in = reinterpret_cast<const float2*>(d.softmax_stats_in);
+    gp.nch_in = (d.k + 31) / 32;
+  }
   gp.vec_ok = d.c != nullptr && ((uintptr_t)d.c & 15) == 0 && d.ldc % 4 == 0 && gp.cbw % 4 == 0 && gp.cbs % 4 == 0 &&
               d.c_batch_stride % 4 == 0 && d.c_batch_stride2 % 4 == 0;
   gp.add_vec_ok = d.addend != nullptr && ((uintptr_t)d.addend & 15) == 0 && d.ld_addend % 4 == 0 &&

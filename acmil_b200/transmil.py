@@ -108,12 +108,15 @@ def _no_grad_path(what, *tensors):
 
 
 def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu=False, gelu=False, precise=True,
-            out=None, out_t=None, k_split=1, b_split=None, b_split_row0=0):
+            out=None, out_t=None, k_split=1, b_split=None, b_split_row0=0, stats_out=None, stats_in=None):
     """out[..., m, n] = alpha * a[..., m, k] @ b[..., n, k]^T (+ diag I) (+ bias) (+ beta * addend) (relu).
 
     ``a`` / ``b`` are fp32 CUDA tensors, 2-D or 3-D (leading batch; a 2-D operand is shared by the batch).
     ``out_t`` optionally receives the transposed result.  ``b_split``: a ``SplitImage`` of the 2-D weight whose rows
-    ``b_split_row0 .. + n`` are ``b`` -- the product then runs on the fp16-split kernel (precise = 2)."""
+    ``b_split_row0 .. + n`` are ``b`` -- the product then runs on the fp16-split kernel (precise = 2).
+    ``stats_out`` (fp32 ``[batch, m, ceil(n / 32), 2]``): the result is stored as exp(c - chunk max) per 32-column chunk
+    with the chunk's (max, sum) in ``stats_out``; a following product that passes the same tensor as ``stats_in`` with
+    those exponentials as ``a`` computes ``softmax(c) @ b^T`` (acmil_gemm_desc.softmax_stats_*)."""
     _need_cuda(a, "gemm_nt")
     _need_cuda(b, "gemm_nt")
     a3 = a if a.dim() == 3 else a.unsqueeze(0)
@@ -152,6 +155,11 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
         if b.dim() != 2 or b_split.k != k or b_split_row0 + n > b_split.rows:
             raise ValueError("gemm_nt: b_split does not match b")
         g.precise, g.b_split, g.b_split_rows, g.b_split_row0 = 2, b_split.ptr, b_split.rows, int(b_split_row0)
+    for name, t, cols in (("stats_out", stats_out, n), ("stats_in", stats_in, k)):
+        if t is not None:
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != batch * m * ((cols + 31) // 32) * 2:
+                raise ValueError(f"gemm_nt: {name} must be a contiguous fp32 CUDA tensor [batch, m, ceil(cols / 32), 2]")
+            setattr(g, "softmax_" + name, _ptr(t))
     ws = None
     if k_split > 1:
         ws = torch.empty(k_split * batch * m * n, device=a.device, dtype=torch.float32)

@@ -69,6 +69,14 @@ typedef struct acmil_gemm_desc {
   const void* b_split;            /* precise = 2: image made by acmil_gemm_split_b, or NULL */
   int32_t b_split_rows;           /* rows of the whole image */
   int32_t b_split_row0;           /* first image row of this product's B */
+  /* Chunked softmax across two products (scores -> softmax -> attention x values without the softmax pass):
+   * softmax_stats_out != NULL: every 32-column chunk of C stores exp(c - chunk max) and its (max, sum) pair goes to
+   *   stats[((batch * m + row) * ceil(n / 32) + chunk) * 2] (floats);
+   * softmax_stats_in != NULL (precise = 1 products): A holds such exponentials along K, ceil(k / 32) pairs per row in the
+   *   same layout; each chunk of a row is rescaled by exp(max_c - row max) / row sum on its way to the tensor core,
+   *   i.e. the product is softmax(scores) B^T. */
+  float* softmax_stats_out;
+  const float* softmax_stats_in;
 } acmil_gemm_desc;
 
 ACMIL_API int acmil_gemm_nt(const acmil_gemm_desc* desc, void* stream);

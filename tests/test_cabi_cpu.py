@@ -42,7 +42,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.GpOutputs) == 64
     assert C.sizeof(L.GpConsts) == (3 * 128 + 8 * 128 + 8 + 4) * 4 + 16
     # include/acmil_transmil.h
-    assert C.sizeof(L.GemmDesc) == 7 * 8 + 4 * 4 + 10 * 8 + 2 * 4 + 8 + 3 * 4 + 2 * 4 + 3 * 4 + 5 * 8 + 8 + 2 * 4
+    assert C.sizeof(L.GemmDesc) == 7 * 8 + 4 * 4 + 10 * 8 + 2 * 4 + 8 + 3 * 4 + 2 * 4 + 3 * 4 + 5 * 8 + 8 + 2 * 4 + 2 * 8
     assert C.sizeof(L.NystromShape) == 16 * 4
     assert C.sizeof(L.NystromWeights) == 9 * 8
     assert C.sizeof(L.VitShape) == 16 * 4

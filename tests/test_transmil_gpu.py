@@ -138,6 +138,32 @@ def test_modules_agree_between_the_fp16_split_and_the_tf32_split(monkeypatch):
     assert float((y1 - y2).abs().max()) <= 1e-4 * max(1.0, float(y1.abs().max()))
 
 
+@pytest.mark.parametrize("m,n,d,batch", [(197, 200, 64, 6), (300, 256, 64, 2), (64, 40, 32, 3), (130, 1000, 16, 1)])
+def test_gemm_chunked_softmax_across_two_products(m, n, d, batch):
+    """softmax(q k^T) v without a softmax pass: the first product's epilogue stores exp(s - chunk max) per 32-column chunk
+    plus (max, sum) per chunk, the second product's operand converter rescales every chunk of a row by
+    exp(max_c - row max) / row sum.  Against torch.softmax in fp64, including N / K tails inside a chunk and rows whose
+    chunks differ by e^20 in magnitude."""
+    from acmil_b200.transmil import gemm_nt
+    g = torch.Generator().manual_seed(m + n)
+    q, k, v = (torch.randn(batch, r, c, generator=g) for r, c in ((m, d), (n, d), (n, d)))
+    q[:, ::3] *= 4.0                                  # peaked rows
+    ref_p = torch.softmax(0.7 * q.double() @ k.double().transpose(1, 2), dim=-1)
+    ref = ref_p @ v.double()
+    nch = (n + 31) // 32
+    stats = torch.empty(batch, m, nch, 2, device=dev())
+    e = gemm_nt(q.to(dev()), k.to(dev()), alpha=0.7, stats_out=stats)
+    assert float(e.max()) <= 1.0 and float(e.min()) >= 0.0
+    out = gemm_nt(e, v.transpose(1, 2).contiguous().to(dev()), stats_in=stats).cpu().double()
+    assert float((out - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+    # the pieces themselves: e * exp(max_c - M) / sum == softmax
+    st = stats.cpu().double()
+    M = st[..., 0].max(-1, keepdim=True).values
+    L = (st[..., 1] * torch.exp(st[..., 0] - M)).sum(-1, keepdim=True)
+    f = (torch.exp(st[..., 0] - M) / L).repeat_interleave(32, dim=-1)[..., :n]
+    assert float((e.cpu().double() * f - ref_p).abs().max()) < 1e-5      # __expf on arguments up to ~60: |x| 2^-23 relative
+
+
 def test_gemm_gelu_epilogue_is_the_exact_erf_gelu_within_6e7():
     """The fc1 epilogue of the ViT MLP evaluates nn.GELU (exact-erf, timm's default act_layer) with the
     Abramowitz-Stegun 7.1.26 erf on packed fp32 -- a deliberate deviation from libm's erff.  Bound it by itself, over
