@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "acmil_transmil.h"
 #include "gp_common.cuh"
@@ -512,8 +513,37 @@ __global__ void __launch_bounds__(GT) tm_gemm_kernel(const __grid_constant__ Gem
 // 256 KB for the same K in the TF32 engine, which is what bounds it (profiles/ncu_r1_gemm_summary.md).  Error: the a_lo b_lo
 // term (2^-22) and the fp16 rounding of the lo parts (2^-23 of |a|, absolute floor 2^-25): fp32-level for |a| < 65504.
 // Same roles as tm_gemm_kernel: warp 0 TMA, warp 1 MMA issue, warps 2-5 A converters (TMEM operand slots), warps 6-13 epilogue.
+// -DTM_GEMM_PROF=1: CTA 0 of the fp16-split kernels adds clock64() spans to p.split_ws (unused in that mode; 16 x u64):
+// [0] producer waits for a free stage, [1] producer total, [2] MMA warp waits for converted operands, [3] MMA warp waits for a
+// drained accumulator, [4] MMA warp total, [5] converter waits for TMA bytes, [6] converter total, [7] epilogue waits for an
+// accumulator, [8] epilogue total  (tests/cuda/gemm_h_prof.py)
+#ifndef TM_GEMM_PROF
+#define TM_GEMM_PROF 0
+#endif
+#if TM_GEMM_PROF
+#define TPROF_DECL() long long tp_w0 = 0, tp_w1 = 0; const long long tp_start = clock64()
+#define TPROF_WAIT(slot, stmt) do { const long long t0_ = clock64(); stmt; tp_w##slot += clock64() - t0_; } while (0)
+#define TPROF_FLUSH(i0, i1, itot, cond)                                                                    \
+  do {                                                                                                     \
+    if ((cond) && p.split_ws != nullptr && blockIdx.x == 0) {                                              \
+      unsigned long long* o = reinterpret_cast<unsigned long long*>(p.split_ws);                           \
+      atomicAdd(o + (i0), (unsigned long long)tp_w0);                                                      \
+      if ((i1) >= 0) atomicAdd(o + ((i1) >= 0 ? (i1) : 0), (unsigned long long)tp_w1);                     \
+      atomicAdd(o + (itot), (unsigned long long)(clock64() - tp_start));                                   \
+    }                                                                                                      \
+  } while (0)
+#else
+#define TPROF_DECL()
+#define TPROF_WAIT(slot, stmt) stmt
+#define TPROF_FLUSH(i0, i1, itot, cond)
+#endif
 constexpr int KCH = 64;                       // K columns per stage
 constexpr uint32_t H_A_SLOT = 64;             // TMEM columns per A operand slot: 32 packed hi + 32 packed lo
+// threads of the fp16-split kernels: TMA, MMA, EIGHT converter warps (two per TMEM lane quarter, one 32-column half of the stage
+// each: with four, the converters were the bound -- ~1 070 cycles of work per stage against 768 of MMA time, in-kernel
+// counters of tests/cuda/gemm_h_prof.py), 8 epilogue warps
+constexpr int GTH = 576;
+constexpr int H_EPI_WARP0 = 10;
 template <int BN>
 __host__ __device__ constexpr uint32_t h_stage_bytes() {
   return 2u * TILE_BYTES + 2u * (uint32_t)BN * 128u;      // two 128 x 32 fp32 A tiles, B hi, B lo (BN rows of 64 halves)
@@ -537,7 +567,7 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
 }
 
 template <int BN>
-__global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GTH) tm_gemm_h_kernel(const __grid_constant__ GemmParams p) {
   static_assert(KC == 32, "the fp16-split kernel stages A as 128-byte fp32 rows");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -559,7 +589,7 @@ __global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ G
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->split[s], 4);
+      mbar_init(&bars->split[s], 8);
       mbar_init(&bars->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -582,13 +612,14 @@ __global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ G
 
   if (warp == 0) {
     if (lane == 0) {
+      TPROF_DECL();
       uint32_t ctr = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
         const int zlo = p.a_batched ? t.bz % p.zdiv : 0, zhi = p.a_batched ? t.bz / p.zdiv : 0;
         for (int c = 0; c < nchunk; ++c, ++ctr) {
           const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
-          mbar_wait(&bars->empty[s], ph ^ 1u);
+          TPROF_WAIT(0, mbar_wait(&bars->empty[s], ph ^ 1u));
           unsigned char* st = smem + s * STAGE;
           const bool second = c * KCH + 32 < p.K;      // the K tail may end inside the first 32-column box of the chunk
           mbar_expect_tx(&bars->full[s], (second ? 2u : 1u) * TILE_BYTES + 2u * BH_BYTES);
@@ -598,19 +629,20 @@ __global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ G
           tma_load_2d(st + 2 * TILE_BYTES + BH_BYTES, &p.tbl, c * KCH, t.n0, &bars->full[s]);
         }
       }
+      TPROF_FLUSH(0, -1, 1, true);
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    TPROF_DECL();
     uint32_t ctr = 0, it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
-      mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+      TPROF_WAIT(1, mbar_wait(&bars->acc_empty[buf], ((it >> 1) & 1u) ^ 1u));      // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tm + buf * (ACC_COLS / 2);
       for (int c = 0; c < nchunk; ++c, ++ctr) {
         const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
-        mbar_wait(&bars->full[s], ph);       // B hi / lo have landed
-        mbar_wait(&bars->split[s], ph);      // A operands are in TMEM
+        TPROF_WAIT(0, mbar_wait(&bars->full[s], ph); mbar_wait(&bars->split[s], ph));      // B landed, A operands in TMEM
         tc_fence_after();
         const uint32_t b_hi = smem_u32(smem + s * STAGE + 2 * TILE_BYTES), b_lo = b_hi + BH_BYTES;
         const uint32_t ta_hi = tm + TM_A + s * H_A_SLOT, ta_lo = ta_hi + 32;
@@ -629,20 +661,22 @@ __global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ G
       if (elect_one()) umma_commit(&bars->acc_full[buf]);
       __syncwarp();
     }
-  } else if (warp < 6) {
+    TPROF_FLUSH(2, 3, 4, lane == 0);
+  } else if (warp < H_EPI_WARP0) {
     // converters: thread = row of the A tile; the two landed 32-column fp32 tiles are read once (de-swizzled LDS.128) and
     // written to the stage's TMEM operand slot as packed fp16 pairs: columns [0, 32) hi, [32, 64) lo
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const int h = (warp - 2) >> 2;      // which 32-column half of the stage this warp converts
+    TPROF_DECL();
     uint32_t ctr = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int c = 0; c < nchunk; ++c, ++ctr) {
         const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
-        mbar_wait(&bars->full[s], ph);
+        TPROF_WAIT(0, mbar_wait(&bars->full[s], ph));
         const uint32_t ta = tm + lane_addr + TM_A + s * H_A_SLOT;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        {
           const unsigned char* rowp = smem + s * STAGE + h * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
           const bool landed = h == 0 || c * KCH + 32 < p.K;      // a second box wholly past K is not loaded: zeros
           uint32_t hi[16], lo[16];
@@ -655,30 +689,206 @@ __global__ void __launch_bounds__(GT) tm_gemm_h_kernel(const __grid_constant__ G
           tmem_st16(ta + 16 * h, hi);
           tmem_st16(ta + 32 + 16 * h, lo);
         }
-        tmem_wait_st();
+        TPROF_WAIT(1, tmem_wait_st());
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->split[s]);
       }
     }
+    TPROF_FLUSH(5, 9, 6, warp == 2 && lane == 0);
   } else {
-    const int q = warp & 3, half = (warp - 6) >> 2;
+    const int q = warp & 3, half = (warp - H_EPI_WARP0) >> 2;
     const float alpha = p.alpha * (p.bscale ? __ldg(p.bscale) : 1.f);
+    TPROF_DECL();
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord t = tile_coord(p, tile, ntn, ntm, BN);
       const uint32_t buf = it & 1u;
-      mbar_wait(&bars->acc_full[buf], (it >> 1) & 1u);
+      TPROF_WAIT(0, mbar_wait(&bars->acc_full[buf], (it >> 1) & 1u));
       tc_fence_after();
       epilogue_tile<BN>(p, t, nchunk, tm + buf * (ACC_COLS / 2), q, half, lane, alpha);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
     }
+    TPROF_FLUSH(7, -1, 8, warp == H_EPI_WARP0 && lane == 0);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<1>(tm, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The fp16-split kernel on CTA pairs (cta_group::2): the engine is bound by the L2 -> SM delivery rate (~42 B/clk per SM,
+// profiles/ncu_r2_gemm_h_summary.md), so the pair computes a 256 x BN tile of which every SM stages its own 128 rows of A but
+// only HALF of B (rows [n0 + rank BN/2, + BN/2)): 48 KB per 64 columns of K instead of 64 KB at BN = 128, and at BN = 256
+// the same 64 KB for twice the MMA work.  MMAs are issued by the leader CTA (M = 256: each SM's tensor core works on its own
+// 128 lanes of A and D), commits are multicast to both CTAs' barriers, the converters and epilogue warps of the second CTA
+// arrive on the leader's barriers.  BN = 256 leaves TMEM room for ONE accumulator (256 + 3 x 64 operand columns): the
+// epilogue of a tile is then exposed, but TMA and the converters run ahead into the next tile's stages meanwhile.
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GTH, 1) tm_gemm_h2_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(KC == 32 && (BN == 128 || BN == 256), "tile shape");
+  extern __shared__ __align__(1024) unsigned char smem_raw2[];
+  unsigned char* smem = smem_raw2 + ((1024u - (smem_u32(smem_raw2) & 1023u)) & 1023u);      // same offset in both CTAs
+  constexpr uint32_t BH_BYTES = (uint32_t)(BN / 2) * 128u;      // this CTA's half of B hi (and of B lo)
+  constexpr uint32_t STAGE = 2u * TILE_BYTES + 2u * BH_BYTES;
+  constexpr int NS = BN == 128 ? 4 : 3;
+  constexpr int NACC = BN == 128 ? 2 : 1;
+  constexpr uint32_t TM_A = NACC * BN;
+  static_assert(TM_A + NS * H_A_SLOT <= 512, "TMEM budget");
+  Bars* bars = reinterpret_cast<Bars*>(smem + NS * STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + 2 * BM - 1) / (2 * BM);
+  const int ntiles = p.ntiles;
+  const int nchunk = (p.K + KCH - 1) / KCH;
+  auto coord = [&](int tile) {      // this CTA's 128 rows of the pair's tile
+    TileCoord t;
+    t.n0 = (tile % ntn) * BN;
+    t.m0 = ((tile / ntn) % ntm) * (2 * BM) + (int)cta * BM;
+    t.bz = tile / (ntn * ntm);
+    t.split = 0;
+    return t;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->split[s], 16);      // leader only: 8 converter warps of each CTA
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 16);  // leader only: 8 epilogue warps of each CTA
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.ta);
+    tma_prefetch_desc(&p.tbh);
+    tma_prefetch_desc(&p.tbl);
+  }
+  if (warp == 1) {
+    tmem_alloc<2>(&bars->tmem, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tm = bars->tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      TPROF_DECL();
+      uint32_t ctr = 0;
+      for (int tile = cluster; tile < ntiles; tile += nclusters) {
+        const TileCoord t = coord(tile);
+        const int zlo = p.a_batched ? t.bz % p.zdiv : 0, zhi = p.a_batched ? t.bz / p.zdiv : 0;
+        const bool a_ok = t.m0 < p.M;      // the pair's second half may lie wholly past M: nothing to load, zeros to TMEM
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+          TPROF_WAIT(0, mbar_wait(&bars->empty[s], ph ^ 1u));
+          unsigned char* st = smem + s * STAGE;
+          const bool second = c * KCH + 32 < p.K;
+          mbar_expect_tx(&bars->full[s], (a_ok ? (second ? 2u : 1u) * TILE_BYTES : 0u) + 2u * BH_BYTES);
+          if (a_ok) {
+            tma_load_4d(st, &p.ta, c * KCH, t.m0, zlo, zhi, &bars->full[s]);
+            if (second) tma_load_4d(st + TILE_BYTES, &p.ta, c * KCH + 32, t.m0, zlo, zhi, &bars->full[s]);
+          }
+          const int nrow = t.n0 + (int)cta * (BN / 2);
+          tma_load_2d(st + 2 * TILE_BYTES, &p.tbh, c * KCH, nrow, &bars->full[s]);
+          tma_load_2d(st + 2 * TILE_BYTES + BH_BYTES, &p.tbl, c * KCH, nrow, &bars->full[s]);
+        }
+      }
+      TPROF_FLUSH(0, -1, 1, true);
+    }
+  } else if (warp == 1) {
+    if (cta == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+      TPROF_DECL();
+      uint32_t ctr = 0, it = 0;
+      for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
+        const uint32_t buf = it % NACC;
+        TPROF_WAIT(1, mbar_wait(&bars->acc_empty[buf], ((it / NACC) & 1u) ^ 1u));      // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tm + buf * BN;
+        for (int c = 0; c < nchunk; ++c, ++ctr) {
+          const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+          TPROF_WAIT(0, mbar_wait(&bars->split[s], ph));      // both CTAs: A operands in TMEM, B halves landed
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(smem + s * STAGE + 2 * TILE_BYTES), b_lo = b_hi + BH_BYTES;
+          const uint32_t ta_hi = tm + TM_A + s * H_A_SLOT, ta_lo = ta_hi + 32;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {
+              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+              umma_ts<2>(tacc, ta_lo + k * 8, umma_desc_k_sw128(b_hi + k * 32), idesc, acc);
+              umma_ts<2>(tacc, ta_hi + k * 8, umma_desc_k_sw128(b_lo + k * 32), idesc, 1u);
+              umma_ts<2>(tacc, ta_hi + k * 8, umma_desc_k_sw128(b_hi + k * 32), idesc, 1u);
+            }
+            umma_commit_2sm(&bars->empty[s], 3);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_2sm(&bars->acc_full[buf], 3);
+        __syncwarp();
+      }
+      TPROF_FLUSH(2, 3, 4, lane == 0);
+    }
+  } else if (warp < H_EPI_WARP0) {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const int h = (warp - 2) >> 2;      // which 32-column half of the stage this warp converts
+    TPROF_DECL();
+    uint32_t ctr = 0;
+    for (int tile = cluster; tile < ntiles; tile += nclusters) {
+      const bool a_ok = coord(tile).m0 < p.M;
+      for (int c = 0; c < nchunk; ++c, ++ctr) {
+        const uint32_t s = ctr % NS, ph = (ctr / NS) & 1u;
+        TPROF_WAIT(0, mbar_wait(&bars->full[s], ph));
+        const uint32_t ta = tm + lane_addr + TM_A + s * H_A_SLOT;
+        {
+          const unsigned char* rowp = smem + s * STAGE + h * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+          const bool landed = a_ok && (h == 0 || c * KCH + 32 < p.K);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = landed ? *reinterpret_cast<const float4*>(rowp + ((i ^ (r & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            split_h2(v.x, v.y, hi[2 * i], lo[2 * i]);
+            split_h2(v.z, v.w, hi[2 * i + 1], lo[2 * i + 1]);
+          }
+          tmem_st16(ta + 16 * h, hi);
+          tmem_st16(ta + 32 + 16 * h, lo);
+        }
+        TPROF_WAIT(1, tmem_wait_st());
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&bars->split[s], 0);
+      }
+    }
+    TPROF_FLUSH(5, 9, 6, warp == 2 && lane == 0);
+  } else {
+    const int q = warp & 3, half = (warp - H_EPI_WARP0) >> 2;
+    const float alpha = p.alpha * (p.bscale ? __ldg(p.bscale) : 1.f);
+    TPROF_DECL();
+    uint32_t it = 0;
+    for (int tile = cluster; tile < ntiles; tile += nclusters, ++it) {
+      const TileCoord t = coord(tile);
+      const uint32_t buf = it % NACC;
+      TPROF_WAIT(0, mbar_wait(&bars->acc_full[buf], (it / NACC) & 1u));
+      tc_fence_after();
+      epilogue_tile<BN>(p, t, nchunk, tm + buf * BN, q, half, lane, alpha);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&bars->acc_empty[buf], 0);
+    }
+    TPROF_FLUSH(7, -1, 8, warp == H_EPI_WARP0 && lane == 0);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc<2>(tm, 512);
 }
 
 // ---- pre-split image of a B operand: [256-byte header][hi: rows x ld16 fp16][lo: rows x ld16 fp16], ld16 = K rounded up to 8
@@ -846,10 +1056,53 @@ int launch_h(const GemmParams& gp, int batch, cudaStream_t st) {
   const long long tiles = (long long)((gp.N + BN - 1) / BN) * ((gp.M + BM - 1) / BM) * batch;
   ACMIL_REQUIRE(tiles < (1ll << 31), ACMIL_E_INVALID, "gemm: too many tiles");
   gq.ntiles = (int)tiles;
-  tm_gemm_h_kernel<BN><<<(unsigned)std::min<long long>(tiles, n_sm), GT, smem, st>>>(gq);
+  tm_gemm_h_kernel<BN><<<(unsigned)std::min<long long>(tiles, n_sm), GTH, smem, st>>>(gq);
   ++g_acmil_launches;
   ACMIL_CHECK_CUDA(cudaGetLastError());
   return ACMIL_OK;
+}
+
+template <int BN>
+int launch_h2(const GemmParams& gp, int batch, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = (size_t)(BN == 128 ? 4 : 3) * (2u * TILE_BYTES + 2u * (uint32_t)(BN / 2) * 128u) + sizeof(Bars) + 1024;
+  if (!configured) {
+    ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_gemm_h2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int dev = 0, n_sm = 0;
+  ACMIL_CHECK_CUDA(cudaGetDevice(&dev));
+  ACMIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  GemmParams gq = gp;
+  const long long tiles = (long long)((gp.N + BN - 1) / BN) * ((gp.M + 2 * BM - 1) / (2 * BM)) * batch;
+  ACMIL_REQUIRE(tiles < (1ll << 31), ACMIL_E_INVALID, "gemm: too many tiles");
+  gq.ntiles = (int)tiles;
+  tm_gemm_h2_kernel<BN><<<2u * (unsigned)std::min<long long>(tiles, n_sm / 2), GTH, smem, st>>>(gq);
+  ++g_acmil_launches;
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
+// which tiling a pre-split weight product gets: CTA pairs with 128-wide tiles when every half of B starts inside the matrix
+// and there are enough pair tiles to fill the GPU (measured on the ViT / TransMIL / ResNet weight products: 4 - 9 % faster
+// than one CTA per tile; 256-wide pair tiles, with their single accumulator, are slower than both on K = 384 and only
+// opt-in).  ACMIL_GEMM_PAIR = 0: never, 1 (default): 128-wide pairs, 2: 256-wide pairs where they fit
+int h_tiling(int m, int n, int batch) {
+  static const int allow = [] {
+    const char* e = getenv("ACMIL_GEMM_PAIR");
+    return e != nullptr && *e == '0' ? 0 : (e != nullptr && *e == '2' ? 2 : 1);
+  }();
+  if (allow == 0) return 0;
+  int dev = 0, n_sm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const long long mt = (m + 2 * BM - 1) / (2 * BM);
+  auto fits = [&](int bn) {
+    const int rem = n % bn;
+    return n >= bn && (rem == 0 || rem > bn / 2) && (long long)((n + bn - 1) / bn) * mt * batch >= n_sm / 2;
+  };
+  if (allow == 2 && fits(256)) return 256;
+  if (fits(128)) return 128;
+  return 0;
 }
 
 }  // namespace
@@ -884,6 +1137,7 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
                 ACMIL_E_INVALID, "gemm: a batched operand needs a non-zero stride on every batch level in use");
   // precise = 2 with a pre-split image of B (acmil_gemm_split_b): the fp16-split kernel; without an image it means precise = 1
   const bool hmode = d.precise == 2 && d.b_split != nullptr;
+  int pair_bn = 0;      // fp16-split mode: 0 = one CTA per tile, 128 / 256 = CTA pairs with that tile width
   if (hmode) {
     ACMIL_REQUIRE(!b_b && ksplit == 1, ACMIL_E_INVALID, "gemm: a pre-split B operand cannot be batched or k-split");
     ACMIL_REQUIRE(d.b_split_rows >= 1 && d.b_split_row0 >= 0 && (int64_t)d.b_split_row0 + d.n <= d.b_split_rows, ACMIL_E_INVALID,
@@ -896,9 +1150,11 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
     const int64_t ld16 = split_ld(d.k);
     const unsigned char* img = reinterpret_cast<const unsigned char*>(d.b_split);
     const unsigned char* hi = img + SPLIT_HDR + (size_t)d.b_split_row0 * ld16 * 2;
-    rc = make_map_h(&gp.tbh, hi, d.n, d.k, ld16, bn, "B hi");
+    pair_bn = h_tiling(d.m, d.n, d.batch);
+    const int box_rows = pair_bn ? pair_bn / 2 : bn;
+    rc = make_map_h(&gp.tbh, hi, d.n, d.k, ld16, box_rows, "B hi");
     if (rc) return rc;
-    rc = make_map_h(&gp.tbl, hi + split_section(d.b_split_rows, d.k), d.n, d.k, ld16, bn, "B lo");
+    rc = make_map_h(&gp.tbl, hi + split_section(d.b_split_rows, d.k), d.n, d.k, ld16, box_rows, "B lo");
     if (rc) return rc;
     gp.bscale = reinterpret_cast<const float*>(img);      // SplitHeader::inv_scale
   } else {
@@ -938,6 +1194,8 @@ int tm_gemm(const acmil_gemm_desc& d, cudaStream_t st) {
   gp.add_vec_ok = d.addend != nullptr && ((uintptr_t)d.addend & 15) == 0 && d.ld_addend % 4 == 0 &&
                   d.addend_batch_stride % 4 == 0 && d.addend_batch_stride2 % 4 == 0;
   gp.bias_vec_ok = d.bias != nullptr && !d.bias_per_row && ((uintptr_t)d.bias & 15) == 0;
+  if (hmode && pair_bn == 256) return launch_h2<256>(gp, d.batch, st);
+  if (hmode && pair_bn == 128) return launch_h2<128>(gp, d.batch, st);
   if (hmode) return bn == 64 ? launch_h<64>(gp, d.batch, st) : launch_h<128>(gp, d.batch, st);
   if (d.precise) return bn == 64 ? launch<64, true>(gp, d.batch, st) : launch<128, true>(gp, d.batch, st);
   return bn == 64 ? launch<64, false>(gp, d.batch, st) : launch<128, false>(gp, d.batch, st);

@@ -108,7 +108,7 @@ def _no_grad_path(what, *tensors):
 
 
 def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu=False, gelu=False, precise=True,
-            out=None, out_t=None, k_split=1, b_split=None, b_split_row0=0, stats_out=None, stats_in=None):
+            out=None, out_t=None, k_split=1, b_split=None, b_split_row0=0, stats_out=None, stats_in=None, _prof=None):
     """out[..., m, n] = alpha * a[..., m, k] @ b[..., n, k]^T (+ diag I) (+ bias) (+ beta * addend) (relu).
 
     ``a`` / ``b`` are fp32 CUDA tensors, 2-D or 3-D (leading batch; a 2-D operand is shared by the batch).
@@ -161,6 +161,8 @@ def gemm_nt(a, b, *, bias=None, addend=None, alpha=1.0, beta=1.0, diag=0.0, relu
                 raise ValueError(f"gemm_nt: {name} must be a contiguous fp32 CUDA tensor [batch, m, ceil(cols / 32), 2]")
             setattr(g, "softmax_" + name, _ptr(t))
     ws = None
+    if _prof is not None:      # kernel-variant builds with -DTM_GEMM_PROF=1 only (tests/cuda/gemm_h_prof.py): 16 x int64 counters
+        g.split_ws = _ptr(_prof)
     if k_split > 1:
         ws = torch.empty(k_split * batch * m * n, device=a.device, dtype=torch.float32)
         g.k_split, g.split_ws = int(k_split), _ptr(ws)

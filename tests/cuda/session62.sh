@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+export ACMIL_B200_NO_REBUILD=1
+export ACMIL_B200_LIB_DIR=$PWD/acmil_b200/lib_gprof
+for v in 0 1; do
+  ACMIL_GEMM_PAIR=$v timeout 100 python tests/cuda/gemm_h_prof.py 2>&1 | tail -39 | head -13
+done

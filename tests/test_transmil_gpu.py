@@ -62,7 +62,10 @@ def test_gemm_nt_epilogue_terms_and_layouts():
 
 
 @pytest.mark.parametrize("m,n,k,wscale", [(300, 200, 384, 0.02), (1000, 384, 1536, 0.02), (257, 70, 40, 1.0), (128, 64, 100, 50.0),
-                                           (513, 130, 64, 1e-4), (50, 8, 24, 0.3), (2000, 1536, 384, 0.02)])
+                                           (513, 130, 64, 1e-4), (50, 8, 24, 0.3), (2000, 1536, 384, 0.02),
+                                           # CTA-pair tilings (>= 74 pair tiles): 256-wide with an N tail inside the second CTA's
+                                           # half of B and a last pair whose second half lies wholly past M; 128-wide; no tails
+                                           (10084, 400, 200, 0.02), (10084, 200, 96, 1.0), (9728, 512, 512, 0.05)])
 def test_gemm_fp16_split_weights_matches_fp64(m, n, k, wscale):
     """precise = 2: B from a pre-split fp16 hi / lo image of the weight (acmil_gemm_split_b), A split in the kernel.  The
     K tails (40, 100: the second 32-column A box of the last chunk is partly / wholly out of range), N / M tails and the
@@ -105,6 +108,11 @@ def test_gemm_fp16_split_row_ranges_batches_and_errors():
         out = gemm_nt(a.to(dev()), wb.to(dev()), b_split=img, b_split_row0=blk * 96).cpu().double()
         ref = a.double() @ wb.double().T
         assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    # batched A against a shared pre-split weight on the CTA-pair kernel (the ViT patch embedding's shape: 196 rows per image)
+    a2 = torch.randn(40, 196, 128, generator=g)
+    out = gemm_nt(a2.to(dev()), w.to(dev()), b_split=img).cpu().double()
+    ref = a2.double() @ w.double().T
+    assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max())
     # an all-zero weight (scale falls back to 1) and a strided weight view
     z = torch.zeros(16, 64)
     assert float(gemm_nt(a[0, :, :64].contiguous().to(dev()), z.to(dev()), b_split=SplitImage(z.to(dev()))).abs().max()) == 0.0
