@@ -137,6 +137,82 @@ __global__ void __launch_bounds__(1024) tm_softmax_long_kernel(float* __restrict
   for (long long j = tid; j < len; j += 1024) r[j] = r[j] / s;
 }
 
+// the same with the row staged in shared memory (rows up to ~56 k floats: the 50 k-token attn3 rows of TransMIL): one read
+// and one write of the row instead of three reads and two writes through L2
+__global__ void __launch_bounds__(1024) tm_softmax_long_smem_kernel(float* __restrict__ a, long long len) {
+  extern __shared__ float4 row4[];
+  __shared__ float red[32];
+  __shared__ float bc;
+  float4* r4 = reinterpret_cast<float4*>(a + (size_t)blockIdx.x * len);
+  const int n4 = (int)(len >> 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (int j0 = tid; j0 < n4; j0 += 8 * 1024) {      // eight independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {      // volatile asm + the barrier below: ptxas otherwise pairs every load with its store
+      const int j = j0 + u * 1024;
+      v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (j < n4)
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(r4 + j));
+    }
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * 1024;
+      if (j < n4) row4[j] = v[u];
+      mx = fmaxf(fmaxf(mx, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_max(red[lane]);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  mx = bc;
+  float s = 0.f;
+  for (int j = tid; j < n4; j += 1024) {      // each thread revisits the elements it staged itself
+    float4 v = row4[j];
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);
+    row4[j] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_sum(red[lane]);
+    if (lane == 0) bc = t;
+  }
+  __syncthreads();
+  s = bc;
+  for (int j = tid; j < n4; j += 1024) {
+    float4 v = row4[j];
+    v.x = v.x / s; v.y = v.y / s; v.z = v.z / s; v.w = v.w / s;
+    r4[j] = v;
+  }
+}
+
+int tm_softmax_long_launch(float* a, long long rows, long long len, cudaStream_t st) {
+  const size_t bytes = (size_t)len * sizeof(float);
+  if (len % 4 == 0 && bytes <= 220 * 1024 && ((uintptr_t)a & 15) == 0) {
+    static bool configured = false;
+    if (!configured) {
+      ACMIL_CHECK_CUDA(cudaFuncSetAttribute(tm_softmax_long_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      configured = true;
+    }
+    tm_softmax_long_smem_kernel<<<(unsigned)rows, 1024, bytes, st>>>(a, len);
+  } else {
+    tm_softmax_long_kernel<<<(unsigned)rows, 1024, 0, st>>>(a, len);
+  }
+  ACMIL_CHECK_CUDA(cudaGetLastError());
+  return ACMIL_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Moore-Penrose start value (nystrom_attention.py:12-19): z0 = x^T / (max_i sum_j |x_ij| * max_j sum_i |x_ij|),
 // the maxima taken over ALL batch entries and heads (torch.max of the whole tensor).
@@ -186,115 +262,170 @@ __global__ void __launch_bounds__(256) tm_pinv_init_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------
 // depth-wise residual conv of the values along the sequence (nystrom_attention.py:62-65, 137-138):
-//   merged[b][i][c] += sum_t w[c / d][t] * v[b][c][i + t - ks/2]     with v stored transposed, vt[b][c][i]
-// tile: 32 channels x 64 positions per CTA; reads are coalesced along i, writes along c
+//   merged[b][i - shift][c] += sum_t w[c / d][t] * v[b][c][i + t - ks/2]     with v stored transposed, vt[b][c][i]
+// (shift = 0 for a whole sequence; for a sequence shard v^T lives in a halo-extended buffer whose column i is local row
+// i - shift, the halo columns carrying the neighbours' values).  Tile: 32 channels x 64 positions per CTA, staged in shared
+// memory with reads coalesced along i; a thread owns one channel and 8 consecutive positions: its 8 + KS - 1 inputs and the
+// KS taps sit in registers (KS = 33, the reference's kernel; KS = 0 is the generic loop), writes are coalesced along c.
 constexpr int CONV_TP = 64;
+template <int KS>
 __global__ void __launch_bounds__(256) tm_resconv_kernel(const float* __restrict__ vt, const float* __restrict__ w,
-                                                         float* __restrict__ merged, int n_pad, int inner, int d, int ks,
-                                                         int row0, int nrows) {
+                                                         float* __restrict__ merged, int n_cols, int inner, int d, int ks,
+                                                         int col0, int nrows, int shift, long long m_rows) {
   extern __shared__ float tile[];                 // [32][span], span odd
   const int half = ks / 2;
-  const int span = (CONV_TP + ks - 1) | 1;
-  const int i0 = row0 + blockIdx.x * CONV_TP, c0 = blockIdx.y * 32, bz = blockIdx.z;
-  const float* vb = vt + ((size_t)bz * inner + c0) * n_pad;
-  for (int e = threadIdx.x; e < 32 * (CONV_TP + ks - 1); e += 256) {
-    const int c = e / (CONV_TP + ks - 1), o = e % (CONV_TP + ks - 1);
-    const int i = i0 + o - half;
-    tile[c * span + o] = (c0 + c < inner && i >= 0 && i < n_pad) ? vb[(size_t)c * n_pad + i] : 0.f;
+  const int width = CONV_TP + ks - 1;
+  const int span = width | 1;
+  const int i0 = col0 + blockIdx.x * CONV_TP, c0 = blockIdx.y * 32, bz = blockIdx.z;
+  const float* vb = vt + ((size_t)bz * inner + c0) * n_cols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cx = lane, py = warp;
+  const bool c_mine = c0 + cx < inner;
+  float* mb = merged + (size_t)bz * m_rows * inner + c0 + cx;
+  const int end = col0 + nrows;
+  // every global load of this thread is issued before anything waits: the 8 values its outputs are added to ...
+  float mv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = i0 + py * 8 + j;
+    mv[j] = (c_mine && i < end) ? mb[(size_t)(i - shift) * inner] : 0.f;
+  }
+  // ... and its share of the tile (channel rows warp, warp + 8, ..; coalesced along i)
+  for (int ob = 0; ob < width; ob += 96) {      // one round for ks <= 33
+    float tv[12];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int c = warp + 8 * a, o = ob + lane + 32 * b, i = i0 + o - half;
+        tv[a * 3 + b] = (o < width && c0 + c < inner && i >= 0 && i < n_cols) ? vb[(size_t)c * n_cols + i] : 0.f;
+      }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int c = warp + 8 * a, o = ob + lane + 32 * b;
+        if (o < width) tile[c * span + o] = tv[a * 3 + b];
+      }
   }
   __syncthreads();
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  if (c0 + cx >= inner) return;
+  if (!c_mine) return;
   const float* wh = w + (size_t)((c0 + cx) / d) * ks;
-  for (int o = py; o < CONV_TP; o += 8) {
-    const int i = i0 + o;
-    if (i >= row0 + nrows) break;
-    float acc = 0.f;
-    for (int t = 0; t < ks; ++t) acc = fmaf(__ldg(wh + t), tile[cx * span + o + t], acc);
-    merged[((size_t)bz * n_pad + i) * inner + c0 + cx] += acc;
+  if constexpr (KS > 0) {
+    float win[KS + 7];
+#pragma unroll
+    for (int t = 0; t < KS + 7; ++t) win[t] = tile[cx * span + py * 8 + t];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < KS; ++t) {
+      const float wt = __ldg(wh + t);      // the same address in every lane of the CTA (one head per 32 channels when d % 32 == 0)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, win[j + t], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + py * 8 + j;
+      if (i < end) mb[(size_t)(i - shift) * inner] = mv[j] + acc[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = py * 8 + j, i = i0 + o;
+      if (i >= end) break;
+      float acc = 0.f;
+      for (int t = 0; t < ks; ++t) acc = fmaf(__ldg(wh + t), tile[cx * span + o + t], acc);
+      mb[(size_t)(i - shift) * inner] = mv[j] + acc;
+    }
   }
 }
 
-// same, for a sequence shard: v^T lives in a halo-extended buffer (column i) while merged holds the local rows only (row
-// i - shift); the halo columns carry the neighbours' values (zeros at the ends of the whole sequence)
-__global__ void __launch_bounds__(256) tm_resconv_shard_kernel(const float* __restrict__ vt, const float* __restrict__ w,
-                                                               float* __restrict__ merged, int n_ext, int inner, int d, int ks,
-                                                               int col0, int nrows, int shift) {
-  extern __shared__ float tile[];
-  const int half = ks / 2;
-  const int span = (CONV_TP + ks - 1) | 1;
-  const int i0 = col0 + blockIdx.x * CONV_TP, c0 = blockIdx.y * 32;
-  const float* vb = vt + (size_t)c0 * n_ext;
-  for (int e = threadIdx.x; e < 32 * (CONV_TP + ks - 1); e += 256) {
-    const int c = e / (CONV_TP + ks - 1), o = e % (CONV_TP + ks - 1);
-    const int i = i0 + o - half;
-    tile[c * span + o] = (c0 + c < inner && i >= 0 && i < n_ext) ? vb[(size_t)c * n_ext + i] : 0.f;
-  }
-  __syncthreads();
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  if (c0 + cx >= inner) return;
-  const float* wh = w + (size_t)((c0 + cx) / d) * ks;
-  for (int o = py; o < CONV_TP; o += 8) {
-    const int i = i0 + o;
-    if (i >= col0 + nrows) break;
-    float acc = 0.f;
-    for (int t = 0; t < ks; ++t) acc = fmaf(__ldg(wh + t), tile[cx * span + o + t], acc);
-    merged[(size_t)(i - shift) * inner + c0 + cx] += acc;
-  }
+void tm_resconv_launch(dim3 grid, size_t smem, cudaStream_t st, const float* vt, const float* w, float* merged, int n_cols, int inner,
+                       int d, int ks, int col0, int nrows, int shift, long long m_rows) {
+  if (ks == 33) tm_resconv_kernel<33><<<grid, 256, smem, st>>>(vt, w, merged, n_cols, inner, d, ks, col0, nrows, shift, m_rows);
+  else tm_resconv_kernel<0><<<grid, 256, smem, st>>>(vt, w, merged, n_cols, inner, d, ks, col0, nrows, shift, m_rows);
 }
 
 // ------------------------------------------------------------------------------------------
 // PPEG (transMIL.py:38-45): out = feat + conv7(feat) + conv5(feat) + conv3(feat) on the [gh, gw] token grid,
 // channels last.  The three depth-wise kernels and the identity are summed into one 7x7 stencil per channel
-// (exact up to fp32 summation order).  CTA = 32 channels x (8 rows x 16 columns); a thread owns one channel and a run
-// of 16 outputs along x, so every loaded input feeds up to 7 FMAs from registers (9.6 loads per output, not 49) and
-// a warp's loads are 128-byte lines (32 consecutive channels of one token).
+// (exact up to fp32 summation order).  CTA = 32 channels x (8 rows x 16 columns): the (8 + 6) x (16 + 6) input halo tile
+// and the 49 combined taps of the 32 channels are staged in shared memory once (every warp load is one 128-byte line:
+// 32 consecutive channels of a token; 38 independent loads per thread in flight instead of 22 per stencil row behind a
+// dependent FMA block -- the direct-from-global version ran at a tenth of the HBM roofline), then a thread owns one
+// channel and a run of 16 outputs along x, every input feeding up to 7 FMAs from registers.
 constexpr int PPEG_TX = 16, PPEG_TY = 8;
 __global__ void __launch_bounds__(256) tm_ppeg_kernel(const float* __restrict__ x, int gh, int gw, int C, const float* __restrict__ w7,
                                                       const float* __restrict__ b7, const float* __restrict__ w5,
                                                       const float* __restrict__ b5, const float* __restrict__ w3,
                                                       const float* __restrict__ b3, float* __restrict__ out, int cblocks,
                                                       int y_first, int y_end) {      // grid rows [y_first, y_end) are produced
+  __shared__ float in_s[PPEG_TY + 6][PPEG_TX + 6][32];
+  __shared__ float w_s[49][32];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = (blockIdx.z % cblocks) * 32 + cx, bz = blockIdx.z / cblocks;
+  const int c0 = (blockIdx.z % cblocks) * 32, bz = blockIdx.z / cblocks;
+  const int c = c0 + cx;
+  const bool c_ok = c < C;
   const size_t tok = (size_t)gh * gw + 1;
   const float* xb = x + (size_t)bz * tok * C;
   float* ob = out + (size_t)bz * tok * C;
-  if (c >= C) return;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && ty == 0 && y_first == 0 && y_end == gh) ob[c] = xb[c];      // class token passes through
-  const int y = y_first + blockIdx.y * PPEG_TY + ty, x0 = blockIdx.x * PPEG_TX;
-  if (y >= y_end) return;
-  float wk[49];
-#pragma unroll
-  for (int dy = 0; dy < 7; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 7; ++dx) {
-      float t = w7[(size_t)c * 49 + dy * 7 + dx];
-      if (dy >= 1 && dy <= 5 && dx >= 1 && dx <= 5) t += w5[(size_t)c * 25 + (dy - 1) * 5 + (dx - 1)];
-      if (dy >= 2 && dy <= 4 && dx >= 2 && dx <= 4) t += w3[(size_t)c * 9 + (dy - 2) * 3 + (dx - 2)];
-      if (dy == 3 && dx == 3) t += 1.f;
-      wk[dy * 7 + dx] = t;
-    }
-  const float bias = b7[c] + b5[c] + b3[c];
+  if (c_ok && blockIdx.x == 0 && blockIdx.y == 0 && ty == 0 && y_first == 0 && y_end == gh) ob[c] = xb[c];      // class token passes through
+  const int y0 = y_first + blockIdx.y * PPEG_TY, x0 = blockIdx.x * PPEG_TX;
   const float* feat = xb + C;
+  constexpr int NPIX = (PPEG_TY + 6) * (PPEG_TX + 6);
+  for (int base = ty; base < NPIX; base += 80) {      // warp = one token's 32 channels; ten independent loads in flight per thread
+    float v[10];
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int pix = base + 8 * u;
+      const int py = pix / (PPEG_TX + 6), px = pix - py * (PPEG_TX + 6);
+      const int yy = y0 + py - 3, xx = x0 + px - 3;
+      v[u] = (pix < NPIX && c_ok && yy >= 0 && yy < gh && xx >= 0 && xx < gw) ? feat[((size_t)yy * gw + xx) * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int pix = base + 8 * u;
+      if (pix < NPIX) in_s[pix / (PPEG_TX + 6)][pix % (PPEG_TX + 6)][cx] = v[u];
+    }
+  }
+  {
+    float tw[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {      // taps ty, ty + 8, ..: all loads issued before the first store
+      const int k = ty + 8 * u;
+      const int dy = k / 7, dx = k - dy * 7;
+      float t = 0.f;
+      if (c_ok && k < 49) {
+        t = w7[(size_t)c * 49 + k];
+        if (dy >= 1 && dy <= 5 && dx >= 1 && dx <= 5) t += w5[(size_t)c * 25 + (dy - 1) * 5 + (dx - 1)];
+        if (dy >= 2 && dy <= 4 && dx >= 2 && dx <= 4) t += w3[(size_t)c * 9 + (dy - 2) * 3 + (dx - 2)];
+        if (k == 24) t += 1.f;
+      }
+      tw[u] = t;
+    }
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+      if (ty + 8 * u < 49) w_s[ty + 8 * u][cx] = tw[u];
+  }
+  __syncthreads();
+  const int y = y0 + ty;
+  if (!c_ok || y >= y_end) return;
+  const float bias = b7[c] + b5[c] + b3[c];
   float acc[PPEG_TX];
 #pragma unroll
   for (int o = 0; o < PPEG_TX; ++o) acc[o] = bias;
 #pragma unroll
   for (int dy = 0; dy < 7; ++dy) {
-    const int yy = y + dy - 3;
-    if (yy < 0 || yy >= gh) continue;
     float in[PPEG_TX + 6];
-    const float* rowp = feat + (size_t)yy * gw * C + c;
 #pragma unroll
-    for (int i = 0; i < PPEG_TX + 6; ++i) {
-      const int xq = x0 + i - 3;
-      in[i] = (xq >= 0 && xq < gw) ? rowp[(size_t)xq * C] : 0.f;
+    for (int i = 0; i < PPEG_TX + 6; ++i) in[i] = in_s[ty + dy][i][cx];
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const float wk = w_s[dy * 7 + dx][cx];
+#pragma unroll
+      for (int o = 0; o < PPEG_TX; ++o) acc[o] = fmaf(wk, in[o + dx], acc[o]);
     }
-#pragma unroll
-    for (int dx = 0; dx < 7; ++dx)
-#pragma unroll
-      for (int o = 0; o < PPEG_TX; ++o) acc[o] = fmaf(wk[dy * 7 + dx], in[o + dx], acc[o]);
   }
 #pragma unroll
   for (int o = 0; o < PPEG_TX; ++o)
@@ -550,7 +681,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     g.b = k; g.ldb = d; g.b_batch_stride = (int64_t)np * d; g.n = np;
     g.c = sbuf; g.ldc = np; g.c_batch_stride = (int64_t)m * np;
     TM_RUN(tm_gemm(g, st));
-    tm_softmax_long_kernel<<<(unsigned)((size_t)H * m), 1024, 0, st>>>(sbuf, np);
+    TM_RUN(tm_softmax_long_launch(sbuf, (long long)H * m, np, st));
     ++g_acmil_launches;
     acmil_gemm_desc g2 = gemm0(P);
     g2.a = vt; g2.lda = np; g2.a_batch_stride = (int64_t)d * np; g2.m = d; g2.k = np; g2.batch = H;
@@ -602,7 +733,7 @@ extern "C" int acmil_nystrom_attn_fwd(const acmil_nystrom_shape* shape, const ac
     const int ks = s.conv_kernel;
     const size_t smem = (size_t)32 * ((CONV_TP + ks - 1) | 1) * sizeof(float);
     dim3 grid((nr + CONV_TP - 1) / CONV_TP, (inner + 31) / 32, s.batch);
-    tm_resconv_kernel<<<grid, 256, smem, st>>>(vt, w->d_wconv, merged, np, inner, d, ks, r0, nr);
+    tm_resconv_launch(grid, smem, st, vt, w->d_wconv, merged, np, inner, d, ks, r0, nr, 0, np);
     ++g_acmil_launches;
     ACMIL_CHECK_CUDA(cudaGetLastError());
   }
@@ -904,7 +1035,7 @@ extern "C" int acmil_nystrom_shard_phase(const acmil_nystrom_shard* shard, const
     const int ks = s.conv_kernel;
     const size_t smem = (size_t)32 * ((CONV_TP + ks - 1) | 1) * sizeof(float);
     dim3 grid((nr + CONV_TP - 1) / CONV_TP, (inner + 31) / 32, 1);
-    tm_resconv_shard_kernel<<<grid, 256, smem, st>>>(b.d_vt_ext, w->d_wconv, merged, n_ext, inner, d, ks, s.halo + r0, nr, s.halo);
+    tm_resconv_launch(grid, smem, st, b.d_vt_ext, w->d_wconv, merged, n_ext, inner, d, ks, s.halo + r0, nr, s.halo, 0);
     ++g_acmil_launches;
     ACMIL_CHECK_CUDA(cudaGetLastError());
   }
