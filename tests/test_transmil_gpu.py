@@ -128,6 +128,32 @@ def test_gemm_fp16_split_row_ranges_batches_and_errors():
         gemm_nt(a.to(dev()), w[:96].to(dev()), b_split=img, k_split=2)
 
 
+@pytest.mark.parametrize("pair", ["0", "2"])
+def test_gemm_fp16_split_other_tilings_in_a_subprocess(pair):
+    """The tiling of the fp16-split products is chosen once per process (ACMIL_GEMM_PAIR; default 1 = 128-wide CTA pairs, what
+    every other test in this file runs): the one-CTA-per-tile kernel (0) and the 256-wide pair tiles (2) get the same shapes
+    in a fresh process each."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from acmil_b200.transmil import SplitImage, gemm_nt\n"
+        "torch.manual_seed(0)\n"
+        "for m, n, k in ((10084, 400, 200), (9728, 512, 512), (10084, 200, 96), (300, 200, 384)):\n"
+        "    a = torch.randn(m, k, device='cuda'); w = torch.randn(n, k, device='cuda') * 0.05\n"
+        "    out = gemm_nt(a, w, b_split=SplitImage(w)).double()\n"
+        "    ref = a.double() @ w.double().T\n"
+        "    err = float((out - ref).abs().max() / ref.abs().max())\n"
+        "    assert err < 1e-5, (m, n, k, err)\n"
+        "print('tilings ok')\n")
+    env = dict(os.environ, ACMIL_GEMM_PAIR=pair)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "tilings ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_modules_agree_between_the_fp16_split_and_the_tf32_split(monkeypatch):
     """The weight products of TransMIL run on the fp16-split kernel by default; ACMIL_GEMM_SPLIT=tf32 keeps every product
     on 3xTF32.  Both are fp32-faithful: the logits agree to 1e-4 relative (and each is checked against the reference's
