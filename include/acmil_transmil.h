@@ -39,7 +39,8 @@ extern "C" {
  * image of b_split_rows rows whose K equals k; `b` is ignored, B cannot be batched or k-split) and A
  * is split to fp16 hi / lo inside the kernel: 3 kind::f16 MMAs per product, half the tensor-pipe time
  * and 56 % of the shared-memory traffic of the TF32 split, fp32-level accuracy (~2^-22) for
- * |a| < 65504 (larger values saturate; |a| below 2^-14 keep an absolute 2^-25).  precise = 2 without
+ * |a| < 65504 (larger values saturate, and the saturating conversion does not carry Inf / NaN of A
+ * through as IEEE arithmetic would; |a| below 2^-14 keep an absolute 2^-25).  precise = 2 without
  * an image behaves like precise = 1.  k_split > 1 partitions K over that many CTAs per tile
  * (d_split_ws: k_split * batch * m * n floats; epilogue terms are applied after the reduction).
  * Two-level batches: with batch_inner > 0, entry z uses offsets (z % batch_inner) * X_batch_stride +
